@@ -1,0 +1,121 @@
+/*
+ * molann_b200.h -- C ABI of the B200-native molann hot path (align -> features -> MLP, fwd and d/dx).
+ *
+ * The reference (zwpku/molann) is pure Python on PyTorch and has NO FFI of its own; the boundary it
+ * fixes is its Python class API (molann/ann.py).  This header is the layer UNDER that API: each entry
+ * point replaces the ATen op sequence of one reference method and is what a binding (ctypes / cgo /
+ * JNI / the torch custom-op shim in molann_b200/csrc/torch_shim.cpp) calls.  See INTEGRATION.md.
+ *
+ *   molann_b200_align_forward / _backward        <- AlignmentLayer.forward      molann/ann.py:157-199 (+ autograd)
+ *   molann_b200_preprocess_forward / _backward   <- PreprocessingANN.forward    molann/ann.py:553-565
+ *                                                   (= FeatureLayer.forward :454-474 when n_align == 0,
+ *                                                    FeatureMap.forward :288-356 for a one-feature plan)
+ *   molann_b200_forward / _backward              <- MolANN.forward              molann/ann.py:620-624
+ *                                                   with ann_layers = create_sequential_nn(...) :37-67
+ *
+ * Conventions: plain C types; every function returns an int status (0 = MOLANN_OK), never throws;
+ * all data pointers are DEVICE pointers owned by the caller unless the name ends in `_host`; no hidden
+ * allocation (scratch comes from the caller-provided workspace); `stream` is a cudaStream_t passed as
+ * void*; calls are asynchronous on that stream and re-entrant from any host thread.
+ * Layouts: x [L, n_inp, 3] fp32 contiguous; features [L, d_feat]; y [L, dims[n_layers]];
+ * W_k [dims[k+1], dims[k]] row-major (torch.nn.Linear.weight), b_k [dims[k+1]].
+ */
+#ifndef MOLANN_B200_H_
+#define MOLANN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MOLANN_B200_VERSION 100
+#define MOLANN_MAX_LAYERS 8
+
+/* feature type ids: molann/feature.py:87-97 */
+#define MOLANN_FEAT_ANGLE 0
+#define MOLANN_FEAT_BOND 1
+#define MOLANN_FEAT_DIHEDRAL 2
+#define MOLANN_FEAT_POSITION 3
+
+/* activation ids (create_sequential_nn's `activation`, molann/ann.py:37,64) */
+#define MOLANN_ACT_TANH 0
+#define MOLANN_ACT_RELU 1
+#define MOLANN_ACT_SIGMOID 2
+#define MOLANN_ACT_IDENTITY 3
+
+/* status codes */
+#define MOLANN_OK 0
+#define MOLANN_ERR_NULL 1        /* required pointer is NULL */
+#define MOLANN_ERR_PLAN 2        /* inconsistent plan (sizes, layer count, activation id ...) */
+#define MOLANN_ERR_WORKSPACE 3   /* workspace too small / NULL */
+#define MOLANN_ERR_ALIGNMENT 4   /* pointer not 4-byte aligned */
+#define MOLANN_ERR_CUDA 5        /* a CUDA runtime call failed (see molann_b200_last_cuda_error) */
+#define MOLANN_ERR_UNSUPPORTED 6 /* valid request this build cannot serve (e.g. no MLP in plan) */
+
+/* One feature-program entry = 6 int32: {type, a0, a1, a2, a3, out_col}.  Atom indices are LOCAL
+ * (positions inside the input atom group, molann/ann.py:144,261).  A reference 'position' feature over
+ * m atoms is expanded into m entries of type 3 with a0 = atom and out_col = first of its 3 columns
+ * (atom-major, xyz-minor: molann/ann.py:354).  Unused atom slots are 0. */
+#define MOLANN_ENTRY_INTS 6
+
+typedef struct MolannPlan {
+  int32_t n_inp;                 /* atoms per frame (input_atom_num, molann/ann.py:133)            */
+  int32_t n_align;               /* alignment selection size; 0 = no AlignmentLayer (nn.Identity)  */
+  const int32_t* align_idx;      /* [n_align] local indices (_local_align_atom_indices, :144)      */
+  const float* ref_x;            /* [n_align*3] centred reference (buffer ref_x, :137-141)         */
+  int32_t n_entries;             /* feature-program entries                                        */
+  const int32_t* entries;        /* [n_entries*MOLANN_ENTRY_INTS]                                  */
+  int32_t d_feat;                /* FeatureLayer.output_dimension(), :446-452                      */
+  int32_t use_angle_value;       /* FeatureLayer use_angle_value, :253                             */
+  int32_t n_layers;              /* number of Linear layers; 0 = preprocessing only               */
+  int32_t act_id;                /* MOLANN_ACT_*: applied after every layer but the last (:62-65)  */
+  int32_t dims[MOLANN_MAX_LAYERS + 1]; /* dims[0] == d_feat                                        */
+  const float* W[MOLANN_MAX_LAYERS];
+  const float* b[MOLANN_MAX_LAYERS];
+} MolannPlan;
+
+int molann_b200_version(void);
+const char* molann_b200_strerror(int status);
+/* last cudaError_t seen by this library on the calling thread's most recent failing call (0 if none) */
+int molann_b200_last_cuda_error(void);
+const char* molann_b200_cuda_error_string(int cuda_error);
+/* number of kernels this library has launched since load (all threads) -- bench.py's gpu_launches */
+int64_t molann_b200_launch_count(void);
+
+/* Host-side consistency check of the scalar fields (device arrays are not dereferenced). */
+int molann_b200_plan_validate(const MolannPlan* plan);
+
+/* Scratch bytes needed by molann_b200_forward (want_backward == 0) or _backward (!= 0) for L frames.
+ * May be 0 (the fused small-system kernels need no scratch). */
+size_t molann_b200_workspace_bytes(const MolannPlan* plan, int64_t L, int want_backward);
+
+/* y[L, dims[n_layers]] = MLP(features(align(x))) */
+int molann_b200_forward(const MolannPlan* plan, const float* x, int64_t L, float* y,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* gx[L, n_inp, 3] = d<gy, y>/dx (overwritten, dense).  gW / gb: NULL, or arrays of n_layers device
+ * pointers into which d<gy,y>/dW_k, /db_k are ACCUMULATED (+=; caller zeroes them). */
+int molann_b200_backward(const MolannPlan* plan, const float* x, const float* gy, int64_t L, float* gx,
+                         float* const* gW, float* const* gb,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* feat[L, d_feat] = features(align(x)); the MLP fields of the plan are ignored */
+int molann_b200_preprocess_forward(const MolannPlan* plan, const float* x, int64_t L, float* feat, void* stream);
+int molann_b200_preprocess_backward(const MolannPlan* plan, const float* x, const float* gfeat, int64_t L,
+                                    float* gx, void* stream);
+
+/* out[L, n_inp, 3] = (x - c(x)) R(x); only n_inp, n_align, align_idx, ref_x of the plan are used */
+int molann_b200_align_forward(const MolannPlan* plan, const float* x, int64_t L, float* out, void* stream);
+int molann_b200_align_backward(const MolannPlan* plan, const float* x, const float* gout, int64_t L,
+                               float* gx, void* stream);
+
+/* Tuning / introspection: which kernel family the dispatcher picks for this plan.
+ * 0 = general (warp-per-frame geometry + layered GEMMs), 1 = fused small-system kernel. */
+int molann_b200_path_for(const MolannPlan* plan, int want_backward);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOLANN_B200_H_ */

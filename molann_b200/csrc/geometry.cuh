@@ -1,0 +1,415 @@
+// geometry.cuh -- per-frame geometry of the molann hot path as device functions.
+//
+// One frame is handled by a *group* of G lanes (G = 1: thread-per-frame on an smem-staged tile,
+// G = 32: warp-per-frame straight from global memory).  All loops are lane-strided and all
+// reductions are xor-butterflies of width G, so the same code serves both mappings.
+//
+// Math (reference molann/ann.py):
+//   alignment  :179-197  c = mean(x[A]);  H = sum_k (x[A_k]-c)^T Y_k;  R = argmax_R tr(R^T H), det R = +1
+//              solved as the dominant eigenvector of Horn's 4x4 quaternion matrix (cyclic Jacobi in
+//              registers) -- identical to U diag(1,1,sign det(U V^T)) V^T of the reference's SVD route.
+//   features   :323-354  angle / bond / dihedral / position.  Internal coordinates are rigid-motion
+//              invariant, so they are evaluated on the RAW coordinates; only position features go
+//              through (c, R).
+//   backward   autograd of the above in closed form (no SVD derivative):  with G_j = dL/dz_j,
+//              M = sum_j (x_j-c)^T G_j, P = R^T H, solve (tr(P) I - P) w = vee(R^T M - M^T R),
+//              dL/dH = R [w]x,  gx_j = G_j R^T,  gx_{A_k} += Y_k (dL/dH)^T - (1/n_a) sum_j G_j R^T.
+#pragma once
+#include <stdint.h>
+#ifdef MOLANN_HOST_EMULATION
+// tests/host_emulation.cpp compiles these device functions for the CPU (G = 1 only) so the closed-form
+// math can be checked against the oracle without a GPU.  Never used by the product.
+#include <cmath>
+#define __device__
+#define __forceinline__ inline
+#define __restrict__
+inline float __shfl_xor_sync(unsigned, float v, int) { return v; }
+inline bool __all_sync(unsigned, bool p) { return p; }
+inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
+inline float __ldg(const float* p) { return *p; }
+#else
+#include <cuda_runtime.h>
+#endif
+
+namespace molann {
+
+enum { FEAT_ANGLE = 0, FEAT_BOND = 1, FEAT_DIHEDRAL = 2, FEAT_POSITION = 3 };
+enum { ACT_TANH = 0, ACT_RELU = 1, ACT_SIGMOID = 2, ACT_IDENTITY = 3 };
+constexpr int ENTRY_INTS = 6;
+
+template <int G>
+__device__ __forceinline__ float gsum(float v) {
+#pragma unroll
+  for (int o = G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// 4x4 symmetric eigenproblem: cyclic Jacobi, everything in registers (indices are compile-time).
+// ------------------------------------------------------------------------------------------------
+template <int I, int J>
+__device__ __forceinline__ float& sym(float (&a)[4][4]) {
+  return (I < J) ? a[I][J] : a[J][I];
+}
+
+template <int P, int Q, int R1, int R2>
+__device__ __forceinline__ void jacobi_rot(float (&a)[4][4], float (&v)[4][4]) {
+  const float apq = a[P][Q];
+  if (apq != 0.0f) {
+    const float theta = 0.5f * (a[Q][Q] - a[P][P]) / apq;
+    float t = 1.0f / (fabsf(theta) + sqrtf(fmaf(theta, theta, 1.0f)));
+    t = copysignf(t, theta);
+    const float c = rsqrtf(fmaf(t, t, 1.0f));
+    const float s = t * c;
+    const float tau = s / (1.0f + c);
+    a[P][P] = fmaf(-t, apq, a[P][P]);
+    a[Q][Q] = fmaf(t, apq, a[Q][Q]);
+    a[P][Q] = 0.0f;
+    {
+      float& x1 = sym<R1, P>(a);
+      float& y1 = sym<R1, Q>(a);
+      const float g = x1, h = y1;
+      x1 = g - s * fmaf(tau, g, h);
+      y1 = h + s * fmaf(-tau, h, g);
+      float& x2 = sym<R2, P>(a);
+      float& y2 = sym<R2, Q>(a);
+      const float g2 = x2, h2 = y2;
+      x2 = g2 - s * fmaf(tau, g2, h2);
+      y2 = h2 + s * fmaf(-tau, h2, g2);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const float g = v[r][P], h = v[r][Q];
+      v[r][P] = g - s * fmaf(tau, g, h);
+      v[r][Q] = h + s * fmaf(-tau, h, g);
+    }
+  }
+}
+
+// Dominant (largest-eigenvalue) unit eigenvector of the symmetric matrix whose upper triangle is `a`.
+// Must be called by all 32 lanes of a warp (uses a warp vote for a uniform exit).
+__device__ __forceinline__ void dominant_eigvec4(float (&a)[4][4], float (&q)[4]) {
+  float v[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[i][j] = (i == j) ? 1.0f : 0.0f;
+#pragma unroll 1
+  for (int sweep = 0; sweep < 10; ++sweep) {
+    const float off = a[0][1] * a[0][1] + a[0][2] * a[0][2] + a[0][3] * a[0][3] + a[1][2] * a[1][2] +
+                      a[1][3] * a[1][3] + a[2][3] * a[2][3];
+    const float dg = a[0][0] * a[0][0] + a[1][1] * a[1][1] + a[2][2] * a[2][2] + a[3][3] * a[3][3];
+    const bool done = !(off > 4e-14f * dg);
+    if (__all_sync(0xffffffffu, done)) break;
+    jacobi_rot<0, 1, 2, 3>(a, v);
+    jacobi_rot<0, 2, 1, 3>(a, v);
+    jacobi_rot<0, 3, 1, 2>(a, v);
+    jacobi_rot<1, 2, 0, 3>(a, v);
+    jacobi_rot<1, 3, 0, 2>(a, v);
+    jacobi_rot<2, 3, 0, 1>(a, v);
+  }
+  int best = 0;
+  float lam = a[0][0];
+  if (a[1][1] > lam) { lam = a[1][1]; best = 1; }
+  if (a[2][2] > lam) { lam = a[2][2]; best = 2; }
+  if (a[3][3] > lam) { lam = a[3][3]; best = 3; }
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+    q[r] = (best == 0) ? v[r][0] : (best == 1) ? v[r][1] : (best == 2) ? v[r][2] : v[r][3];
+  const float inv = rsqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+#pragma unroll
+  for (int r = 0; r < 4; ++r) q[r] *= inv;
+}
+
+struct Rigid {
+  float c[3];   // centroid of the alignment selection
+  float R[9];   // row-major rotation, z = (x - c) R
+  float H[9];   // row-major covariance  sum_k (x_k - c)^T Y_k
+};
+
+// Optimal superposition of frame `xf` ([n,3]) onto the centred reference.  All lanes of the group
+// return the same result.  aidx / refx may live in shared or global memory.
+template <int G>
+__device__ __forceinline__ void kabsch(const float* __restrict__ xf, const int* __restrict__ aidx,
+                                       const float* __restrict__ refx, int n_align, int lane, Rigid& rg) {
+  float sx = 0.f, sy = 0.f, sz = 0.f;
+  for (int k = lane; k < n_align; k += G) {
+    const float* p = xf + 3 * aidx[k];
+    sx += p[0]; sy += p[1]; sz += p[2];
+  }
+  const float inv_n = 1.0f / (float)n_align;
+  rg.c[0] = gsum<G>(sx) * inv_n;
+  rg.c[1] = gsum<G>(sy) * inv_n;
+  rg.c[2] = gsum<G>(sz) * inv_n;
+  float h[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) h[i] = 0.f;
+  for (int k = lane; k < n_align; k += G) {
+    const float* p = xf + 3 * aidx[k];
+    const float px = p[0] - rg.c[0], py = p[1] - rg.c[1], pz = p[2] - rg.c[2];
+    const float y0 = refx[3 * k], y1 = refx[3 * k + 1], y2 = refx[3 * k + 2];
+    h[0] = fmaf(px, y0, h[0]); h[1] = fmaf(px, y1, h[1]); h[2] = fmaf(px, y2, h[2]);
+    h[3] = fmaf(py, y0, h[3]); h[4] = fmaf(py, y1, h[4]); h[5] = fmaf(py, y2, h[5]);
+    h[6] = fmaf(pz, y0, h[6]); h[7] = fmaf(pz, y1, h[7]); h[8] = fmaf(pz, y2, h[8]);
+  }
+#pragma unroll
+  for (int i = 0; i < 9; ++i) rg.H[i] = gsum<G>(h[i]);
+  const float Sxx = rg.H[0], Sxy = rg.H[1], Sxz = rg.H[2];
+  const float Syx = rg.H[3], Syy = rg.H[4], Syz = rg.H[5];
+  const float Szx = rg.H[6], Szy = rg.H[7], Szz = rg.H[8];
+  float a[4][4];
+  a[0][0] = Sxx + Syy + Szz; a[0][1] = Syz - Szy; a[0][2] = Szx - Sxz; a[0][3] = Sxy - Syx;
+  a[1][1] = Sxx - Syy - Szz; a[1][2] = Sxy + Syx; a[1][3] = Szx + Sxz;
+  a[2][2] = -Sxx + Syy - Szz; a[2][3] = Syz + Szy;
+  a[3][3] = -Sxx - Syy + Szz;
+  a[1][0] = a[2][0] = a[2][1] = a[3][0] = a[3][1] = a[3][2] = 0.f;   // lower triangle unused
+  float q[4];
+  dominant_eigvec4(a, q);
+  const float qa = q[0], qb = q[1], qc = q[2], qd = q[3];
+  rg.R[0] = qa * qa + qb * qb - qc * qc - qd * qd;
+  rg.R[1] = 2.f * (qb * qc + qa * qd);
+  rg.R[2] = 2.f * (qb * qd - qa * qc);
+  rg.R[3] = 2.f * (qb * qc - qa * qd);
+  rg.R[4] = qa * qa - qb * qb + qc * qc - qd * qd;
+  rg.R[5] = 2.f * (qc * qd + qa * qb);
+  rg.R[6] = 2.f * (qb * qd + qa * qc);
+  rg.R[7] = 2.f * (qc * qd - qa * qb);
+  rg.R[8] = qa * qa - qb * qb - qc * qc + qd * qd;
+}
+
+// z = (p - c) R
+__device__ __forceinline__ void rigid_apply(const Rigid& rg, float px, float py, float pz, float& zx,
+                                            float& zy, float& zz) {
+  const float dx = px - rg.c[0], dy = py - rg.c[1], dz = pz - rg.c[2];
+  zx = fmaf(dx, rg.R[0], fmaf(dy, rg.R[3], dz * rg.R[6]));
+  zy = fmaf(dx, rg.R[1], fmaf(dy, rg.R[4], dz * rg.R[7]));
+  zz = fmaf(dx, rg.R[2], fmaf(dy, rg.R[5], dz * rg.R[8]));
+}
+
+// t = g R^T
+__device__ __forceinline__ void rot_transpose_apply(const Rigid& rg, float gx, float gy, float gz, float& tx,
+                                                    float& ty, float& tz) {
+  tx = fmaf(gx, rg.R[0], fmaf(gy, rg.R[1], gz * rg.R[2]));
+  ty = fmaf(gx, rg.R[3], fmaf(gy, rg.R[4], gz * rg.R[5]));
+  tz = fmaf(gx, rg.R[6], fmaf(gy, rg.R[7], gz * rg.R[8]));
+}
+
+struct Entry {
+  int type, a0, a1, a2, a3, off;
+};
+__device__ __forceinline__ Entry load_entry(const int* __restrict__ e) {
+  Entry r;
+  r.type = e[0]; r.a0 = e[1]; r.a1 = e[2]; r.a2 = e[3]; r.a3 = e[4]; r.off = e[5];
+  return r;
+}
+
+struct V3 {
+  float x, y, z;
+};
+__device__ __forceinline__ V3 ld3(const float* __restrict__ xf, int a) {
+  const float* p = xf + 3 * a;
+  V3 v; v.x = p[0]; v.y = p[1]; v.z = p[2];
+  return v;
+}
+__device__ __forceinline__ V3 sub(V3 a, V3 b) { V3 r; r.x = a.x - b.x; r.y = a.y - b.y; r.z = a.z - b.z; return r; }
+__device__ __forceinline__ V3 add(V3 a, V3 b) { V3 r; r.x = a.x + b.x; r.y = a.y + b.y; r.z = a.z + b.z; return r; }
+__device__ __forceinline__ V3 scale(V3 a, float s) { V3 r; r.x = a.x * s; r.y = a.y * s; r.z = a.z * s; return r; }
+__device__ __forceinline__ float dot(V3 a, V3 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)); }
+__device__ __forceinline__ V3 cross(V3 a, V3 b) {
+  V3 r;
+  r.x = a.y * b.z - a.z * b.y;
+  r.y = a.z * b.x - a.x * b.z;
+  r.z = a.x * b.y - a.y * b.x;
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Feature forward for one program entry.  `out(col, value)` stores one feature column.
+// ------------------------------------------------------------------------------------------------
+template <class Out>
+__device__ __forceinline__ void feature_forward(const Entry& e, const float* __restrict__ xf, bool aligned,
+                                                const Rigid& rg, int use_angle, Out& out) {
+  if (e.type == FEAT_POSITION) {
+    const V3 p = ld3(xf, e.a0);
+    float zx = p.x, zy = p.y, zz = p.z;
+    if (aligned) rigid_apply(rg, p.x, p.y, p.z, zx, zy, zz);
+    out(e.off, zx); out(e.off + 1, zy); out(e.off + 2, zz);
+  } else if (e.type == FEAT_DIHEDRAL) {        // reference ann.py:338-351
+    const V3 x0 = ld3(xf, e.a0), x1 = ld3(xf, e.a1), x2 = ld3(xf, e.a2), x3 = ld3(xf, e.a3);
+    const V3 r12 = sub(x1, x0), r23 = sub(x2, x1), r34 = sub(x3, x2);
+    const V3 n1 = cross(r12, r23), n2 = cross(r23, r34);
+    const float C = dot(n1, n2);
+    const float S = dot(n1, r34) * sqrtf(dot(r23, r23));
+    if (use_angle) {
+      out(e.off, atan2f(S, C));
+    } else {
+      const float rho = sqrtf(fmaf(C, C, S * S));
+      out(e.off, C / rho); out(e.off + 1, S / rho);
+    }
+  } else if (e.type == FEAT_BOND) {            // ann.py:334-336
+    const V3 r = sub(ld3(xf, e.a1), ld3(xf, e.a0));
+    out(e.off, sqrtf(dot(r, r)));
+  } else {                                     // angle, ann.py:323-332
+    const V3 xv = ld3(xf, e.a1);
+    const V3 u = sub(ld3(xf, e.a0), xv), w = sub(ld3(xf, e.a2), xv);
+    const float cs = dot(u, w) / (sqrtf(dot(u, u)) * sqrtf(dot(w, w)));
+    out(e.off, use_angle ? acosf(cs) : cs);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Feature backward for one entry.  `gin(col)` reads the cotangent of a feature column,
+// `acc(atom, V3)` accumulates into the frame's coordinate gradient.  For aligned position entries the
+// 3x3 moment M = (x-c)^T G and sg = sum G R^T needed by the alignment backward are accumulated too.
+// ------------------------------------------------------------------------------------------------
+template <class GIn, class Acc>
+__device__ __forceinline__ void feature_backward(const Entry& e, const float* __restrict__ xf, bool aligned,
+                                                 const Rigid& rg, int use_angle, GIn& gin, Acc& acc,
+                                                 float (&M)[9], float (&sg)[3]) {
+  if (e.type == FEAT_POSITION) {
+    const float g0 = gin(e.off), g1 = gin(e.off + 1), g2 = gin(e.off + 2);
+    if (aligned) {
+      const V3 p = ld3(xf, e.a0);
+      const float dx = p.x - rg.c[0], dy = p.y - rg.c[1], dz = p.z - rg.c[2];
+      M[0] = fmaf(dx, g0, M[0]); M[1] = fmaf(dx, g1, M[1]); M[2] = fmaf(dx, g2, M[2]);
+      M[3] = fmaf(dy, g0, M[3]); M[4] = fmaf(dy, g1, M[4]); M[5] = fmaf(dy, g2, M[5]);
+      M[6] = fmaf(dz, g0, M[6]); M[7] = fmaf(dz, g1, M[7]); M[8] = fmaf(dz, g2, M[8]);
+      V3 t;
+      rot_transpose_apply(rg, g0, g1, g2, t.x, t.y, t.z);
+      sg[0] += t.x; sg[1] += t.y; sg[2] += t.z;
+      acc(e.a0, t);
+    } else {
+      V3 t; t.x = g0; t.y = g1; t.z = g2;
+      acc(e.a0, t);
+    }
+  } else if (e.type == FEAT_DIHEDRAL) {
+    const V3 x0 = ld3(xf, e.a0), x1 = ld3(xf, e.a1), x2 = ld3(xf, e.a2), x3 = ld3(xf, e.a3);
+    const V3 r12 = sub(x1, x0), r23 = sub(x2, x1), r34 = sub(x3, x2);
+    const V3 n1 = cross(r12, r23), n2 = cross(r23, r34);
+    const float l23 = sqrtf(dot(r23, r23));
+    const float d1 = dot(n1, r34);
+    const float C = dot(n1, n2);
+    const float S = d1 * l23;
+    const float rho2 = fmaf(C, C, S * S);
+    float gC, gS;
+    if (use_angle) {
+      const float g = gin(e.off);
+      gC = -g * S / rho2;
+      gS = g * C / rho2;
+    } else {
+      const float gc = gin(e.off), gs = gin(e.off + 1);
+      const float rho3 = rho2 * sqrtf(rho2);
+      const float k = (gc * S - gs * C) / rho3;
+      gC = S * k;
+      gS = -C * k;
+    }
+    // C = n1.n2 ; S = (n1.r34) * |r23|
+    V3 gn1 = add(scale(n2, gC), scale(r34, gS * l23));
+    V3 gn2 = scale(n1, gC);
+    V3 gr34 = scale(n1, gS * l23);
+    V3 gr23 = scale(r23, gS * d1 / l23);
+    // n1 = r12 x r23 ; n2 = r23 x r34     (c = a x b: g_a = b x g_c, g_b = g_c x a)
+    V3 gr12 = cross(r23, gn1);
+    gr23 = add(gr23, cross(gn1, r12));
+    gr23 = add(gr23, cross(r34, gn2));
+    gr34 = add(gr34, cross(gn2, r23));
+    acc(e.a0, scale(gr12, -1.f));
+    acc(e.a1, sub(gr12, gr23));
+    acc(e.a2, sub(gr23, gr34));
+    acc(e.a3, gr34);
+  } else if (e.type == FEAT_BOND) {
+    const V3 r = sub(ld3(xf, e.a1), ld3(xf, e.a0));
+    const float g = gin(e.off) / sqrtf(dot(r, r));
+    acc(e.a1, scale(r, g));
+    acc(e.a0, scale(r, -g));
+  } else {  // angle
+    const V3 xv = ld3(xf, e.a1);
+    const V3 u = sub(ld3(xf, e.a0), xv), w = sub(ld3(xf, e.a2), xv);
+    const float lu = sqrtf(dot(u, u)), lw = sqrtf(dot(w, w));
+    const float inv = 1.0f / (lu * lw);
+    const float cs = dot(u, w) * inv;
+    float g = gin(e.off);
+    if (use_angle) g = -g / sqrtf(1.0f - cs * cs);
+    const V3 gu = scale(sub(scale(w, inv), scale(u, cs / (lu * lu))), g);
+    const V3 gw = scale(sub(scale(u, inv), scale(w, cs / (lw * lw))), g);
+    acc(e.a0, gu);
+    acc(e.a2, gw);
+    acc(e.a1, scale(add(gu, gw), -1.f));
+  }
+}
+
+// dL/dH (row-major 3x3) from the reduced moment M and the frame's rigid transform.
+__device__ __forceinline__ void align_backward_dH(const Rigid& rg, const float (&M)[9], float (&dH)[9]) {
+  const float* R = rg.R;
+  const float* H = rg.H;
+  // P = R^T H (symmetric in exact arithmetic; symmetrised here)
+  float P[9];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) P[3 * i + j] = R[i] * H[j] + R[3 + i] * H[3 + j] + R[6 + i] * H[6 + j];
+  const float p01 = 0.5f * (P[1] + P[3]), p02 = 0.5f * (P[2] + P[6]), p12 = 0.5f * (P[5] + P[7]);
+  const float tr = P[0] + P[4] + P[8];
+  // B = tr(P) I - P
+  const float b00 = tr - P[0], b11 = tr - P[4], b22 = tr - P[8];
+  const float b01 = -p01, b02 = -p02, b12 = -p12;
+  // A = R^T M - M^T R  (antisymmetric); ax = (A21, A02, A10)
+  float RtM[9];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) RtM[3 * i + j] = R[i] * M[j] + R[3 + i] * M[3 + j] + R[6 + i] * M[6 + j];
+  const float ax0 = RtM[7] - RtM[5];
+  const float ax1 = RtM[2] - RtM[6];
+  const float ax2 = RtM[3] - RtM[1];
+  // solve B w = ax by the adjugate (B symmetric)
+  const float c00 = b11 * b22 - b12 * b12;
+  const float c01 = b02 * b12 - b01 * b22;
+  const float c02 = b01 * b12 - b02 * b11;
+  const float c11 = b00 * b22 - b02 * b02;
+  const float c12 = b01 * b02 - b00 * b12;
+  const float c22 = b00 * b11 - b01 * b01;
+  const float det = b00 * c00 + b01 * c01 + b02 * c02;
+  const float idet = 1.0f / det;
+  const float w0 = (c00 * ax0 + c01 * ax1 + c02 * ax2) * idet;
+  const float w1 = (c01 * ax0 + c11 * ax1 + c12 * ax2) * idet;
+  const float w2 = (c02 * ax0 + c12 * ax1 + c22 * ax2) * idet;
+  // dH = R [w]x,  [w]x = [[0,-w2,w1],[w2,0,-w0],[-w1,w0,0]]
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const float r0 = R[3 * i], r1 = R[3 * i + 1], r2 = R[3 * i + 2];
+    dH[3 * i + 0] = r1 * w2 - r2 * w1;
+    dH[3 * i + 1] = r2 * w0 - r0 * w2;
+    dH[3 * i + 2] = r0 * w1 - r1 * w0;
+  }
+}
+
+// gradient contribution of alignment atom k (reference row y): y dH^T - sg / n_a
+__device__ __forceinline__ V3 align_atom_grad(const float (&dH)[9], const float (&sg)[3], float inv_na, float y0,
+                                              float y1, float y2) {
+  V3 t;
+  t.x = fmaf(y0, dH[0], fmaf(y1, dH[1], y2 * dH[2])) - sg[0] * inv_na;
+  t.y = fmaf(y0, dH[3], fmaf(y1, dH[4], y2 * dH[5])) - sg[1] * inv_na;
+  t.z = fmaf(y0, dH[6], fmaf(y1, dH[7], y2 * dH[8])) - sg[2] * inv_na;
+  return t;
+}
+
+__device__ __forceinline__ float act_forward(float v, int act) {
+  switch (act) {
+    case ACT_TANH: return tanhf(v);
+    case ACT_RELU: return fmaxf(v, 0.f);
+    case ACT_SIGMOID: return 1.0f / (1.0f + expf(-v));
+    default: return v;
+  }
+}
+// derivative expressed through the activation OUTPUT h
+__device__ __forceinline__ float act_grad_from_output(float h, int act) {
+  switch (act) {
+    case ACT_TANH: return fmaf(-h, h, 1.0f);
+    case ACT_RELU: return h > 0.f ? 1.0f : 0.f;
+    case ACT_SIGMOID: return h * (1.0f - h);
+    default: return 1.0f;
+  }
+}
+
+}  // namespace molann

@@ -1,0 +1,570 @@
+// molann_b200.cu -- C ABI (include/molann_b200.h) and kernel dispatch for the molann hot path.
+//
+// Two kernel families:
+//   * fused small-system kernels (fused_small.cuh): one kernel, frame tile + MLP resident in smem;
+//   * general path (general.cuh): warp-per-frame geometry + layered FFMA GEMMs over a caller
+//     workspace, processed in frame chunks so scratch stays O(chunk).
+// No CPU fallback exists: without a CUDA device every entry point returns MOLANN_ERR_CUDA.
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "common.cuh"
+#include "fused_small.cuh"
+#include "general.cuh"
+
+using namespace molann;
+
+namespace {
+
+std::atomic<long long> g_launches{0};
+thread_local int t_last_cuda_error = 0;
+
+struct DeviceInfo {
+  int sm_count = 0;
+  int max_smem_optin = 0;
+  bool ok = false;
+};
+
+DeviceInfo device_info() {
+  // re-queried per call: cheap, and correct when the caller switches devices between calls
+  DeviceInfo d;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return d;
+  if (cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return d;
+  if (cudaDeviceGetAttribute(&d.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return d;
+  d.ok = true;
+  return d;
+}
+
+int env_int(const char* name, int dflt) {
+  const char* v = std::getenv(name);
+  return (v && *v) ? std::atoi(v) : dflt;
+}
+
+int check_cuda(cudaError_t e) {
+  if (e == cudaSuccess) return MOLANN_OK;
+  t_last_cuda_error = (int)e;
+  return MOLANN_ERR_CUDA;
+}
+
+int post_launch() {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return check_cuda(cudaGetLastError());
+}
+
+DevPlan to_dev(const MolannPlan* p) {
+  DevPlan d;
+  std::memset(&d, 0, sizeof(d));
+  d.n_inp = p->n_inp; d.n_align = p->n_align; d.n_entries = p->n_entries; d.d_feat = p->d_feat;
+  d.use_angle = p->use_angle_value; d.n_layers = p->n_layers; d.act = p->act_id;
+  d.align_idx = p->align_idx; d.ref_x = p->ref_x; d.entries = p->entries;
+  for (int k = 0; k <= MOLANN_MAX_LAYERS; ++k) d.dims[k] = p->dims[k];
+  for (int k = 0; k < MOLANN_MAX_LAYERS; ++k) { d.W[k] = p->W[k]; d.b[k] = p->b[k]; }
+  return d;
+}
+
+int validate_geometry(const MolannPlan* p) {
+  if (!p) return MOLANN_ERR_NULL;
+  if (p->n_inp <= 0 || p->n_align < 0 || p->n_align > p->n_inp * 64) return MOLANN_ERR_PLAN;
+  if (p->n_align > 0 && (!p->align_idx || !p->ref_x)) return MOLANN_ERR_NULL;
+  return MOLANN_OK;
+}
+
+int validate_features(const MolannPlan* p) {
+  int s = validate_geometry(p);
+  if (s) return s;
+  if (p->n_entries <= 0 || p->d_feat <= 0) return MOLANN_ERR_PLAN;
+  if (!p->entries) return MOLANN_ERR_NULL;
+  if (p->use_angle_value != 0 && p->use_angle_value != 1) return MOLANN_ERR_PLAN;
+  return MOLANN_OK;
+}
+
+int validate_full(const MolannPlan* p) {
+  int s = validate_features(p);
+  if (s) return s;
+  if (p->n_layers < 0 || p->n_layers > MOLANN_MAX_LAYERS) return MOLANN_ERR_PLAN;
+  if (p->n_layers > 0) {
+    if (p->act_id < 0 || p->act_id > MOLANN_ACT_IDENTITY) return MOLANN_ERR_PLAN;
+    if (p->dims[0] != p->d_feat) return MOLANN_ERR_PLAN;
+    for (int k = 0; k <= p->n_layers; ++k)
+      if (p->dims[k] <= 0) return MOLANN_ERR_PLAN;
+    for (int k = 0; k < p->n_layers; ++k)
+      if (!p->W[k] || !p->b[k]) return MOLANN_ERR_NULL;
+  }
+  return MOLANN_OK;
+}
+
+bool misaligned4(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 3u) != 0; }
+
+// ---------------------------------------------------------------------------------------------
+// fused small-system path
+// ---------------------------------------------------------------------------------------------
+int pick_tm(int F, int NT, int n_out) {
+  const int nog = (n_out + 7) / 8;
+  const int cands[4] = {8, 4, 2, 1};
+  for (int c = 0; c < 4; ++c)
+    if ((F / cands[c]) * nog >= NT) return cands[c];
+  return 1;
+}
+
+struct Carver {
+  int off = 0;
+  int take(int bytes, int align = 16) {
+    off = (off + align - 1) / align * align;
+    const int r = off;
+    off += bytes;
+    return r;
+  }
+};
+
+SmallLayout small_layout(const MolannPlan* p, int F, int NT, bool backward, bool alias) {
+  SmallLayout lay;
+  std::memset(&lay, 0, sizeof(lay));
+  const int n3 = 3 * p->n_inp;
+  const int nl = p->n_layers;
+  Carver c;
+  lay.mbar_off = c.take(16, 16);
+  const int xs_bytes = F * n3 * 4;
+  if (!backward) {
+    int rows0 = round_up(p->d_feat, 8), rows1 = 8;
+    for (int k = 1; k < nl; ++k) {       // h_k lands in buffer k & 1
+      const int r = round_up(p->dims[k], 8);
+      if (k & 1) rows1 = r > rows1 ? r : rows1; else rows0 = r > rows0 ? r : rows0;
+    }
+    const int b1_bytes = rows1 * F * 4;
+    if (alias) {                         // activation buffer 1 overlays the coordinate tile
+      lay.alias_xs = 1;
+      lay.xs_off = c.take(xs_bytes > b1_bytes ? xs_bytes : b1_bytes, 128);
+      lay.buf_off[1] = lay.xs_off;
+    } else {
+      lay.xs_off = c.take(xs_bytes, 128);
+      lay.buf_off[1] = c.take(b1_bytes, 128);
+    }
+    lay.buf_off[0] = c.take(rows0 * F * 4, 128);
+    for (int k = 0; k < nl; ++k) {
+      lay.ldwt[k] = round_up(p->dims[k + 1], 8);
+      lay.wt_off[k] = c.take(p->dims[k] * lay.ldwt[k] * 4, 16);
+      lay.b_off[k] = c.take(lay.ldwt[k] * 4, 16);
+      lay.tm_fwd[k] = pick_tm(F, NT, p->dims[k + 1]);
+    }
+  } else {
+    lay.xs_off = c.take(xs_bytes, 128);
+    lay.gxs_off = c.take(xs_bytes, 128);
+    int rows[MOLANN_MAX_LAYERS];
+    for (int s = 0; s < MOLANN_MAX_LAYERS; ++s) rows[s] = 0;
+    rows[0] = round_up(p->d_feat, 8);
+    for (int k = 1; k < nl; ++k) {
+      const int s = act_slot(k), r = round_up(p->dims[k], 8);
+      rows[s] = r > rows[s] ? r : rows[s];
+    }
+    for (int s = 0; s < MOLANN_MAX_LAYERS; ++s)
+      if (rows[s] > 0) lay.buf_off[s] = c.take(rows[s] * F * 4, 128);
+    lay.gys_off = c.take(round_up(p->dims[nl], 8) * F * 4, 128);
+    for (int k = 0; k < nl; ++k) {
+      lay.ldw[k] = round_up(p->dims[k], 8);
+      lay.w_off[k] = c.take(round_up(p->dims[k + 1], 8) * lay.ldw[k] * 4, 16);
+      lay.tm_bwd[k] = pick_tm(F, NT, p->dims[k]);
+      if (k < nl - 1) {
+        lay.ldwt[k] = round_up(p->dims[k + 1], 8);
+        lay.wt_off[k] = c.take(p->dims[k] * lay.ldwt[k] * 4, 16);
+        lay.b_off[k] = c.take(lay.ldwt[k] * 4, 16);
+        lay.tm_fwd[k] = pick_tm(F, NT, p->dims[k + 1]);
+      }
+    }
+  }
+  lay.aidx_off = c.take((p->n_align > 0 ? p->n_align : 1) * 4, 16);
+  lay.ref_off = c.take((p->n_align > 0 ? 3 * p->n_align : 1) * 4, 16);
+  lay.ent_off = c.take(p->n_entries * ENTRY_INTS * 4, 16);
+  lay.total_bytes = round_up(c.off, 128);
+  return lay;
+}
+
+struct SmallChoice {
+  bool ok = false;
+  int F = 0, NT = 0;
+  bool alias = false;
+  SmallLayout lay;
+};
+
+// Tunables (env, read per call; defaults chosen from B200 measurements):
+//   MOLANN_B200_PATH      = 0 general | 1 fused small | -1 auto (default)
+//   MOLANN_B200_FWD_F/NT  frames per tile / threads per CTA of the fused forward kernel
+//   MOLANN_B200_BWD_F/NT  same for the fused backward kernel
+//   MOLANN_B200_FWD_ALIAS overlay activation buffer 1 on the coordinate tile (forward)
+SmallChoice choose_small(const MolannPlan* p, bool backward, const DeviceInfo& dev) {
+  SmallChoice ch;
+  if (p->n_layers < 1) return ch;
+  const int forced = env_int("MOLANN_B200_PATH", -1);
+  if (forced == 0) return ch;
+  if ((long long)p->n_entries * ENTRY_INTS * 4 > 64 * 1024) return ch;
+  int F = backward ? env_int("MOLANN_B200_BWD_F", 64) : env_int("MOLANN_B200_FWD_F", 128);
+  int NT = backward ? env_int("MOLANN_B200_BWD_NT", 128) : env_int("MOLANN_B200_FWD_NT", 128);
+  if (F != 64 && F != 128) F = backward ? 64 : 128;
+  if (NT != 128 && NT != 256) NT = 128;
+  const bool alias = !backward && env_int("MOLANN_B200_FWD_ALIAS", 1) != 0;
+  // try the preferred tile first, then the smaller one
+  const int tries[2] = {F, 64};
+  for (int t = 0; t < 2; ++t) {
+    const int Ft = tries[t];
+    if ((long long)Ft * 3 * p->n_inp * 4 > 200 * 1024) continue;
+    SmallLayout lay = small_layout(p, Ft, NT, backward, alias);
+    if (lay.total_bytes <= dev.max_smem_optin) {
+      ch.ok = true; ch.F = Ft; ch.NT = NT; ch.alias = alias; ch.lay = lay;
+      return ch;
+    }
+  }
+  return ch;
+}
+
+template <int F, int NT>
+int launch_small_forward(const DevPlan& dp, const SmallLayout& lay, const float* x, float* y, long long L,
+                         const DeviceInfo& dev, cudaStream_t st) {
+  auto kern = fused_small_forward_kernel<F, NT>;
+  int s = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.total_bytes));
+  if (s) return s;
+  int occ = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, lay.total_bytes);
+  if (occ < 1) occ = 1;
+  const long long ntiles = (L + F - 1) / F;
+  long long grid = (long long)dev.sm_count * occ;
+  if (grid > ntiles) grid = ntiles;
+  const int use_tma = ((reinterpret_cast<uintptr_t>(x) & 15u) == 0) && ((F * 3 * dp.n_inp * 4) % 16 == 0);
+  kern<<<(unsigned)grid, NT, lay.total_bytes, st>>>(dp, lay, x, y, L, use_tma);
+  return post_launch();
+}
+
+template <int F, int NT>
+int launch_small_backward(const DevPlan& dp, const SmallLayout& lay, const float* x, const float* gy, float* gx,
+                          long long L, const DeviceInfo& dev, cudaStream_t st) {
+  auto kern = fused_small_backward_kernel<F, NT>;
+  int s = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.total_bytes));
+  if (s) return s;
+  int occ = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, lay.total_bytes);
+  if (occ < 1) occ = 1;
+  const long long ntiles = (L + F - 1) / F;
+  long long grid = (long long)dev.sm_count * occ;
+  if (grid > ntiles) grid = ntiles;
+  const int use_tma = ((reinterpret_cast<uintptr_t>(x) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(gx) & 15u) == 0) &&
+                      ((F * 3 * dp.n_inp * 4) % 16 == 0);
+  kern<<<(unsigned)grid, NT, lay.total_bytes, st>>>(dp, lay, x, gy, gx, L, use_tma);
+  return post_launch();
+}
+
+#define SMALL_DISPATCH(ch, FN, ...)                                   \
+  ((ch).F == 128 ? ((ch).NT == 256 ? FN<128, 256>(__VA_ARGS__) : FN<128, 128>(__VA_ARGS__)) \
+                 : ((ch).NT == 256 ? FN<64, 256>(__VA_ARGS__) : FN<64, 128>(__VA_ARGS__)))
+
+// ---------------------------------------------------------------------------------------------
+// general path
+// ---------------------------------------------------------------------------------------------
+constexpr long long kChunkFrames = 32768;
+
+long long chunk_frames(const MolannPlan* p, long long L) {
+  long long ch = env_int("MOLANN_B200_CHUNK", (int)kChunkFrames);
+  if (ch < 256) ch = 256;
+  (void)p;
+  return L < ch ? L : ch;
+}
+
+int max_dim(const MolannPlan* p) {
+  int m = p->d_feat;
+  for (int k = 0; k <= p->n_layers; ++k) m = p->dims[k] > m ? p->dims[k] : m;
+  return m;
+}
+
+size_t align256(size_t v) { return (v + 255) / 256 * 256; }
+
+size_t general_ws_bytes(const MolannPlan* p, long long L, bool backward) {
+  const long long ch = chunk_frames(p, L);
+  size_t total = align256((size_t)ch * p->d_feat * 4);
+  if (!backward) {
+    total += 2 * align256((size_t)ch * max_dim(p) * 4);
+  } else {
+    for (int k = 1; k < p->n_layers; ++k) total += align256((size_t)ch * p->dims[k] * 4);
+    total += 2 * align256((size_t)ch * max_dim(p) * 4);
+  }
+  return total;
+}
+
+unsigned warp_grid(long long L, const DeviceInfo& dev) {
+  long long blocks = (L + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+  const long long cap = (long long)dev.sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (unsigned)blocks;
+}
+
+int launch_linear_forward(const float* in, const float* W, const float* b, float* out, long long M, int K, int N,
+                          int act, int apply_act, cudaStream_t st) {
+  dim3 grid((N + 63) / 64, (unsigned)((M + 63) / 64), 1);
+  gemm_kernel<EPI_BIAS_ACT><<<grid, 256, 0, st>>>(in, K, 1, W, 1, K, out, N, (int)M, N, K, K, b, nullptr, act,
+                                                  apply_act);
+  return post_launch();
+}
+
+// gprev[M, K] = (gz[M, N] W[N, K]) * act'(hprev[M, K])
+int launch_linear_backward_input(const float* gz, const float* W, const float* hprev, float* gprev, long long M,
+                                 int K, int N, int act, cudaStream_t st) {
+  dim3 grid((K + 63) / 64, (unsigned)((M + 63) / 64), 1);
+  gemm_kernel<EPI_DACT><<<grid, 256, 0, st>>>(gz, N, 1, W, K, 1, gprev, K, (int)M, K, N, N, nullptr, hprev, act,
+                                              hprev != nullptr);
+  return post_launch();
+}
+
+// gW[N, K] += gz[M, N]^T hin[M, K];  gb[N] += colsum(gz)
+int launch_linear_backward_params(const float* gz, const float* hin, float* gW, float* gb, long long M, int K, int N,
+                                  cudaStream_t st) {
+  const long long kchunk = 2048;
+  dim3 grid((K + 63) / 64, (N + 63) / 64, (unsigned)((M + kchunk - 1) / kchunk));
+  gemm_kernel<EPI_ATOMIC><<<grid, 256, 0, st>>>(gz, 1, N, hin, K, 1, gW, K, N, K, M, kchunk, nullptr, nullptr, 0, 0);
+  int s = post_launch();
+  if (s) return s;
+  if (gb) {
+    const int rows_per_block = 4096;
+    dim3 g2((N + 31) / 32, (unsigned)((M + rows_per_block - 1) / rows_per_block), 1);
+    colsum_atomic_kernel<<<g2, 256, 0, st>>>(gz, (int)M, N, gb, rows_per_block);
+    s = post_launch();
+  }
+  return s;
+}
+
+int general_forward(const MolannPlan* p, const float* x, long long L, float* y, void* ws, size_t ws_bytes,
+                    const DeviceInfo& dev, cudaStream_t st) {
+  if (!ws || ws_bytes < general_ws_bytes(p, L, false)) return MOLANN_ERR_WORKSPACE;
+  const DevPlan dp = to_dev(p);
+  const long long ch = chunk_frames(p, L);
+  char* base = static_cast<char*>(ws);
+  float* feat = reinterpret_cast<float*>(base);
+  base += align256((size_t)ch * p->d_feat * 4);
+  float* pp[2];
+  pp[0] = reinterpret_cast<float*>(base);
+  base += align256((size_t)ch * max_dim(p) * 4);
+  pp[1] = reinterpret_cast<float*>(base);
+  const int kout = p->dims[p->n_layers];
+  for (long long c0 = 0; c0 < L; c0 += ch) {
+    const long long Lc = (L - c0 < ch) ? (L - c0) : ch;
+    preprocess_forward_warp_kernel<<<warp_grid(Lc, dev), WARPS_PER_CTA * 32, 0, st>>>(
+        dp, x + c0 * 3 * p->n_inp, feat, Lc);
+    int s = post_launch();
+    if (s) return s;
+    const float* in = feat;
+    for (int k = 0; k < p->n_layers; ++k) {
+      const bool last = (k == p->n_layers - 1);
+      float* out = last ? (y + c0 * kout) : pp[k & 1];
+      s = launch_linear_forward(in, p->W[k], p->b[k], out, Lc, p->dims[k], p->dims[k + 1], p->act_id, !last, st);
+      if (s) return s;
+      in = out;
+    }
+  }
+  return MOLANN_OK;
+}
+
+int general_backward(const MolannPlan* p, const float* x, const float* gy, long long L, float* gx, float* const* gW,
+                     float* const* gb, void* ws, size_t ws_bytes, const DeviceInfo& dev, cudaStream_t st) {
+  if (!ws || ws_bytes < general_ws_bytes(p, L, true)) return MOLANN_ERR_WORKSPACE;
+  const DevPlan dp = to_dev(p);
+  const long long ch = chunk_frames(p, L);
+  const int nl = p->n_layers;
+  char* base = static_cast<char*>(ws);
+  float* h[MOLANN_MAX_LAYERS];       // h[0] = features, h[k] = activation after layer k
+  h[0] = reinterpret_cast<float*>(base);
+  base += align256((size_t)ch * p->d_feat * 4);
+  for (int k = 1; k < nl; ++k) {
+    h[k] = reinterpret_cast<float*>(base);
+    base += align256((size_t)ch * p->dims[k] * 4);
+  }
+  float* pp[2];
+  pp[0] = reinterpret_cast<float*>(base);
+  base += align256((size_t)ch * max_dim(p) * 4);
+  pp[1] = reinterpret_cast<float*>(base);
+  const int kout = p->dims[nl];
+  for (long long c0 = 0; c0 < L; c0 += ch) {
+    const long long Lc = (L - c0 < ch) ? (L - c0) : ch;
+    const float* xc = x + c0 * 3 * p->n_inp;
+    preprocess_forward_warp_kernel<<<warp_grid(Lc, dev), WARPS_PER_CTA * 32, 0, st>>>(dp, xc, h[0], Lc);
+    int s = post_launch();
+    if (s) return s;
+    for (int k = 0; k < nl - 1; ++k) {
+      s = launch_linear_forward(h[k], p->W[k], p->b[k], h[k + 1], Lc, p->dims[k], p->dims[k + 1], p->act_id, 1, st);
+      if (s) return s;
+    }
+    const float* gz = gy + c0 * kout;
+    for (int k = nl - 1; k >= 0; --k) {
+      if (gW && gW[k]) {
+        s = launch_linear_backward_params(gz, h[k], gW[k], gb ? gb[k] : nullptr, Lc, p->dims[k], p->dims[k + 1], st);
+        if (s) return s;
+      }
+      float* gprev = pp[k & 1];
+      s = launch_linear_backward_input(gz, p->W[k], k > 0 ? h[k] : nullptr, gprev, Lc, p->dims[k], p->dims[k + 1],
+                                       p->act_id, st);
+      if (s) return s;
+      gz = gprev;
+    }
+    preprocess_backward_warp_kernel<<<warp_grid(Lc, dev), WARPS_PER_CTA * 32, 0, st>>>(dp, xc, gz,
+                                                                                       gx + c0 * 3 * p->n_inp, Lc);
+    s = post_launch();
+    if (s) return s;
+  }
+  return MOLANN_OK;
+}
+
+}  // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+int molann_b200_version(void) { return MOLANN_B200_VERSION; }
+
+const char* molann_b200_strerror(int status) {
+  switch (status) {
+    case MOLANN_OK: return "ok";
+    case MOLANN_ERR_NULL: return "required pointer is NULL";
+    case MOLANN_ERR_PLAN: return "inconsistent plan";
+    case MOLANN_ERR_WORKSPACE: return "workspace missing or too small";
+    case MOLANN_ERR_ALIGNMENT: return "pointer is not 4-byte aligned";
+    case MOLANN_ERR_CUDA: return "CUDA runtime error (see molann_b200_last_cuda_error)";
+    case MOLANN_ERR_UNSUPPORTED: return "request not supported for this plan";
+    default: return "unknown status";
+  }
+}
+
+int molann_b200_last_cuda_error(void) { return t_last_cuda_error; }
+
+const char* molann_b200_cuda_error_string(int cuda_error) {
+  return cudaGetErrorString(static_cast<cudaError_t>(cuda_error));
+}
+
+int64_t molann_b200_launch_count(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }
+
+int molann_b200_plan_validate(const MolannPlan* plan) { return validate_full(plan); }
+
+int molann_b200_path_for(const MolannPlan* plan, int want_backward) {
+  if (validate_full(plan) != MOLANN_OK) return -1;
+  DeviceInfo dev = device_info();
+  if (!dev.ok) { dev.sm_count = 148; dev.max_smem_optin = 232448; }   // B200 figures, for offline queries
+  return choose_small(plan, want_backward != 0, dev).ok ? 1 : 0;
+}
+
+size_t molann_b200_workspace_bytes(const MolannPlan* plan, int64_t L, int want_backward) {
+  if (validate_full(plan) != MOLANN_OK || plan->n_layers < 1 || L <= 0) return 0;
+  // always sized for the general path: a backward with parameter gradients uses it even when the
+  // fused kernel serves the forward
+  return general_ws_bytes(plan, L, want_backward != 0);
+}
+
+int molann_b200_forward(const MolannPlan* plan, const float* x, int64_t L, float* y, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  int s = validate_full(plan);
+  if (s) return s;
+  if (plan->n_layers < 1) return MOLANN_ERR_UNSUPPORTED;
+  if (L < 0) return MOLANN_ERR_PLAN;
+  if (L == 0) return MOLANN_OK;
+  if (!x || !y) return MOLANN_ERR_NULL;
+  if (misaligned4(x) || misaligned4(y)) return MOLANN_ERR_ALIGNMENT;
+  const DeviceInfo dev = device_info();
+  if (!dev.ok) return MOLANN_ERR_CUDA;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const SmallChoice ch = choose_small(plan, false, dev);
+  if (ch.ok) {
+    const DevPlan dp = to_dev(plan);
+    return SMALL_DISPATCH(ch, launch_small_forward, dp, ch.lay, x, y, (long long)L, dev, st);
+  }
+  return general_forward(plan, x, L, y, workspace, workspace_bytes, dev, st);
+}
+
+int molann_b200_backward(const MolannPlan* plan, const float* x, const float* gy, int64_t L, float* gx,
+                         float* const* gW, float* const* gb, void* workspace, size_t workspace_bytes,
+                         void* stream) {
+  int s = validate_full(plan);
+  if (s) return s;
+  if (plan->n_layers < 1) return MOLANN_ERR_UNSUPPORTED;
+  if (L < 0) return MOLANN_ERR_PLAN;
+  if (L == 0) return MOLANN_OK;
+  if (!x || !gy || !gx) return MOLANN_ERR_NULL;
+  if (misaligned4(x) || misaligned4(gy) || misaligned4(gx)) return MOLANN_ERR_ALIGNMENT;
+  const DeviceInfo dev = device_info();
+  if (!dev.ok) return MOLANN_ERR_CUDA;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  bool want_params = false;
+  if (gW)
+    for (int k = 0; k < plan->n_layers; ++k) want_params = want_params || (gW[k] != nullptr);
+  if (!want_params) {
+    const SmallChoice ch = choose_small(plan, true, dev);
+    if (ch.ok) {
+      const DevPlan dp = to_dev(plan);
+      return SMALL_DISPATCH(ch, launch_small_backward, dp, ch.lay, x, gy, gx, (long long)L, dev, st);
+    }
+  }
+  return general_backward(plan, x, gy, L, gx, gW, gb, workspace, workspace_bytes, dev, st);
+}
+
+int molann_b200_preprocess_forward(const MolannPlan* plan, const float* x, int64_t L, float* feat, void* stream) {
+  int s = validate_features(plan);
+  if (s) return s;
+  if (L < 0) return MOLANN_ERR_PLAN;
+  if (L == 0) return MOLANN_OK;
+  if (!x || !feat) return MOLANN_ERR_NULL;
+  if (misaligned4(x) || misaligned4(feat)) return MOLANN_ERR_ALIGNMENT;
+  const DeviceInfo dev = device_info();
+  if (!dev.ok) return MOLANN_ERR_CUDA;
+  const DevPlan dp = to_dev(plan);
+  preprocess_forward_warp_kernel<<<warp_grid(L, dev), WARPS_PER_CTA * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      dp, x, feat, L);
+  return post_launch();
+}
+
+int molann_b200_preprocess_backward(const MolannPlan* plan, const float* x, const float* gfeat, int64_t L, float* gx,
+                                    void* stream) {
+  int s = validate_features(plan);
+  if (s) return s;
+  if (L < 0) return MOLANN_ERR_PLAN;
+  if (L == 0) return MOLANN_OK;
+  if (!x || !gfeat || !gx) return MOLANN_ERR_NULL;
+  if (misaligned4(x) || misaligned4(gfeat) || misaligned4(gx)) return MOLANN_ERR_ALIGNMENT;
+  const DeviceInfo dev = device_info();
+  if (!dev.ok) return MOLANN_ERR_CUDA;
+  const DevPlan dp = to_dev(plan);
+  preprocess_backward_warp_kernel<<<warp_grid(L, dev), WARPS_PER_CTA * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      dp, x, gfeat, gx, L);
+  return post_launch();
+}
+
+int molann_b200_align_forward(const MolannPlan* plan, const float* x, int64_t L, float* out, void* stream) {
+  int s = validate_geometry(plan);
+  if (s) return s;
+  if (plan->n_align < 1) return MOLANN_ERR_PLAN;
+  if (L < 0) return MOLANN_ERR_PLAN;
+  if (L == 0) return MOLANN_OK;
+  if (!x || !out) return MOLANN_ERR_NULL;
+  if (misaligned4(x) || misaligned4(out)) return MOLANN_ERR_ALIGNMENT;
+  const DeviceInfo dev = device_info();
+  if (!dev.ok) return MOLANN_ERR_CUDA;
+  const DevPlan dp = to_dev(plan);
+  align_forward_warp_kernel<<<warp_grid(L, dev), WARPS_PER_CTA * 32, 0, static_cast<cudaStream_t>(stream)>>>(dp, x,
+                                                                                                             out, L);
+  return post_launch();
+}
+
+int molann_b200_align_backward(const MolannPlan* plan, const float* x, const float* gout, int64_t L, float* gx,
+                               void* stream) {
+  int s = validate_geometry(plan);
+  if (s) return s;
+  if (plan->n_align < 1) return MOLANN_ERR_PLAN;
+  if (L < 0) return MOLANN_ERR_PLAN;
+  if (L == 0) return MOLANN_OK;
+  if (!x || !gout || !gx) return MOLANN_ERR_NULL;
+  if (misaligned4(x) || misaligned4(gout) || misaligned4(gx)) return MOLANN_ERR_ALIGNMENT;
+  const DeviceInfo dev = device_info();
+  if (!dev.ok) return MOLANN_ERR_CUDA;
+  const DevPlan dp = to_dev(plan);
+  align_backward_warp_kernel<<<warp_grid(L, dev), WARPS_PER_CTA * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      dp, x, gout, gx, L);
+  return post_launch();
+}
+
+}  // extern "C"

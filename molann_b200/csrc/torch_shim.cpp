@@ -1,0 +1,332 @@
+// torch_shim.cpp -- thin dispatcher-registered custom ops over the C ABI (include/molann_b200.h).
+//
+//   molann_b200::align       <- AlignmentLayer.forward      (reference molann/ann.py:157-199)
+//   molann_b200::preprocess  <- PreprocessingANN.forward    (:553-565; FeatureLayer.forward :454-474 when
+//                                                            align_idx is empty)
+//   molann_b200::molann      <- MolANN.forward              (:620-624) with a create_sequential_nn MLP
+//
+// Autograd is implemented in C++ (torch::autograd::Function) so that TorchScript archives loaded from
+// libtorch-only consumers (MD-engine plugins) still get d/dx and parameter gradients.  PyTorch is
+// plumbing here: tensors for device memory, the current stream, and the dispatcher; all arithmetic is
+// in the sm_100a kernels behind the C ABI.  There is no CPU implementation: CPU tensors raise.
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <torch/library.h>
+#include <ATen/ATen.h>
+#include <torch/csrc/autograd/custom_function.h>
+
+#include <vector>
+
+#include "../../include/molann_b200.h"
+
+namespace {
+
+using at::Tensor;
+using torch::autograd::AutogradContext;
+using torch::autograd::variable_list;
+
+void check_status(int status, const char* what) {
+  if (status == MOLANN_OK) return;
+  if (status == MOLANN_ERR_CUDA) {
+    TORCH_CHECK(false, "molann_b200: ", what, " failed: ", molann_b200_strerror(status), " (cudaError ",
+                molann_b200_last_cuda_error(), ": ", molann_b200_cuda_error_string(molann_b200_last_cuda_error()),
+                ")");
+  }
+  TORCH_CHECK(false, "molann_b200: ", what, " failed: ", molann_b200_strerror(status));
+}
+
+void check_x(const Tensor& x, const char* op) {
+  TORCH_CHECK(x.is_cuda(), "molann_b200::", op,
+              ": input must be a CUDA tensor (this build has no CPU implementation); got device ", x.device());
+  TORCH_CHECK(x.scalar_type() == at::kFloat, "molann_b200::", op, ": input must be float32, got ", x.scalar_type());
+  TORCH_CHECK(x.dim() == 3 && x.size(2) == 3, "molann_b200::", op, ": input must have shape [L, n_inp, 3]");
+  TORCH_CHECK(x.is_contiguous(), "molann_b200::", op, ": input must be contiguous");
+}
+
+void check_const(const Tensor& t, const Tensor& x, at::ScalarType dt, const char* name) {
+  if (t.numel() == 0) return;
+  TORCH_CHECK(t.device() == x.device(), "molann_b200: ", name, " must live on the input's device (", x.device(),
+              "), got ", t.device(), " -- call module.to(device)");
+  TORCH_CHECK(t.scalar_type() == dt, "molann_b200: ", name, " has wrong dtype ", t.scalar_type());
+  TORCH_CHECK(t.is_contiguous(), "molann_b200: ", name, " must be contiguous");
+}
+
+struct PlanHolder {
+  MolannPlan plan;
+  std::vector<Tensor> keep;      // contiguous views kept alive for the duration of the call
+};
+
+void fill_geometry(PlanHolder& h, const Tensor& x, const Tensor& align_idx, const Tensor& ref_x) {
+  std::memset(&h.plan, 0, sizeof(MolannPlan));
+  check_const(align_idx, x, at::kInt, "align_idx");
+  check_const(ref_x, x, at::kFloat, "ref_x");
+  h.plan.n_inp = static_cast<int32_t>(x.size(1));
+  h.plan.n_align = static_cast<int32_t>(align_idx.numel());
+  TORCH_CHECK(ref_x.numel() == 3 * align_idx.numel(), "molann_b200: ref_x must be [n_align, 3]");
+  h.plan.align_idx = h.plan.n_align ? align_idx.data_ptr<int32_t>() : nullptr;
+  h.plan.ref_x = h.plan.n_align ? ref_x.data_ptr<float>() : nullptr;
+}
+
+void fill_features(PlanHolder& h, const Tensor& x, const Tensor& entries, int64_t d_feat, bool use_angle_value) {
+  check_const(entries, x, at::kInt, "feature program");
+  TORCH_CHECK(entries.dim() == 2 && entries.size(1) == MOLANN_ENTRY_INTS && entries.size(0) > 0,
+              "molann_b200: feature program must be a non-empty int32 [n_entries, ", MOLANN_ENTRY_INTS, "] tensor");
+  h.plan.n_entries = static_cast<int32_t>(entries.size(0));
+  h.plan.entries = entries.data_ptr<int32_t>();
+  h.plan.d_feat = static_cast<int32_t>(d_feat);
+  h.plan.use_angle_value = use_angle_value ? 1 : 0;
+}
+
+void fill_mlp(PlanHolder& h, const Tensor& x, at::TensorList params, int64_t act) {
+  TORCH_CHECK(params.size() >= 2 && params.size() % 2 == 0, "molann_b200: params must be [W1, b1, W2, b2, ...]");
+  const int nl = static_cast<int>(params.size() / 2);
+  TORCH_CHECK(nl <= MOLANN_MAX_LAYERS, "molann_b200: at most ", MOLANN_MAX_LAYERS, " linear layers are supported");
+  h.plan.n_layers = nl;
+  h.plan.act_id = static_cast<int32_t>(act);
+  h.plan.dims[0] = h.plan.d_feat;
+  for (int k = 0; k < nl; ++k) {
+    const Tensor& W = params[2 * k];
+    const Tensor& b = params[2 * k + 1];
+    TORCH_CHECK(W.dim() == 2 && b.dim() == 1 && W.size(0) == b.size(0), "molann_b200: bad Linear shapes at layer ",
+                k + 1);
+    TORCH_CHECK(W.size(1) == h.plan.dims[k], "molann_b200: layer ", k + 1, " expects ", W.size(1),
+                " inputs but receives ", h.plan.dims[k]);
+    TORCH_CHECK(W.device() == x.device() && b.device() == x.device(),
+                "molann_b200: MLP parameters must live on the input's device -- call module.to(device)");
+    TORCH_CHECK(W.scalar_type() == at::kFloat && b.scalar_type() == at::kFloat,
+                "molann_b200: MLP parameters must be float32");
+    h.keep.push_back(W.contiguous());
+    h.keep.push_back(b.contiguous());
+    h.plan.W[k] = h.keep[2 * k].data_ptr<float>();
+    h.plan.b[k] = h.keep[2 * k + 1].data_ptr<float>();
+    h.plan.dims[k + 1] = static_cast<int32_t>(W.size(0));
+  }
+}
+
+void* cur_stream() { return static_cast<void*>(at::cuda::getCurrentCUDAStream().stream()); }
+
+// ------------------------------------------------------------------------------------------
+// raw (non-differentiable) implementations
+// ------------------------------------------------------------------------------------------
+Tensor align_fwd_impl(const Tensor& x, const Tensor& align_idx, const Tensor& ref_x) {
+  check_x(x, "align");
+  c10::cuda::CUDAGuard guard(x.device());
+  PlanHolder h;
+  fill_geometry(h, x, align_idx, ref_x);
+  TORCH_CHECK(h.plan.n_align > 0, "molann_b200::align: empty alignment selection");
+  Tensor out = at::empty_like(x);
+  check_status(molann_b200_align_forward(&h.plan, x.data_ptr<float>(), x.size(0), out.data_ptr<float>(), cur_stream()),
+               "align_forward");
+  return out;
+}
+
+Tensor align_bwd_impl(const Tensor& x, const Tensor& align_idx, const Tensor& ref_x, const Tensor& gout_in) {
+  c10::cuda::CUDAGuard guard(x.device());
+  PlanHolder h;
+  fill_geometry(h, x, align_idx, ref_x);
+  Tensor gout = gout_in.contiguous();
+  Tensor gx = at::empty_like(x);
+  check_status(molann_b200_align_backward(&h.plan, x.data_ptr<float>(), gout.data_ptr<float>(), x.size(0),
+                                          gx.data_ptr<float>(), cur_stream()),
+               "align_backward");
+  return gx;
+}
+
+Tensor preprocess_fwd_impl(const Tensor& x, const Tensor& align_idx, const Tensor& ref_x, const Tensor& entries,
+                           int64_t d_feat, bool use_angle_value) {
+  check_x(x, "preprocess");
+  c10::cuda::CUDAGuard guard(x.device());
+  PlanHolder h;
+  fill_geometry(h, x, align_idx, ref_x);
+  fill_features(h, x, entries, d_feat, use_angle_value);
+  Tensor feat = at::empty({x.size(0), d_feat}, x.options());
+  check_status(molann_b200_preprocess_forward(&h.plan, x.data_ptr<float>(), x.size(0), feat.data_ptr<float>(),
+                                              cur_stream()),
+               "preprocess_forward");
+  return feat;
+}
+
+Tensor preprocess_bwd_impl(const Tensor& x, const Tensor& align_idx, const Tensor& ref_x, const Tensor& entries,
+                           int64_t d_feat, bool use_angle_value, const Tensor& gfeat_in) {
+  c10::cuda::CUDAGuard guard(x.device());
+  PlanHolder h;
+  fill_geometry(h, x, align_idx, ref_x);
+  fill_features(h, x, entries, d_feat, use_angle_value);
+  Tensor gfeat = gfeat_in.contiguous();
+  Tensor gx = at::empty_like(x);
+  check_status(molann_b200_preprocess_backward(&h.plan, x.data_ptr<float>(), gfeat.data_ptr<float>(), x.size(0),
+                                               gx.data_ptr<float>(), cur_stream()),
+               "preprocess_backward");
+  return gx;
+}
+
+Tensor molann_fwd_impl(const Tensor& x, const Tensor& align_idx, const Tensor& ref_x, const Tensor& entries,
+                       int64_t d_feat, bool use_angle_value, at::TensorList params, int64_t act) {
+  check_x(x, "molann");
+  c10::cuda::CUDAGuard guard(x.device());
+  PlanHolder h;
+  fill_geometry(h, x, align_idx, ref_x);
+  fill_features(h, x, entries, d_feat, use_angle_value);
+  fill_mlp(h, x, params, act);
+  const int64_t L = x.size(0);
+  Tensor y = at::empty({L, h.plan.dims[h.plan.n_layers]}, x.options());
+  Tensor ws;
+  void* wsp = nullptr;
+  size_t ws_bytes = 0;
+  if (molann_b200_path_for(&h.plan, 0) != 1) {
+    ws_bytes = molann_b200_workspace_bytes(&h.plan, L, 0);
+    ws = at::empty({static_cast<int64_t>(ws_bytes)}, x.options().dtype(at::kByte));
+    wsp = ws.data_ptr();
+  }
+  check_status(molann_b200_forward(&h.plan, x.data_ptr<float>(), L, y.data_ptr<float>(), wsp, ws_bytes, cur_stream()),
+               "forward");
+  return y;
+}
+
+// returns {gx, gW1, gb1, gW2, gb2, ...}; parameter gradients are undefined tensors unless requested
+std::vector<Tensor> molann_bwd_impl(const Tensor& x, const Tensor& align_idx, const Tensor& ref_x,
+                                    const Tensor& entries, int64_t d_feat, bool use_angle_value,
+                                    at::TensorList params, int64_t act, const Tensor& gy_in, bool want_params) {
+  c10::cuda::CUDAGuard guard(x.device());
+  PlanHolder h;
+  fill_geometry(h, x, align_idx, ref_x);
+  fill_features(h, x, entries, d_feat, use_angle_value);
+  fill_mlp(h, x, params, act);
+  const int64_t L = x.size(0);
+  const int nl = h.plan.n_layers;
+  Tensor gy = gy_in.contiguous();
+  Tensor gx = at::empty_like(x);
+  std::vector<Tensor> out;
+  out.push_back(gx);
+  float* gW[MOLANN_MAX_LAYERS] = {nullptr};
+  float* gb[MOLANN_MAX_LAYERS] = {nullptr};
+  if (want_params) {
+    for (int k = 0; k < nl; ++k) {
+      out.push_back(at::zeros_like(params[2 * k], at::MemoryFormat::Contiguous));
+      out.push_back(at::zeros_like(params[2 * k + 1], at::MemoryFormat::Contiguous));
+      gW[k] = out[1 + 2 * k].data_ptr<float>();
+      gb[k] = out[2 + 2 * k].data_ptr<float>();
+    }
+  }
+  Tensor ws;
+  void* wsp = nullptr;
+  size_t ws_bytes = 0;
+  if (want_params || molann_b200_path_for(&h.plan, 1) != 1) {
+    ws_bytes = molann_b200_workspace_bytes(&h.plan, L, 1);
+    ws = at::empty({static_cast<int64_t>(ws_bytes)}, x.options().dtype(at::kByte));
+    wsp = ws.data_ptr();
+  }
+  check_status(molann_b200_backward(&h.plan, x.data_ptr<float>(), gy.data_ptr<float>(), L, gx.data_ptr<float>(),
+                                    want_params ? gW : nullptr, want_params ? gb : nullptr, wsp, ws_bytes,
+                                    cur_stream()),
+               "backward");
+  return out;
+}
+
+// ------------------------------------------------------------------------------------------
+// autograd
+// ------------------------------------------------------------------------------------------
+struct AlignFn : public torch::autograd::Function<AlignFn> {
+  static Tensor forward(AutogradContext* ctx, const Tensor& x, const Tensor& align_idx, const Tensor& ref_x) {
+    at::AutoDispatchBelowADInplaceOrView g;
+    ctx->save_for_backward({x, align_idx, ref_x});
+    return align_fwd_impl(x, align_idx, ref_x);
+  }
+  static variable_list backward(AutogradContext* ctx, variable_list grads) {
+    auto saved = ctx->get_saved_variables();
+    Tensor gx = align_bwd_impl(saved[0], saved[1], saved[2], grads[0]);
+    return {gx, Tensor(), Tensor()};
+  }
+};
+
+struct PreprocessFn : public torch::autograd::Function<PreprocessFn> {
+  static Tensor forward(AutogradContext* ctx, const Tensor& x, const Tensor& align_idx, const Tensor& ref_x,
+                        const Tensor& entries, int64_t d_feat, bool use_angle_value) {
+    at::AutoDispatchBelowADInplaceOrView g;
+    ctx->save_for_backward({x, align_idx, ref_x, entries});
+    ctx->saved_data["d_feat"] = d_feat;
+    ctx->saved_data["use_angle_value"] = use_angle_value;
+    return preprocess_fwd_impl(x, align_idx, ref_x, entries, d_feat, use_angle_value);
+  }
+  static variable_list backward(AutogradContext* ctx, variable_list grads) {
+    auto saved = ctx->get_saved_variables();
+    Tensor gx = preprocess_bwd_impl(saved[0], saved[1], saved[2], saved[3], ctx->saved_data["d_feat"].toInt(),
+                                    ctx->saved_data["use_angle_value"].toBool(), grads[0]);
+    return {gx, Tensor(), Tensor(), Tensor(), Tensor(), Tensor()};
+  }
+};
+
+struct MolannFn : public torch::autograd::Function<MolannFn> {
+  static Tensor forward(AutogradContext* ctx, const Tensor& x, const Tensor& align_idx, const Tensor& ref_x,
+                        const Tensor& entries, int64_t d_feat, bool use_angle_value, at::TensorList params,
+                        int64_t act) {
+    at::AutoDispatchBelowADInplaceOrView g;
+    std::vector<Tensor> to_save = {x, align_idx, ref_x, entries};
+    bool want_params = false;
+    for (const Tensor& p : params) {
+      to_save.push_back(p);
+      want_params = want_params || p.requires_grad();
+    }
+    ctx->save_for_backward(to_save);
+    ctx->saved_data["d_feat"] = d_feat;
+    ctx->saved_data["use_angle_value"] = use_angle_value;
+    ctx->saved_data["act"] = act;
+    ctx->saved_data["want_params"] = want_params;
+    ctx->saved_data["n_params"] = static_cast<int64_t>(params.size());
+    return molann_fwd_impl(x, align_idx, ref_x, entries, d_feat, use_angle_value, params, act);
+  }
+  static variable_list backward(AutogradContext* ctx, variable_list grads) {
+    auto saved = ctx->get_saved_variables();
+    const int64_t np = ctx->saved_data["n_params"].toInt();
+    std::vector<Tensor> params(saved.begin() + 4, saved.begin() + 4 + np);
+    const bool want_params = ctx->saved_data["want_params"].toBool();
+    auto g = molann_bwd_impl(saved[0], saved[1], saved[2], saved[3], ctx->saved_data["d_feat"].toInt(),
+                             ctx->saved_data["use_angle_value"].toBool(), params, ctx->saved_data["act"].toInt(),
+                             grads[0], want_params);
+    variable_list out;
+    out.push_back(g[0]);                                         // x
+    for (int i = 0; i < 5; ++i) out.push_back(Tensor());         // align_idx, ref_x, entries, d_feat, use_angle
+    for (int64_t i = 0; i < np; ++i) out.push_back(want_params ? g[1 + i] : Tensor());
+    out.push_back(Tensor());                                     // act
+    return out;
+  }
+};
+
+Tensor align_autograd(const Tensor& x, const Tensor& align_idx, const Tensor& ref_x) {
+  check_x(x, "align");
+  return AlignFn::apply(x, align_idx, ref_x);
+}
+Tensor preprocess_autograd(const Tensor& x, const Tensor& align_idx, const Tensor& ref_x, const Tensor& entries,
+                           int64_t d_feat, bool use_angle_value) {
+  check_x(x, "preprocess");
+  return PreprocessFn::apply(x, align_idx, ref_x, entries, d_feat, use_angle_value);
+}
+Tensor molann_autograd(const Tensor& x, const Tensor& align_idx, const Tensor& ref_x, const Tensor& entries,
+                       int64_t d_feat, bool use_angle_value, at::TensorList params, int64_t act) {
+  check_x(x, "molann");
+  return MolannFn::apply(x, align_idx, ref_x, entries, d_feat, use_angle_value, params, act);
+}
+
+int64_t launch_count() { return molann_b200_launch_count(); }
+
+}  // namespace
+
+TORCH_LIBRARY(molann_b200, m) {
+  m.def("align(Tensor x, Tensor align_idx, Tensor ref_x) -> Tensor");
+  m.def("preprocess(Tensor x, Tensor align_idx, Tensor ref_x, Tensor entries, int d_feat, bool use_angle_value) -> Tensor");
+  m.def("molann(Tensor x, Tensor align_idx, Tensor ref_x, Tensor entries, int d_feat, bool use_angle_value, "
+        "Tensor[] params, int act) -> Tensor");
+  m.def("launch_count() -> int", &launch_count);
+}
+
+TORCH_LIBRARY_IMPL(molann_b200, CUDA, m) {
+  m.impl("align", &align_fwd_impl);
+  m.impl("preprocess", &preprocess_fwd_impl);
+  m.impl("molann", &molann_fwd_impl);
+}
+
+TORCH_LIBRARY_IMPL(molann_b200, Autograd, m) {
+  m.impl("align", &align_autograd);
+  m.impl("preprocess", &preprocess_autograd);
+  m.impl("molann", &molann_autograd);
+}
