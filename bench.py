@@ -1,0 +1,417 @@
+#!/usr/bin/env python
+"""Benchmark of the molann hot path (BASELINE.json: frames/s, fwd and fwd+d/dx, % of HBM roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C2]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A *step* is one pass of the fused align -> features -> MLP path over one device-resident batch of
+synthetic frames (workload C2 = BASELINE.json configs[1]: alanine dipeptide, heavy-atom alignment +
+30 position features -> MLP [30,64,64,2], 2**20 frames per GPU per step; weak scaling: every rank owns
+its own frames, no data-path collective).  One JSON line is printed by rank 0:
+
+  value       whole-job forward frames/s with inputs resident in HBM (CUDA events, max over ranks)
+  fwd_dx      same for forward + gradient wrt coordinates (the biasing-force path)
+  e2e         the same metric through the public API with HOST buffers (pinned H2D of every step's frames
+              and D2H of its outputs inside the timed region, molann_b200.stream.HostPipeline)
+  roofline    algorithmic bytes / kernel time vs the measured HBM copy peak (MEASURED_PEAKS.json)
+  cpu_baseline the reference's PyTorch CPU path on this box's host cores (bounded sample)
+
+`--impl reference` times the reference's own CPU implementation (baseline/_ref = unmodified
+zwpku/molann if installed, else the oracle port) on the same workload / metric.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "frames_per_sec_fwd"
+UNIT = "frames/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C3", "C5"])
+    ap.add_argument("--frames", type=int, default=0, help="frames per GPU per step (default: workload's)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        try:
+            with open(path) as fh:
+                d = json.load(fh)
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(workload, which):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+    path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.isfile(path):
+        try:
+            with open(path) as fh:
+                return json.load(fh).get(workload, {}).get(which)
+        except Exception:
+            return None
+    return None
+
+
+class ClockSampler(object):
+    """Samples SM clock + throttle reasons of one GPU with NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._active = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake_slowdown",
+        }
+        getter = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons", None)
+        while not self._stop.is_set():
+            if self._active.is_set():
+                try:
+                    self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                    if getter is not None:
+                        mask = int(getter(self.h))
+                        for bit, nm in names.items():
+                            if mask & bit:
+                                self.reasons.add(nm)
+                except Exception:
+                    pass
+            time.sleep(0.002)
+
+    def start(self):
+        self._active.set()
+
+    def pause(self):
+        self._active.clear()
+
+    def close(self):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=1.0)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def reference_api():
+    """-> (namespace, kind): the unmodified reference if importable, else the oracle port."""
+    from types import SimpleNamespace
+    from oracle.ref_loader import load_reference
+    ref = load_reference()
+    if ref is not None:
+        ann, feature, root = ref
+        return SimpleNamespace(Feature=feature.Feature, FeatureLayer=ann.FeatureLayer,
+                               AlignmentLayer=ann.AlignmentLayer, PreprocessingANN=ann.PreprocessingANN,
+                               MolANN=ann.MolANN, create_sequential_nn=ann.create_sequential_nn), "reference", root
+    return None, "port", "oracle/restatement.py"
+
+
+def cpu_model(spec):
+    """CPU callable frames -> outputs for `spec` (reference modules, or the oracle restatement)."""
+    import warnings
+    from molann_b200 import synthetic as S
+    api, kind, where = reference_api()
+    if api is not None:
+        model, _ = S.build_model(spec, api)
+
+        def fn(x):
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                return model(x)
+        return fn, kind, where
+    from oracle import restatement as R
+    import numpy as np
+    ours, _ = S.build_model(spec)
+    sd = ours.state_dict()
+    nl = len(spec.layer_dims) - 1
+    ws = [sd["ann_layers.%dth_layer.weight" % (k + 1)] for k in range(nl)]
+    bs = [sd["ann_layers.%dth_layer.bias" % (k + 1)] for k in range(nl)]
+    inp = list(spec.input_ix)
+    tid = {"angle": 0, "bond": 1, "dihedral": 2, "position": 3}
+    feats = [(tid[t], [inp.index(i) for i in ix]) for _, t, ix in spec.features]
+    aidx = [inp.index(i) for i in spec.align_ix] if spec.align_ix is not None else None
+    ref = torch.from_numpy(spec.positions[np.asarray(spec.align_ix)].copy()) if aidx is not None else torch.zeros(0, 3)
+    ref = ref - ref.mean(0) if aidx is not None else ref
+
+    def fn(x):
+        return R.molann_forward(x, aidx, ref, feats, spec.use_angle_value, ws, bs, spec.activation)
+    return fn, kind, where
+
+
+def time_cpu(spec, frames_fwd, frames_dx, reps=3):
+    """Best-of-`reps` CPU frames/s, forward (no_grad) and forward + d/dx (autograd)."""
+    from molann_b200 import synthetic as S
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    fn, kind, where = cpu_model(spec)
+    x = S.make_frames(spec, max(frames_fwd, frames_dx), seed=spec.seed + 1)
+    with torch.no_grad():
+        fn(x[:1024])
+    best_f = 0.0
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            fn(x[:frames_fwd])
+        best_f = max(best_f, frames_fwd / (time.perf_counter() - t0))
+    best_d = 0.0
+    for _ in range(reps):
+        xx = x[:frames_dx].clone().requires_grad_(True)
+        t0 = time.perf_counter()
+        y = fn(xx)
+        torch.autograd.grad(y.sum(), xx)
+        best_d = max(best_d, frames_dx / (time.perf_counter() - t0))
+    return best_f, best_d, cores, kind, where
+
+
+def cpu_sample_sizes(spec):
+    n = spec.n_inp
+    if n <= 64:
+        return 1 << 19, 1 << 18
+    if n <= 2000:
+        return 4096, 512
+    return 1024, 128
+
+
+def run_reference(args, rank):
+    """`--impl reference`: the reference's CPU implementation on the same workload / metric (rank 0 only)."""
+    if rank != 0:
+        return
+    from molann_b200 import synthetic as S
+    spec = S.get_spec(args.workload)
+    ff, fd = cpu_sample_sizes(spec)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    fn, kind, where = cpu_model(spec)
+    x = S.make_frames(spec, max(ff, fd), seed=spec.seed + 1)
+    with torch.no_grad():
+        for _ in range(max(1, min(args.warmup, 3))):
+            fn(x[:ff])
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            fn(x[:ff])
+        dt = time.perf_counter() - t0
+    value = args.steps * ff / dt
+    t0 = time.perf_counter()
+    nd = max(1, args.steps // 4)
+    for _ in range(nd):
+        xx = x[:fd].clone().requires_grad_(True)
+        torch.autograd.grad(fn(xx).sum(), xx)
+    vdx = nd * fd / (time.perf_counter() - t0)
+    sample = "%d frames/step fwd (no_grad), %d frames/step fwd+dx (autograd), %s, torch %d threads" % (
+        ff, fd, where, cores)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": dict(workload_config(spec, spec.default_frames, args.gpus), reference_sample_frames_per_step=ff),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "fwd_dx": {"value": vdx, "unit": UNIT},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(spec, frames, n_gpus):
+    return {"workload": "%s: %s" % (spec.name, spec.note), "n_inp": spec.n_inp, "d_feat": spec.feature_dim(),
+            "mlp": spec.layer_dims, "frames_per_gpu_per_step": frames,
+            "bytes_per_frame_fwd": spec.bytes_fwd(), "bytes_per_frame_fwd_dx": spec.bytes_fwd_dx(),
+            "l2_policy": "inputs larger than L2 (%.0f MB read per step per GPU, no flush needed)"
+                         % (frames * 12 * spec.n_inp / 1e6),
+            "parallelism": "frame-sharded x%d, no data-path collective" % n_gpus}
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- molann_b200 has no CPU path (use --impl reference for the CPU arm)")
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+
+    from molann_b200 import _lib
+    from molann_b200 import synthetic as S
+    from molann_b200.stream import HostPipeline
+
+    spec = S.get_spec(args.workload)
+    frames = args.frames or spec.default_frames
+    model, _ = S.build_model(spec)
+    model = model.cuda()
+    x = S.make_frames(spec, frames, device="cuda", seed=spec.seed + rank)
+    cot = torch.zeros(frames, spec.out_dim(), device="cuda")
+    cot[:, 0] = 1.0                                        # d y_0 / dx: one collective-variable force
+    xg = x.clone().requires_grad_(True)
+    K, W = args.steps, max(args.warmup, 3)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    def fwd_step():
+        with torch.no_grad():
+            return model(x)
+
+    def fwd_dx_step():
+        y = model(xg)
+        (g,) = torch.autograd.grad(y, xg, cot)
+        return g
+
+    sampler = ClockSampler(local_rank)
+
+    def timed(step, k, w, sample_clocks):
+        for _ in range(w):
+            step()
+        barrier()
+        l0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if sample_clocks:
+            sampler.start()
+        e0.record()
+        for _ in range(k):
+            step()
+        e1.record()
+        barrier()
+        if sample_clocks:
+            sampler.pause()
+        return max_over_ranks(e0.elapsed_time(e1)), _lib.launch_count() - l0
+
+    ms_f, launches_f = timed(fwd_step, K, W, True)
+    ms_d, launches_d = timed(fwd_dx_step, K, W, True)
+    clocks = sampler.summary()
+    sampler.close()
+
+    # ---- end to end through the public API with host buffers ----
+    e2e = e2e_dx = None
+    if not args.no_e2e:
+        xh = x.cpu().pin_memory()
+        yh = torch.empty(frames, spec.out_dim()).pin_memory()
+        pipe = HostPipeline(model, spec.n_inp, spec.out_dim(), chunk_frames=max(1 << 16, frames // 8))
+        ke = max(3, min(K, 10))
+
+        def e2e_step():
+            pipe.run(xh, yh)
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            e2e_step()
+        torch.cuda.synchronize()
+        ms_e = max_over_ranks(1e3 * (time.perf_counter() - t0))
+        checksum = float(yh[:: max(1, frames // 1024)].double().sum())
+        e2e = {"value": world * frames * ke / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes,
+               "d2h_bytes_per_step": pipe.d2h_bytes, "steps": ke, "ms_per_step": ms_e / ke,
+               "api": "molann_b200.stream.HostPipeline(MolANN).run(pinned x, pinned y)", "result_checksum": checksum}
+        coth = cot.cpu().pin_memory()
+        gxh = torch.empty(frames, spec.n_inp, 3).pin_memory()
+        pipe.run(xh, yh, coth, gxh)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            pipe.run(xh, yh, coth, gxh)
+        torch.cuda.synchronize()
+        ms_ed = max_over_ranks(1e3 * (time.perf_counter() - t0))
+        e2e_dx = {"value": world * frames * ke / (ms_ed * 1e-3), "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes,
+                  "d2h_bytes_per_step": pipe.d2h_bytes, "steps": ke, "ms_per_step": ms_ed / ke}
+        del xh, yh, coth, gxh
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = peaks()
+    value = world * frames * K / (ms_f * 1e-3)
+    value_dx = world * frames * K / (ms_d * 1e-3)
+
+    def roofline(bytes_per_frame, ms_total, launches, which):
+        per_launch_s = ms_total * 1e-3 / K
+        achieved = bytes_per_frame * frames / per_launch_s / 1e9
+        return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ncu_traffic(spec.name, which), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": bytes_per_frame * frames, "kernel_launches_per_step": launches / K,
+                "frac_of_nominal_8TBs": achieved / 8000.0}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_f / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(spec, frames, world),
+        "roofline": roofline(spec.bytes_fwd(), ms_f, launches_f, "fwd"),
+        "gpu_launches": int(launches_f), "clocks": clocks,
+        "fwd_dx": {"value": value_dx, "unit": UNIT, "ms_per_step": ms_d / K, "gpu_launches": int(launches_d),
+                   "roofline": roofline(spec.bytes_fwd_dx(), ms_d, launches_d, "fwd_dx"), "e2e": e2e_dx},
+        "e2e": e2e,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        ff, fd = cpu_sample_sizes(spec)
+        cf, cd, cores, kind, where = time_cpu(spec, ff, fd)
+        line["cpu_baseline"] = {"value": cf, "unit": UNIT, "cores": cores, "kind": kind,
+                                "sample": "best of 3: %d frames fwd (no_grad), %d frames fwd+dx (autograd); %s; "
+                                          "torch.set_num_threads(%d)" % (ff, fd, where, cores),
+                                "fwd_dx_value": cd}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,95 @@
+"""The C-ABI shared library: loads without a GPU, exports every symbol include/molann_b200.h declares,
+validates plans on the host, and refuses to compute when there is no CUDA device."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from helpers import ROOT, S, golden, golden_weights, spec_program
+from molann_b200 import _lib
+
+
+def declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "molann_b200.h")).read()
+    return sorted(set(re.findall(r"\b(molann_b200_[a-z_0-9]+)\s*\(", hdr)))
+
+
+def test_library_loads_and_exports_header_symbols():
+    lib = _lib.cabi()
+    syms = declared_symbols()
+    assert len(syms) >= 14
+    for s in syms:
+        assert hasattr(lib, s), "symbol %s declared in include/molann_b200.h is not exported" % s
+    assert lib.molann_b200_version() == 100
+    assert lib.molann_b200_strerror(0) == b"ok" and b"plan" in lib.molann_b200_strerror(2)
+
+
+def test_struct_layout_matches_header():
+    # 2 int32, 2 ptr, int32 (+pad), ptr, 4 int32, 9 int32 (+pad), 8 ptr, 8 ptr
+    assert ctypes.sizeof(_lib.MolannPlan) == 8 + 16 + 8 + 8 + 16 + 36 + 4 + 64 + 64
+
+
+def host_plan(spec, n_layers=None):
+    """Plan with fake (non-null) device pointers: only scalar validation is exercised."""
+    aidx, ref, feats, entries, d = spec_program(spec)
+    p = _lib.MolannPlan()
+    p.n_inp = spec.n_inp
+    if aidx is not None:
+        p.n_align, p.align_idx, p.ref_x = len(aidx), 0x1000, 0x2000
+    p.n_entries, p.entries, p.d_feat, p.use_angle_value = entries.shape[0], 0x3000, d, int(spec.use_angle_value)
+    dims = spec.layer_dims
+    p.n_layers = len(dims) - 1 if n_layers is None else n_layers
+    for k, v in enumerate(dims):
+        p.dims[k] = v
+    for k in range(len(dims) - 1):
+        p.W[k], p.b[k] = 0x4000 + k * 0x100, 0x8000 + k * 0x100
+    return p
+
+
+def test_plan_validate_statuses():
+    lib = _lib.cabi()
+    p = host_plan(S.get_spec("C2"))
+    assert lib.molann_b200_plan_validate(ctypes.byref(p)) == 0
+    assert lib.molann_b200_plan_validate(None) == 1
+    bad = host_plan(S.get_spec("C2")); bad.dims[0] = 31
+    assert lib.molann_b200_plan_validate(ctypes.byref(bad)) == 2
+    bad = host_plan(S.get_spec("C2")); bad.W[1] = None
+    assert lib.molann_b200_plan_validate(ctypes.byref(bad)) == 1
+    bad = host_plan(S.get_spec("C2")); bad.act_id = 9
+    assert lib.molann_b200_plan_validate(ctypes.byref(bad)) == 2
+    bad = host_plan(S.get_spec("C2")); bad.n_layers = 9
+    assert lib.molann_b200_plan_validate(ctypes.byref(bad)) == 2
+    bad = host_plan(S.get_spec("C2")); bad.entries = None
+    assert lib.molann_b200_plan_validate(ctypes.byref(bad)) == 1
+    bad = host_plan(S.get_spec("C2")); bad.n_inp = 0
+    assert lib.molann_b200_plan_validate(ctypes.byref(bad)) == 2
+
+
+def test_dispatch_table_and_workspace():
+    """Small systems go to the fused kernel, big ones to the general path; workspace is O(chunk)."""
+    lib = _lib.cabi()
+    for name, want in (("C1", 1), ("C2", 1), ("C3", 0), ("C5", 0)):
+        p = host_plan(S.get_spec(name))
+        assert lib.molann_b200_path_for(ctypes.byref(p), 0) == want, name
+        assert lib.molann_b200_path_for(ctypes.byref(p), 1) == want, name
+    p = host_plan(S.get_spec("C3"))
+    w1 = lib.molann_b200_workspace_bytes(ctypes.byref(p), 1 << 20, 0)
+    w2 = lib.molann_b200_workspace_bytes(ctypes.byref(p), 1 << 24, 0)
+    assert w1 == w2 > 0
+    assert lib.molann_b200_workspace_bytes(ctypes.byref(p), 1 << 20, 1) > w1
+    assert lib.molann_b200_workspace_bytes(ctypes.byref(p), 100, 0) < w1
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_compute_entry_points_fail_without_gpu():
+    lib = _lib.cabi()
+    p = host_plan(S.get_spec("C2"))
+    st = lib.molann_b200_forward(ctypes.byref(p), 0x10000, 8, 0x20000, None, 0, None)
+    assert st == 5                                     # MOLANN_ERR_CUDA, never a silent CPU result
+    assert lib.molann_b200_forward(ctypes.byref(p), None, 8, 0x20000, None, 0, None) == 1
+    assert lib.molann_b200_forward(ctypes.byref(p), 0x10000, 0, 0x20000, None, 0, None) == 0     # L == 0: no-op
+    assert lib.molann_b200_forward(ctypes.byref(p), 0x10001, 8, 0x20000, None, 0, None) == 4
+    q = host_plan(S.get_spec("C2"), n_layers=0)
+    assert lib.molann_b200_forward(ctypes.byref(q), 0x10000, 8, 0x20000, None, 0, None) == 6

@@ -1,0 +1,411 @@
+"""Parity of the CUDA path with the oracle / the reference's golden vectors (run on a B200: -m gpu).
+
+Every case goes through the C ABI (ctypes, helpers.CPlan) and/or the drop-in module API (which calls the
+same C ABI through the torch shim).  Acceptance rule: per frame,
+|new - ref64| / |ref64| <= max(1e-5, 2 |ref32 - ref64| / |ref64|) in max-abs norm; integer side exact."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import (ROOT, S, CPlan, assert_parity, frame_rel_err, golden, golden_weights, oracle_model,
+                     oracle_preprocess, oracle_value_and_grad, spec_program, R)
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+
+@pytest.fixture(autouse=True)
+def _clean_env(monkeypatch):
+    for k in list(os.environ):
+        if k.startswith("MOLANN_B200_"):
+            monkeypatch.delenv(k, raising=False)
+    yield
+
+
+def dev(t):
+    return torch.as_tensor(t).cuda().contiguous()
+
+
+def test_native_library_is_loaded_and_counts_launches():
+    from molann_b200 import _lib
+    import molann_b200.ann  # noqa: F401
+    maps = open("/proc/self/maps").read()
+    assert "libmolann_b200.so" in maps and "libmolann_b200_torch.so" in maps
+    spec = S.get_spec("C2")
+    model, _ = S.build_model(spec)
+    model = model.cuda()
+    before = _lib.launch_count()
+    model(S.make_frames(spec, 300, device="cuda"))
+    torch.cuda.synchronize()
+    assert _lib.launch_count() == before + 1          # ONE fused kernel for align + features + MLP
+    assert int(torch.ops.molann_b200.launch_count()) == _lib.launch_count()
+
+
+@pytest.mark.parametrize("path", ["auto", "general"])
+@pytest.mark.parametrize("name", ["C1", "C2", "C3s"])
+def test_cabi_against_reference_goldens(name, path, monkeypatch):
+    if path == "general":
+        monkeypatch.setenv("MOLANN_B200_PATH", "0")
+    spec = S.get_spec(name)
+    g = golden("config_" + name)
+    ws, bs = golden_weights(g, len(spec.layer_dims) - 1)
+    plan = CPlan(spec, ws, bs)
+    want = 1 if path == "auto" else 0
+    import ctypes
+    assert plan.lib.molann_b200_path_for(ctypes.byref(plan.p), 0) == want
+    x = dev(g["x"])
+    y = plan.forward(x)
+    assert_parity(y.cpu(), g["y64"], g["y32"], TOL, "%s y" % name)
+    gx = plan.backward(x, dev(g["cot"]))
+    assert_parity(gx.cpu(), g["gx64"], g["gx32"], TOL, "%s gx" % name)
+    feat = plan.preprocess_forward(x)
+    assert_parity(feat.cpu(), g["feat64"], g["feat32"], TOL, "%s feat" % name)
+    gxf = plan.preprocess_backward(x, dev(g["cotf"]))
+    assert_parity(gxf.cpu(), g["gxf64"], g["gxf32"], TOL, "%s gxf" % name)
+
+
+@pytest.mark.parametrize("name", ["C1", "C2", "C3s"])
+def test_parameter_gradients_against_goldens(name):
+    spec = S.get_spec(name)
+    g = golden("config_" + name)
+    nl = len(spec.layer_dims) - 1
+    ws, bs = golden_weights(g, nl)
+    plan = CPlan(spec, ws, bs)
+    x = dev(g["x"])
+    gx, gW, gb = plan.backward(x, dev(g["cot"]), want_params=True)
+    assert_parity(gx.cpu(), g["gx64"], g["gx32"], TOL, "gx (general path)")
+    for k in range(nl):
+        rw = torch.from_numpy(g["gp64::ann_layers.%dth_layer.weight" % (k + 1)])
+        rb = torch.from_numpy(g["gp64::ann_layers.%dth_layer.bias" % (k + 1)])
+        assert float((gW[k].cpu().double() - rw).abs().max() / rw.abs().max()) < 2e-5
+        assert float((gb[k].cpu().double() - rb).abs().max() / rb.abs().max()) < 2e-5
+
+
+def test_fixture_known_answers_through_modules():
+    """SURVEY App. C on the 22-atom fixture, through the drop-in classes."""
+    from molann_b200.ann import AlignmentLayer, FeatureLayer
+    from molann_b200.atomgroup import Universe
+    from molann_b200.feature import Feature
+    g = golden("fixture")
+    u = Universe(g["x"])
+    x = dev(g["x"]).unsqueeze(0)
+    one = lambda *ids: u.select_ix([i - 1 for i in ids])
+    hist = [("d1", "dihedral", (5, 7, 9, 15)), ("d2", "dihedral", (7, 9, 15, 17)), ("b1", "bond", (2, 5)),
+            ("b2", "bond", (5, 6)), ("a1", "angle", (20, 19, 21)), ("a2", "angle", (16, 15, 17))]
+    feats = [Feature(n, t, one(*ids)) for n, t, ids in hist]
+    out = FeatureLayer(feats, u.atoms, use_angle_value=False).cuda()(x).cpu().numpy()
+    np.testing.assert_allclose(out, g["hist_cs"], atol=2e-6)
+    out = FeatureLayer(feats, u.atoms, use_angle_value=True).cuda()(x).cpu().numpy()
+    np.testing.assert_allclose(out, g["hist_angle"], atol=2e-6)
+    extra = [(1, 2, 5, 6), (3, 2, 5, 7), (10, 9, 11, 12), (9, 15, 17, 19)]
+    fe = [Feature("e", "dihedral", one(*ids)) for ids in extra]
+    out = FeatureLayer(fe, u.atoms).cuda()(x).cpu().numpy()
+    np.testing.assert_allclose(out, g["extra_dihedrals"], atol=2e-6)
+    inp = one(1, 2, 3, 4, 5)
+    fl = FeatureLayer([Feature("n", "dihedral", one(1, 2, 3, 4)), Feature("n", "bond", one(1, 3)),
+                       Feature("n", "angle", one(1, 2, 3))], inp).cuda()
+    out = fl(dev(inp.positions).unsqueeze(0)).cpu().numpy()
+    np.testing.assert_allclose(out, g["test_feature_layer"], atol=2e-6)
+    al = AlignmentLayer(one(1, 2, 5), u.atoms).cuda()
+    np.testing.assert_allclose(al(x).cpu().numpy(), g["align_self"], atol=3e-6)
+    np.testing.assert_allclose(al(dev(g["align_moved_x"]).unsqueeze(0)).cpu().numpy(), g["align_moved"], atol=5e-6)
+
+
+@pytest.mark.parametrize("name", ["C1", "C2", "C3s"])
+def test_module_api_forward_and_autograd(name):
+    spec = S.get_spec(name)
+    g = golden("config_" + name)
+    model, _ = S.build_model(spec)
+    model.load_state_dict({k[4:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd::")}, strict=True)
+    model = model.cuda()
+    x = dev(g["x"]).requires_grad_(True)
+    y = model(x)
+    assert_parity(y.detach().cpu(), g["y64"], g["y32"], TOL, "module y")
+    (gx,) = torch.autograd.grad(y, x, dev(g["cot"]))
+    assert_parity(gx.cpu(), g["gx64"], g["gx32"], TOL, "module gx")
+    # preprocessing layer alone, and parameter gradients through autograd (training path)
+    pp = model.get_preprocessing_layer()
+    x2 = dev(g["x"]).requires_grad_(True)
+    f = pp(x2)
+    assert_parity(f.detach().cpu(), g["feat64"], g["feat32"], TOL, "module feat")
+    (gxf,) = torch.autograd.grad(f, x2, dev(g["cotf"]))
+    assert_parity(gxf.cpu(), g["gxf64"], g["gxf32"], TOL, "module gxf")
+    model.zero_grad()
+    (model(dev(g["x"])) * dev(g["cot"])).sum().backward()
+    for k, p in model.named_parameters():
+        ref = torch.from_numpy(g["gp64::" + k])
+        assert float((p.grad.cpu().double() - ref).abs().max() / ref.abs().max()) < 2e-5, k
+
+
+def test_alignment_layer_standalone_and_composition():
+    """AlignmentLayer alone (fwd + autograd) and the unfused composition feature(align(x))."""
+    spec = S.get_spec("C2")
+    g = golden("config_C2")
+    model, _ = S.build_model(spec)
+    model = model.cuda()
+    pp = model.get_preprocessing_layer()
+    aidx, ref, feats, _, _ = spec_program(spec)
+    x = dev(g["x"]).requires_grad_(True)
+    z = pp.align_layer(x)
+    x64 = torch.from_numpy(g["x"]).double().requires_grad_(True)
+    z64 = R.align_forward(x64, aidx, ref.double())
+    assert_parity(z.detach().cpu(), z64.detach(), None, TOL, "align z")
+    cot = torch.randn(z.shape, generator=torch.Generator().manual_seed(3))
+    (gz,) = torch.autograd.grad(z, x, cot.cuda())
+    (gz64,) = torch.autograd.grad((z64 * cot.double()).sum(), x64)
+    assert_parity(gz.cpu(), gz64, None, TOL, "align gx")
+    f2 = pp.feature_layer(pp.align_layer(dev(g["x"])))
+    assert_parity(f2.cpu(), g["feat64"], g["feat32"], TOL, "composed feat")
+
+
+@pytest.mark.parametrize("L", [1, 2, 3, 4, 5, 63, 64, 65, 127, 128, 129, 257, 1000])
+def test_ragged_frame_counts(L):
+    """Partial tiles, L < tile, L == 3 (the reference's torch.cross quirk case is defined by intent)."""
+    for name in ("C1", "C2"):
+        spec = S.get_spec(name)
+        g = golden("config_" + name)
+        ws, bs = golden_weights(g, len(spec.layer_dims) - 1)
+        plan = CPlan(spec, ws, bs)
+        x = S.make_frames(spec, L, seed=900 + L)
+        cot = torch.randn(L, spec.out_dim(), generator=torch.Generator().manual_seed(L))
+        y64, gx64 = oracle_value_and_grad(oracle_model(spec, ws, bs), x, cot)
+        assert_parity(plan.forward(dev(x)).cpu(), y64, None, TOL, "%s L=%d y" % (name, L))
+        assert_parity(plan.backward(dev(x), dev(cot)).cpu(), gx64, None, 2e-5, "%s L=%d gx" % (name, L))
+
+
+def test_empty_batch():
+    spec = S.get_spec("C2")
+    model, _ = S.build_model(spec)
+    model = model.cuda()
+    y = model(torch.zeros(0, 22, 3, device="cuda"))
+    assert tuple(y.shape) == (0, 2)
+
+
+def test_unaligned_input_pointer_takes_the_non_tma_path():
+    spec = S.get_spec("C2")
+    g = golden("config_C2")
+    ws, bs = golden_weights(g, 3)
+    plan = CPlan(spec, ws, bs)
+    base = torch.zeros(1 + g["x"].size, device="cuda")
+    xv = base[1:].view(g["x"].shape)                  # 4-byte aligned only
+    xv.copy_(dev(g["x"]))
+    assert xv.data_ptr() % 16 != 0
+    assert_parity(plan.forward(xv).cpu(), g["y64"], g["y32"], TOL, "unaligned y")
+    assert_parity(plan.backward(xv, dev(g["cot"])).cpu(), g["gx64"], g["gx32"], TOL, "unaligned gx")
+
+
+@pytest.mark.parametrize("act", ["relu", "sigmoid"])
+def test_other_activations(act):
+    spec = S.get_spec("C2")
+    spec.activation = act
+    model, _ = S.build_model(spec, init_seed=5)
+    sd = model.state_dict()
+    ws = [sd["ann_layers.%dth_layer.weight" % k] for k in (1, 2, 3)]
+    bs = [sd["ann_layers.%dth_layer.bias" % k] for k in (1, 2, 3)]
+    x = S.make_frames(spec, 333, seed=8)
+    cot = torch.randn(333, 2, generator=torch.Generator().manual_seed(1))
+    y64, gx64 = oracle_value_and_grad(oracle_model(spec, ws, bs), x, cot)
+    model = model.cuda()
+    xd = dev(x).requires_grad_(True)
+    y = model(xd)
+    (gx,) = torch.autograd.grad(y, xd, cot.cuda())
+    assert_parity(y.detach().cpu(), y64, None, TOL, act + " y")
+    if act == "relu":       # kinks: frames with a pre-activation within fp32 noise of 0 may flip a unit
+        err = frame_rel_err(gx.cpu(), gx64)
+        assert float((err > 2e-5).float().mean()) < 0.02
+    else:
+        assert_parity(gx.cpu(), gx64, None, 2e-5, act + " gx")
+
+
+def test_mixed_feature_program_with_alignment():
+    """All four feature types + alignment in one layer, angle values on/off, shuffled input group."""
+    from molann_b200.ann import AlignmentLayer, FeatureLayer, PreprocessingANN
+    from molann_b200.atomgroup import Universe
+    from molann_b200.feature import Feature
+    rng = np.random.RandomState(21)
+    u = Universe(S.ala2_positions())
+    inp_ix = rng.permutation(22)[:17]
+    inp = u.select_ix(inp_ix)
+    pick = lambda m: u.select_ix(rng.permutation(inp_ix)[:m])
+    feats = [Feature("d", "dihedral", pick(4)), Feature("p", "position", pick(5)), Feature("b", "bond", pick(2)),
+             Feature("a", "angle", pick(3)), Feature("d2", "dihedral", pick(4)), Feature("p2", "position", pick(2))]
+    al_group = pick(6)
+    for ua in (False, True):
+        pp = PreprocessingANN(AlignmentLayer(al_group, inp), FeatureLayer(feats, inp, use_angle_value=ua)).cuda()
+        base = torch.from_numpy(u.atoms.positions[inp_ix])
+        x = base.unsqueeze(0) + 0.25 * torch.randn(500, 17, 3, generator=torch.Generator().manual_seed(2))
+        x = torch.bmm(x, S.random_rotations(500, torch.Generator().manual_seed(3), "cpu")) + 7.0
+        inp_list = inp_ix.tolist()
+        fl = [(f.get_type_id(), [inp_list.index(i) for i in f.atom_group.ix]) for f in feats]
+        aidx = [inp_list.index(i) for i in al_group.ix]
+        ref = torch.from_numpy(al_group.positions)
+        ref = ref - ref.mean(0)
+        fn = lambda xx: R.preprocess_forward(xx, aidx, ref.double(), fl, ua)
+        cot = torch.randn(500, pp.output_dimension(), generator=torch.Generator().manual_seed(4))
+        f64, gx64 = oracle_value_and_grad(fn, x, cot)
+        xd = dev(x).requires_grad_(True)
+        f = pp(xd)
+        (gx,) = torch.autograd.grad(f, xd, cot.cuda())
+        assert_parity(f.detach().cpu(), f64, None, TOL, "mixed feat ua=%s" % ua)
+        err = frame_rel_err(gx.cpu(), gx64)          # acos / atan2 derivative is ill-conditioned near 0, pi
+        assert float(err.median()) < 1e-5 and float((err > 1e-4).float().mean()) < 0.02
+
+
+def test_large_coordinate_offset():
+    spec = S.get_spec("C2")
+    g = golden("config_C2")
+    ws, bs = golden_weights(g, 3)
+    plan = CPlan(spec, ws, bs)
+    x = torch.from_numpy(g["x"]) + 1000.0
+    y64, gx64 = oracle_value_and_grad(oracle_model(spec, ws, bs), x, torch.from_numpy(g["cot"]))
+    y32, gx32 = oracle_value_and_grad(oracle_model(spec, ws, bs, torch.float32), x, torch.from_numpy(g["cot"]),
+                                      torch.float32)
+    assert_parity(plan.forward(dev(x)).cpu(), y64, y32, 1e-4, "offset y")
+    assert_parity(plan.backward(dev(x), dev(g["cot"])).cpu(), gx64, gx32, 1e-4, "offset gx")
+
+
+def test_full_size_properties_c2():
+    """BASELINE size (1 Mi frames): size-independent properties + a sampled oracle check."""
+    spec = S.get_spec("C2")
+    model, _ = S.build_model(spec)
+    model = model.cuda()
+    L = 1 << 20
+    x = S.make_frames(spec, L, device="cuda")
+    with torch.no_grad():
+        y = model(x)
+        assert torch.isfinite(y).all()
+        # frames are independent: any sub-batch / permutation gives bit-identical rows
+        perm = torch.randperm(L, device="cuda")
+        assert torch.equal(model(x[perm].contiguous()), y[perm])
+        assert torch.equal(model(x[12345:12345 + 777].contiguous()), y[12345:12345 + 777])
+        # rigid-motion invariance of the aligned model
+        Rm = S.random_rotations(L, torch.Generator(device="cuda").manual_seed(7), "cuda")
+        x2 = torch.bmm(x, Rm) + 3.0
+        assert float((model(x2) - y).abs().max()) < 2e-4
+    cot = torch.randn(L, 2, device="cuda")
+    xg = x.clone().requires_grad_(True)
+    (g1,) = torch.autograd.grad(model(xg), xg, cot)
+    (g2,) = torch.autograd.grad(model(xg), xg, 2.0 * cot)
+    assert torch.equal(g2, 2.0 * g1)                                   # linear in the cotangent, exactly
+    assert float(g1.sum(dim=1).abs().max()) < 1e-3 * float(g1.abs().max())      # translation invariance
+    sd = model.state_dict()
+    ws = [sd["ann_layers.%dth_layer.weight" % k].cpu() for k in (1, 2, 3)]
+    bs = [sd["ann_layers.%dth_layer.bias" % k].cpu() for k in (1, 2, 3)]
+    idx = torch.randint(0, L, (2000,), generator=torch.Generator().manual_seed(0))
+    y64, gx64 = oracle_value_and_grad(oracle_model(spec, ws, bs), x[idx.cuda()].cpu(), cot[idx.cuda()].cpu())
+    assert_parity(y[idx.cuda()].cpu(), y64, None, TOL, "full-size y sample")
+    assert_parity(g1[idx.cuda()].cpu(), gx64, None, 2e-5, "full-size gx sample")
+
+
+def test_c3_full_width_general_path():
+    """n = 2000 atoms, d = 800 -> [800,256,128,2]: warp-per-frame geometry + layered GEMMs."""
+    spec = S.get_spec("C3")
+    model, _ = S.build_model(spec)
+    sd = model.state_dict()
+    ws = [sd["ann_layers.%dth_layer.weight" % k] for k in (1, 2, 3)]
+    bs = [sd["ann_layers.%dth_layer.bias" % k] for k in (1, 2, 3)]
+    L = 96
+    x = S.make_frames(spec, L, seed=17)
+    cot = torch.randn(L, 2, generator=torch.Generator().manual_seed(5))
+    y64, gx64 = oracle_value_and_grad(oracle_model(spec, ws, bs), x, cot)
+    y32, gx32 = oracle_value_and_grad(oracle_model(spec, ws, bs, torch.float32), x, cot, torch.float32)
+    model = model.cuda()
+    xd = dev(x).requires_grad_(True)
+    y = model(xd)
+    (gx,) = torch.autograd.grad(y, xd, cot.cuda())
+    assert_parity(y.detach().cpu(), y64, y32, TOL, "C3 y")
+    assert_parity(gx.cpu(), gx64, gx32, 2e-5, "C3 gx")
+    assert int((gx.cpu() != 0).any(dim=2).sum(dim=1).max()) <= 200 + 400       # dense row, sparse support
+
+
+def test_torchscript_roundtrip_in_fresh_process(tmp_path):
+    spec = S.get_spec("C2")
+    model, _ = S.build_model(spec)
+    model = model.cuda()
+    x = S.make_frames(spec, 777, device="cuda")
+    cot = torch.randn(777, 2, device="cuda")
+    xg = x.clone().requires_grad_(True)
+    y = model(xg)
+    (gx,) = torch.autograd.grad(y, xg, cot)
+    scripted = torch.jit.script(model)
+    assert torch.equal(scripted(x), y.detach())
+    path = os.path.join(tmp_path, "molann.pt")
+    scripted.save(path)
+    torch.save({"x": x.cpu(), "cot": cot.cpu(), "y": y.detach().cpu(), "gx": gx.cpu()}, os.path.join(tmp_path, "io.pt"))
+    code = """
+import sys, torch
+torch.ops.load_library(sys.argv[1])            # a consumer only needs the shim library, not the Python package
+m = torch.jit.load(sys.argv[2]).cuda()
+io = torch.load(sys.argv[3])
+x = io['x'].cuda().requires_grad_(True)
+y = m(x)
+(gx,) = torch.autograd.grad(y, x, io['cot'].cuda())
+assert torch.equal(y.detach().cpu(), io['y']), 'forward differs'
+assert torch.equal(gx.cpu(), io['gx']), 'gradient differs'
+print('ROUNDTRIP_OK')
+"""
+    lib = os.path.join(ROOT, "molann_b200", "libmolann_b200_torch.so")
+    out = subprocess.run([sys.executable, "-c", code, lib, path, os.path.join(tmp_path, "io.pt")],
+                         capture_output=True, text=True, timeout=600)
+    assert "ROUNDTRIP_OK" in out.stdout, out.stdout + out.stderr
+
+
+def test_host_pipeline_end_to_end():
+    from molann_b200.stream import HostPipeline
+    spec = S.get_spec("C2")
+    model, _ = S.build_model(spec)
+    model = model.cuda()
+    L = 50000
+    xh = S.make_frames(spec, L).pin_memory()
+    yh = torch.empty(L, 2).pin_memory()
+    pipe = HostPipeline(model, 22, 2, chunk_frames=8192)
+    pipe.run(xh, yh)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ref = model(xh.cuda()).cpu()
+    assert torch.equal(yh, ref)
+    assert pipe.h2d_bytes == L * 22 * 12 and pipe.d2h_bytes == L * 2 * 4
+    coth = torch.randn(L, 2).pin_memory()
+    gxh = torch.empty(L, 22, 3).pin_memory()
+    pipe.run(xh, yh, coth, gxh)
+    torch.cuda.synchronize()
+    xg = xh.cuda().requires_grad_(True)
+    (gref,) = torch.autograd.grad(model(xg), xg, coth.cuda())
+    assert torch.equal(gxh, gref.cpu())
+
+
+def test_wrong_dtype_device_layout_raise():
+    spec = S.get_spec("C2")
+    model, _ = S.build_model(spec)
+    model = model.cuda()
+    x = S.make_frames(spec, 16, device="cuda")
+    with pytest.raises(RuntimeError, match="float32"):
+        model(x.double())
+    with pytest.raises(RuntimeError, match="contiguous"):
+        model(x.transpose(0, 1).contiguous().transpose(0, 1))
+    cpu_model, _ = S.build_model(spec)
+    with pytest.raises(RuntimeError, match="device"):
+        cpu_model(x)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_sharded_inference_is_bitwise_identical():
+    from molann_b200.shard import frame_range
+    spec = S.get_spec("C2")
+    model, _ = S.build_model(spec)
+    x = S.make_frames(spec, 100001)
+    with torch.no_grad():
+        full = model.cuda(0)(x.cuda(0)).cpu()
+        parts = []
+        G = torch.cuda.device_count()
+        for r in range(G):
+            s, e = frame_range(x.shape[0], r, G)
+            m = S.build_model(spec)[0].cuda(r)
+            with torch.cuda.device(r):
+                parts.append(m(x[s:e].cuda(r)).cpu())
+    assert torch.equal(torch.cat(parts), full)
