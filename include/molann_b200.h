@@ -114,6 +114,8 @@ int molann_b200_align_backward(const MolannPlan* plan, const float* x, const flo
 /* Tuning / introspection: which kernel family the dispatcher picks for this plan.
  * 0 = general (warp-per-frame geometry + layered GEMMs), 1 = fused small-system kernel. */
 int molann_b200_path_for(const MolannPlan* plan, int want_backward);
+/* Finer: 0 = general, 1 = fused FFMA kernel, 2 = fused tcgen05 (3xTF32 tensor-core MLP) kernel. */
+int molann_b200_kernel_family(const MolannPlan* plan, int want_backward);
 
 #ifdef __cplusplus
 }

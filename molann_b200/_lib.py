@@ -56,6 +56,7 @@ def cabi():
     lib.molann_b200_launch_count.restype = i64
     lib.molann_b200_plan_validate.argtypes = [P]
     lib.molann_b200_path_for.argtypes = [P, ctypes.c_int]
+    lib.molann_b200_kernel_family.argtypes = [P, ctypes.c_int]
     lib.molann_b200_workspace_bytes.restype = sz
     lib.molann_b200_workspace_bytes.argtypes = [P, i64, ctypes.c_int]
     lib.molann_b200_forward.argtypes = [P, vp, i64, vp, vp, sz, vp]

@@ -186,7 +186,7 @@ template <int F, int NT>
 __global__ void __launch_bounds__(NT)
 fused_small_forward_kernel(const __grid_constant__ DevPlan p, const __grid_constant__ SmallLayout lay,
                            const float* __restrict__ x, float* __restrict__ y, long long L, int use_tma) {
-  extern __shared__ __align__(128) unsigned char smem[];
+  extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x;
   const int n3 = 3 * p.n_inp;
   float* xs = reinterpret_cast<float*>(smem + lay.xs_off);
@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(NT)
 fused_small_backward_kernel(const __grid_constant__ DevPlan p, const __grid_constant__ SmallLayout lay,
                             const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ gx,
                             long long L, int use_tma) {
-  extern __shared__ __align__(128) unsigned char smem[];
+  extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x;
   const int n3 = 3 * p.n_inp;
   float* xs = reinterpret_cast<float*>(smem + lay.xs_off);

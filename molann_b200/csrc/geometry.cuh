@@ -94,19 +94,26 @@ __device__ __forceinline__ void dominant_eigvec4(float (&a)[4][4], float (&q)[4]
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) v[i][j] = (i == j) ? 1.0f : 0.0f;
+  // Each lane latches its own convergence, so a frame's result never depends on its warp-mates (frames are
+  // bitwise independent of batch composition / sharding); the vote only decides when the warp leaves the loop.
+  bool done = false;
 #pragma unroll 1
   for (int sweep = 0; sweep < 10; ++sweep) {
-    const float off = a[0][1] * a[0][1] + a[0][2] * a[0][2] + a[0][3] * a[0][3] + a[1][2] * a[1][2] +
-                      a[1][3] * a[1][3] + a[2][3] * a[2][3];
-    const float dg = a[0][0] * a[0][0] + a[1][1] * a[1][1] + a[2][2] * a[2][2] + a[3][3] * a[3][3];
-    const bool done = !(off > 4e-14f * dg);
+    if (!done) {
+      const float off = a[0][1] * a[0][1] + a[0][2] * a[0][2] + a[0][3] * a[0][3] + a[1][2] * a[1][2] +
+                        a[1][3] * a[1][3] + a[2][3] * a[2][3];
+      const float dg = a[0][0] * a[0][0] + a[1][1] * a[1][1] + a[2][2] * a[2][2] + a[3][3] * a[3][3];
+      done = !(off > 4e-14f * dg);
+    }
     if (__all_sync(0xffffffffu, done)) break;
-    jacobi_rot<0, 1, 2, 3>(a, v);
-    jacobi_rot<0, 2, 1, 3>(a, v);
-    jacobi_rot<0, 3, 1, 2>(a, v);
-    jacobi_rot<1, 2, 0, 3>(a, v);
-    jacobi_rot<1, 3, 0, 2>(a, v);
-    jacobi_rot<2, 3, 0, 1>(a, v);
+    if (!done) {
+      jacobi_rot<0, 1, 2, 3>(a, v);
+      jacobi_rot<0, 2, 1, 3>(a, v);
+      jacobi_rot<0, 3, 1, 2>(a, v);
+      jacobi_rot<1, 2, 0, 3>(a, v);
+      jacobi_rot<1, 3, 0, 2>(a, v);
+      jacobi_rot<2, 3, 0, 1>(a, v);
+    }
   }
   int best = 0;
   float lam = a[0][0];

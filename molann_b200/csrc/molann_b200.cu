@@ -12,6 +12,7 @@
 
 #include "common.cuh"
 #include "fused_small.cuh"
+#include "fused_tc.cuh"
 #include "general.cuh"
 
 using namespace molann;
@@ -253,6 +254,72 @@ int launch_small_backward(const DevPlan& dp, const SmallLayout& lay, const float
   return post_launch();
 }
 
+// ---------------------------------------------------------------------------------------------
+// fused tensor-core path (tcgen05 3xTF32 MLP), forward
+// ---------------------------------------------------------------------------------------------
+struct TcChoice {
+  bool ok = false;
+  TcLayout lay;
+};
+
+// MOLANN_B200_TC = 0 disables the tensor-core kernels (A/B testing against the FFMA kernels).
+TcChoice choose_tc(const MolannPlan* p, bool backward, const DeviceInfo& dev) {
+  TcChoice ch;
+  std::memset(&ch.lay, 0, sizeof(ch.lay));
+  if (backward) return ch;
+  if (env_int("MOLANN_B200_TC", 1) == 0 || env_int("MOLANN_B200_PATH", -1) == 0) return ch;
+  const int nl = p->n_layers;
+  if (nl < 2) return ch;
+  for (int k = 0; k < nl; ++k)
+    if (p->dims[k] > TC_MAXW) return ch;
+  if (p->dims[nl] > 8) return ch;
+  if ((long long)p->n_entries * ENTRY_INTS * 4 > 32 * 1024) return ch;
+  if ((long long)TC_F * 3 * p->n_inp * 4 > 96 * 1024) return ch;
+  TcLayout& lay = ch.lay;
+  Carver c;
+  lay.mbar_off = c.take(16, 16);
+  lay.tptr_off = c.take(16, 16);
+  lay.xs_off = c.take(TC_F * 3 * p->n_inp * 4, 128);
+  lay.kp[0] = round_up(p->dims[0], 8);
+  lay.feat_off = c.take(lay.kp[0] * TC_F * 4, 128);
+  for (int k = 0; k < nl - 1; ++k) {
+    lay.kp[k] = round_up(p->dims[k], 8);
+    lay.np[k] = round_up(p->dims[k + 1], 16);
+    lay.bhi_off[k] = c.take(lay.kp[k] * lay.np[k] * 4, 1024);
+    lay.blo_off[k] = c.take(lay.kp[k] * lay.np[k] * 4, 1024);
+    lay.bias_off[k] = c.take(lay.np[k] * 4, 16);
+  }
+  lay.wlast_off = c.take(p->dims[nl] * TC_MAXW * 4, 16);
+  lay.blast_off = c.take(p->dims[nl] * 4, 16);
+  lay.aidx_off = c.take((p->n_align > 0 ? p->n_align : 1) * 4, 16);
+  lay.ref_off = c.take((p->n_align > 0 ? 3 * p->n_align : 1) * 4, 16);
+  lay.ent_off = c.take(p->n_entries * ENTRY_INTS * 4, 16);
+  lay.total_bytes = round_up(c.off, 128);
+  // exactly two CTAs (2 x 256 TMEM columns) may share an SM: keep the footprint above a third of it
+  const int min_bytes = dev.max_smem_optin / 3 + 1024;
+  if (lay.total_bytes < min_bytes) lay.total_bytes = round_up(min_bytes, 128);
+  if (lay.total_bytes > dev.max_smem_optin) return ch;
+  ch.ok = true;
+  return ch;
+}
+
+int launch_tc_forward(const DevPlan& dp, const TcLayout& lay, const float* x, float* y, long long L,
+                      const DeviceInfo& dev, cudaStream_t st) {
+  auto kern = fused_tc_forward_kernel;
+  int s = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.total_bytes));
+  if (s) return s;
+  int occ = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TC_F, lay.total_bytes);
+  if (occ < 1) occ = 1;
+  if (occ > 2) occ = 2;
+  const long long ntiles = (L + TC_F - 1) / TC_F;
+  long long grid = (long long)dev.sm_count * occ;
+  if (grid > ntiles) grid = ntiles;
+  const int use_tma = ((reinterpret_cast<uintptr_t>(x) & 15u) == 0) && ((TC_F * 3 * dp.n_inp * 4) % 16 == 0);
+  kern<<<(unsigned)grid, TC_F, lay.total_bytes, st>>>(dp, lay, x, y, L, use_tma);
+  return post_launch();
+}
+
 #define SMALL_DISPATCH(ch, FN, ...)                                   \
   ((ch).F == 128 ? ((ch).NT == 256 ? FN<128, 256>(__VA_ARGS__) : FN<128, 128>(__VA_ARGS__)) \
                  : ((ch).NT == 256 ? FN<64, 256>(__VA_ARGS__) : FN<64, 128>(__VA_ARGS__)))
@@ -444,9 +511,15 @@ int64_t molann_b200_launch_count(void) { return (int64_t)g_launches.load(std::me
 int molann_b200_plan_validate(const MolannPlan* plan) { return validate_full(plan); }
 
 int molann_b200_path_for(const MolannPlan* plan, int want_backward) {
+  const int fam = molann_b200_kernel_family(plan, want_backward);
+  return fam < 0 ? fam : (fam > 0 ? 1 : 0);
+}
+
+int molann_b200_kernel_family(const MolannPlan* plan, int want_backward) {
   if (validate_full(plan) != MOLANN_OK) return -1;
   DeviceInfo dev = device_info();
   if (!dev.ok) { dev.sm_count = 148; dev.max_smem_optin = 232448; }   // B200 figures, for offline queries
+  if (choose_tc(plan, want_backward != 0, dev).ok) return 2;
   return choose_small(plan, want_backward != 0, dev).ok ? 1 : 0;
 }
 
@@ -469,6 +542,8 @@ int molann_b200_forward(const MolannPlan* plan, const float* x, int64_t L, float
   const DeviceInfo dev = device_info();
   if (!dev.ok) return MOLANN_ERR_CUDA;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const TcChoice tc = choose_tc(plan, false, dev);
+  if (tc.ok) return launch_tc_forward(to_dev(plan), tc.lay, x, y, (long long)L, dev, st);
   const SmallChoice ch = choose_small(plan, false, dev);
   if (ch.ok) {
     const DevPlan dp = to_dev(plan);

@@ -1,0 +1,125 @@
+// tc.cuh -- sm_100a tensor-core primitives (tcgen05 + TMEM) used by the fused kernels, as inline PTX.
+//
+// The MLP contraction runs as 3xTF32: every fp32 operand is split x = hi + lo with hi = x & 0xffffe000
+// (the 19 bits a TF32 multiplier consumes) and lo = x - hi (exact in fp32); D += A_hi B_hi + A_lo B_hi +
+// A_hi B_lo with fp32 accumulation in TMEM reproduces an fp32 product to ~2^-21 relative, inside the
+// 1e-5 contract that plain TF32 (2^-11) would break.
+//
+// Operand conventions (cta_group::1, M = 128 rows = frames):
+//   A  [128 x K]  in TMEM: lane = row, one 32-bit column per k (written with tcgen05.st by the thread
+//                 that owns the row) or in smem (K-major, no swizzle);
+//   B  [N x K]    in smem, K-major, no swizzle, "chunk-major": element (n, k) lives at
+//                 ((k/4) * N + n) * 16 + (k%4) * 4 bytes  ->  core matrices (8 rows x 16 B) are contiguous,
+//                 SBO (8-row group stride) = 128 B, LBO (K-chunk stride) = N * 16 B;
+//   D  [128 x N]  fp32 accumulator in TMEM: lane = row, column = n.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace molann {
+
+// ---- TMEM allocation (one full warp) ---------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before_sync() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after_sync() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// 16 consecutive columns of this thread's lane  <->  16 registers
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&r)[16]) {
+  uint32_t u[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
+        "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) r[i] = __uint_as_float(u[i]);
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&u)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(
+          taddr),
+      "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7]), "r"(u[8]), "r"(u[9]),
+      "r"(u[10]), "r"(u[11]), "r"(u[12]), "r"(u[13]), "r"(u[14]), "r"(u[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&u)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(u[0]),
+               "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7])
+               : "memory");
+}
+
+// ---- descriptors -----------------------------------------------------------------------------
+// shared-memory matrix descriptor, K-major, SWIZZLE_NONE, Blackwell version field = 1
+__device__ __forceinline__ uint64_t smem_desc_kmajor(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+// instruction descriptor: D = F32, A = B = TF32, both K-major, dense
+__host__ __device__ inline uint32_t idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---- MMA issue (ONE thread) --------------------------------------------------------------------
+// D[tmem] (+)= A[tmem] * B[smem]^T
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T
+__device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// all MMAs issued so far by this thread arrive (once) on the mbarrier when they complete
+__device__ __forceinline__ void mma_commit(void* mbar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar))
+               : "memory");
+}
+
+// ---- 3xTF32 split ---------------------------------------------------------------------------------
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(x) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+
+// byte offset of element (row n, column k) inside a chunk-major K-major operand with `rows` rows
+__host__ __device__ inline uint32_t chunk_major_offset(int n, int k, int rows) {
+  return (uint32_t)(((k >> 2) * rows + n) * 16 + (k & 3) * 4);
+}
+
+}  // namespace molann

@@ -279,7 +279,11 @@ struct MolannFn : public torch::autograd::Function<MolannFn> {
     auto saved = ctx->get_saved_variables();
     const int64_t np = ctx->saved_data["n_params"].toInt();
     std::vector<Tensor> params(saved.begin() + 4, saved.begin() + 4 + np);
-    const bool want_params = ctx->saved_data["want_params"].toBool();
+    // parameter gradients only when the engine actually asks for them (torch.autograd.grad(y, x) for the
+    // biasing-force path does not, even if the Linear parameters have requires_grad=True)
+    bool want_params = false;
+    if (ctx->saved_data["want_params"].toBool())
+      for (int64_t i = 0; i < np; ++i) want_params = want_params || ctx->needs_input_grad(4 + i);
     auto g = molann_bwd_impl(saved[0], saved[1], saved[2], saved[3], ctx->saved_data["d_feat"].toInt(),
                              ctx->saved_data["use_angle_value"].toBool(), params, ctx->saved_data["act"].toInt(),
                              grads[0], want_params);

@@ -46,18 +46,25 @@ def test_native_library_is_loaded_and_counts_launches():
     assert int(torch.ops.molann_b200.launch_count()) == _lib.launch_count()
 
 
-@pytest.mark.parametrize("path", ["auto", "general"])
+@pytest.mark.parametrize("path", ["auto", "ffma", "general"])
 @pytest.mark.parametrize("name", ["C1", "C2", "C3s"])
 def test_cabi_against_reference_goldens(name, path, monkeypatch):
+    """auto = best fused kernel (tcgen05 3xTF32 MLP where eligible), ffma = fused CUDA-core kernel,
+    general = warp-per-frame geometry + layered GEMMs."""
     if path == "general":
         monkeypatch.setenv("MOLANN_B200_PATH", "0")
+    if path == "ffma":
+        monkeypatch.setenv("MOLANN_B200_TC", "0")
     spec = S.get_spec(name)
     g = golden("config_" + name)
     ws, bs = golden_weights(g, len(spec.layer_dims) - 1)
     plan = CPlan(spec, ws, bs)
-    want = 1 if path == "auto" else 0
+    want = 0 if path == "general" else 1
     import ctypes
     assert plan.lib.molann_b200_path_for(ctypes.byref(plan.p), 0) == want
+    if name == "C2":
+        fam = plan.lib.molann_b200_kernel_family(ctypes.byref(plan.p), 0)
+        assert fam == {"auto": 2, "ffma": 1, "general": 0}[path]
     x = dev(g["x"])
     y = plan.forward(x)
     assert_parity(y.cpu(), g["y64"], g["y32"], TOL, "%s y" % name)
