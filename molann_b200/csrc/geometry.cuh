@@ -27,6 +27,7 @@ inline float __shfl_xor_sync(unsigned, float v, int) { return v; }
 inline bool __all_sync(unsigned, bool p) { return p; }
 inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 inline float __ldg(const float* p) { return *p; }
+inline float __fdividef(float a, float b) { return a / b; }
 #else
 #include <cuda_runtime.h>
 #endif
@@ -47,46 +48,67 @@ __device__ __forceinline__ float gsum(float v) {
 // ------------------------------------------------------------------------------------------------
 // 4x4 symmetric eigenproblem: cyclic Jacobi, everything in registers (indices are compile-time).
 // ------------------------------------------------------------------------------------------------
-template <int I, int J>
-__device__ __forceinline__ float& sym(float (&a)[4][4]) {
-  return (I < J) ? a[I][J] : a[J][I];
+// Jacobi rotation in the (P,Q) plane: (c, s) with c^2 + s^2 = 1 to fp32 rounding, chosen to zero a[P][Q].
+//   t = sgn(d) 2 a_pq / (|d| + sqrt(d^2 + 4 a_pq^2)),  d = a_qq - a_pp   (the smaller root of t^2 + (d/a_pq) t - 1)
+// Approximate MUFU ops (rsqrt / rcp) only perturb the ANGLE (convergence stays quadratic); orthogonality of
+// the rotation rests on c = rsqrt(1 + t^2), which gets one Newton step so that c^2 (1 + t^2) = 1 to rounding.
+__device__ __forceinline__ void jacobi_params(float app, float aqq, float apq, float& c, float& s, float& t) {
+  const float d = aqq - app;
+  const float r2 = fmaf(d, d, 4.0f * apq * apq);
+  float t_ = 0.0f;
+  if (r2 > 0.0f) {
+    const float r = r2 * rsqrtf(r2);
+    t_ = __fdividef(copysignf(2.0f * apq, d * apq), fabsf(d) + r);     // sign(t) = sign(d * a_pq)
+    if (d == 0.0f) t_ = copysignf(1.0f, apq);
+  }
+  const float w = fmaf(t_, t_, 1.0f);
+  float c_ = rsqrtf(w);
+  c_ = c_ * fmaf(-0.5f * w, c_ * c_, 1.5f);
+  t = t_;
+  c = c_;
+  s = t_ * c_;
 }
 
+// apply the rotation of plane (P,Q) to the symmetric matrix (upper triangle in `a`) and accumulate it in v
 template <int P, int Q, int R1, int R2>
-__device__ __forceinline__ void jacobi_rot(float (&a)[4][4], float (&v)[4][4]) {
+__device__ __forceinline__ void jacobi_apply(float (&a)[4][4], float (&v)[4][4], float c, float s, float t) {
   const float apq = a[P][Q];
-  if (apq != 0.0f) {
-    const float theta = 0.5f * (a[Q][Q] - a[P][P]) / apq;
-    float t = 1.0f / (fabsf(theta) + sqrtf(fmaf(theta, theta, 1.0f)));
-    t = copysignf(t, theta);
-    const float c = rsqrtf(fmaf(t, t, 1.0f));
-    const float s = t * c;
-    const float tau = s / (1.0f + c);
-    a[P][P] = fmaf(-t, apq, a[P][P]);
-    a[Q][Q] = fmaf(t, apq, a[Q][Q]);
-    a[P][Q] = 0.0f;
-    {
-      float& x1 = sym<R1, P>(a);
-      float& y1 = sym<R1, Q>(a);
-      const float g = x1, h = y1;
-      x1 = g - s * fmaf(tau, g, h);
-      y1 = h + s * fmaf(-tau, h, g);
-      float& x2 = sym<R2, P>(a);
-      float& y2 = sym<R2, Q>(a);
-      const float g2 = x2, h2 = y2;
-      x2 = g2 - s * fmaf(tau, g2, h2);
-      y2 = h2 + s * fmaf(-tau, h2, g2);
-    }
+  a[P][P] = fmaf(-t, apq, a[P][P]);
+  a[Q][Q] = fmaf(t, apq, a[Q][Q]);
+  a[P][Q] = 0.0f;
+  {
+    float& x1 = (R1 < P) ? a[R1][P] : a[P][R1];
+    float& y1 = (R1 < Q) ? a[R1][Q] : a[Q][R1];
+    const float g = x1, h = y1;
+    x1 = fmaf(c, g, -s * h);
+    y1 = fmaf(s, g, c * h);
+    float& x2 = (R2 < P) ? a[R2][P] : a[P][R2];
+    float& y2 = (R2 < Q) ? a[R2][Q] : a[Q][R2];
+    const float g2 = x2, h2 = y2;
+    x2 = fmaf(c, g2, -s * h2);
+    y2 = fmaf(s, g2, c * h2);
+  }
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const float g = v[r][P], h = v[r][Q];
-      v[r][P] = g - s * fmaf(tau, g, h);
-      v[r][Q] = h + s * fmaf(-tau, h, g);
-    }
+  for (int r = 0; r < 4; ++r) {
+    const float g = v[r][P], h = v[r][Q];
+    v[r][P] = fmaf(c, g, -s * h);
+    v[r][Q] = fmaf(s, g, c * h);
   }
 }
 
+// Two rotations on DISJOINT planes (P,Q) and (R,S): their parameters depend on disjoint matrix entries, so
+// both long-latency parameter chains are issued back to back (ILP 2) before the updates are applied.
+template <int P, int Q, int R, int S>
+__device__ __forceinline__ void jacobi_pair(float (&a)[4][4], float (&v)[4][4]) {
+  float c1, s1, t1, c2, s2, t2;
+  jacobi_params(a[P][P], a[Q][Q], a[P][Q], c1, s1, t1);
+  jacobi_params(a[R][R], a[S][S], a[R][S], c2, s2, t2);
+  jacobi_apply<P, Q, R, S>(a, v, c1, s1, t1);
+  jacobi_apply<R, S, P, Q>(a, v, c2, s2, t2);
+}
+
 // Dominant (largest-eigenvalue) unit eigenvector of the symmetric matrix whose upper triangle is `a`.
+// Parallel-ordered cyclic Jacobi: a sweep is {(0,1),(2,3)}, {(0,2),(1,3)}, {(0,3),(1,2)}.
 // Must be called by all 32 lanes of a warp (uses a warp vote for a uniform exit).
 __device__ __forceinline__ void dominant_eigvec4(float (&a)[4][4], float (&q)[4]) {
   float v[4][4];
@@ -98,7 +120,7 @@ __device__ __forceinline__ void dominant_eigvec4(float (&a)[4][4], float (&q)[4]
   // bitwise independent of batch composition / sharding); the vote only decides when the warp leaves the loop.
   bool done = false;
 #pragma unroll 1
-  for (int sweep = 0; sweep < 10; ++sweep) {
+  for (int sweep = 0; sweep < 12; ++sweep) {
     if (!done) {
       const float off = a[0][1] * a[0][1] + a[0][2] * a[0][2] + a[0][3] * a[0][3] + a[1][2] * a[1][2] +
                         a[1][3] * a[1][3] + a[2][3] * a[2][3];
@@ -107,12 +129,9 @@ __device__ __forceinline__ void dominant_eigvec4(float (&a)[4][4], float (&q)[4]
     }
     if (__all_sync(0xffffffffu, done)) break;
     if (!done) {
-      jacobi_rot<0, 1, 2, 3>(a, v);
-      jacobi_rot<0, 2, 1, 3>(a, v);
-      jacobi_rot<0, 3, 1, 2>(a, v);
-      jacobi_rot<1, 2, 0, 3>(a, v);
-      jacobi_rot<1, 3, 0, 2>(a, v);
-      jacobi_rot<2, 3, 0, 1>(a, v);
+      jacobi_pair<0, 1, 2, 3>(a, v);
+      jacobi_pair<0, 2, 1, 3>(a, v);
+      jacobi_pair<0, 3, 1, 2>(a, v);
     }
   }
   int best = 0;

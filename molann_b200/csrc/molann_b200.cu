@@ -25,6 +25,7 @@ thread_local int t_last_cuda_error = 0;
 struct DeviceInfo {
   int sm_count = 0;
   int max_smem_optin = 0;
+  int smem_per_sm = 0;
   bool ok = false;
 };
 
@@ -35,6 +36,7 @@ DeviceInfo device_info() {
   if (cudaGetDevice(&dev) != cudaSuccess) return d;
   if (cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return d;
   if (cudaDeviceGetAttribute(&d.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return d;
+  if (cudaDeviceGetAttribute(&d.smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev) != cudaSuccess) return d;
   d.ok = true;
   return d;
 }
@@ -308,8 +310,9 @@ int launch_tc_forward(const DevPlan& dp, const TcLayout& lay, const float* x, fl
   auto kern = fused_tc_forward_kernel;
   int s = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.total_bytes));
   if (s) return s;
-  int occ = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TC_F, lay.total_bytes);
+  // ask for the full shared-memory carveout so that two CTAs (2 x 256 TMEM columns) share an SM
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  int occ = dev.smem_per_sm / (lay.total_bytes + 1024);
   if (occ < 1) occ = 1;
   if (occ > 2) occ = 2;
   const long long ntiles = (L + TC_F - 1) / TC_F;
@@ -518,7 +521,7 @@ int molann_b200_path_for(const MolannPlan* plan, int want_backward) {
 int molann_b200_kernel_family(const MolannPlan* plan, int want_backward) {
   if (validate_full(plan) != MOLANN_OK) return -1;
   DeviceInfo dev = device_info();
-  if (!dev.ok) { dev.sm_count = 148; dev.max_smem_optin = 232448; }   // B200 figures, for offline queries
+  if (!dev.ok) { dev.sm_count = 148; dev.max_smem_optin = 232448; dev.smem_per_sm = 233472; }   // B200 figures
   if (choose_tc(plan, want_backward != 0, dev).ok) return 2;
   return choose_small(plan, want_backward != 0, dev).ok ? 1 : 0;
 }
