@@ -101,6 +101,12 @@ int molann_b200_backward(const MolannPlan* plan, const float* x, const float* gy
                          float* const* gW, float* const* gb,
                          void* workspace, size_t workspace_bytes, void* stream);
 
+/* Biasing-force entry point: y = model(x) AND gx = d<gy,y>/dx in one pass over x (one fused kernel when the
+ * plan is eligible, else forward + backward).  Not in the reference tree; it is what an MD-engine plugin that
+ * loads the exported model does with two autograd calls (README.rst:51, molann/ann.py:109-111). */
+int molann_b200_value_and_grad(const MolannPlan* plan, const float* x, const float* gy, int64_t L, float* y,
+                               float* gx, void* workspace, size_t workspace_bytes, void* stream);
+
 /* feat[L, d_feat] = features(align(x)); the MLP fields of the plan are ignored */
 int molann_b200_preprocess_forward(const MolannPlan* plan, const float* x, int64_t L, float* feat, void* stream);
 int molann_b200_preprocess_backward(const MolannPlan* plan, const float* x, const float* gfeat, int64_t L,

@@ -61,6 +61,7 @@ def cabi():
     lib.molann_b200_workspace_bytes.argtypes = [P, i64, ctypes.c_int]
     lib.molann_b200_forward.argtypes = [P, vp, i64, vp, vp, sz, vp]
     lib.molann_b200_backward.argtypes = [P, vp, vp, i64, vp, vp, vp, vp, sz, vp]
+    lib.molann_b200_value_and_grad.argtypes = [P, vp, vp, i64, vp, vp, vp, sz, vp]
     lib.molann_b200_preprocess_forward.argtypes = [P, vp, i64, vp, vp]
     lib.molann_b200_preprocess_backward.argtypes = [P, vp, vp, i64, vp, vp]
     lib.molann_b200_align_forward.argtypes = [P, vp, i64, vp, vp]

@@ -9,7 +9,7 @@ float32 CUDA tensors, anything else raises.
 At construction each layer compiles its atom indices into int32 *program* buffers (registered
 ``persistent=False`` so ``state_dict()`` stays identical to the reference's, and moved by ``.to(device)``).
 """
-from typing import List
+from typing import List, Optional
 
 import pandas as pd
 import torch
@@ -288,6 +288,39 @@ class MolANN(torch.nn.Module):
     def get_preprocessing_layer(self):
         """the :class:`PreprocessingANN` of this model"""
         return self.preprocessing_layer
+
+    @torch.jit.export
+    def value_and_grad(self, x, cotangent):
+        """``(y, d<cotangent, y>/dx)`` in ONE fused pass over ``x`` (the biasing-force path of MD plugins).
+
+        Not part of the reference API: it replaces ``y = model(x); torch.autograd.grad(y, x, cotangent)``
+        (two passes over the coordinates) when no autograd graph is needed.  ``cotangent``: ``[l, k]``.
+        """
+        assert x.size(1) == self.preprocessing_layer.feature_layer.input_atom_num and x.size(2) == 3, \
+            'Input should be a 3d torch tensor with sizes [*, n_inp, 3]'
+        if not self._fused:
+            xg = x.detach().requires_grad_(True)
+            y = self.forward(xg)
+            cots: List[Optional[torch.Tensor]] = [cotangent]
+            g = torch.autograd.grad([y], [xg], cots)[0]
+            assert g is not None
+            return y.detach(), g
+        else:
+            flayer = self.preprocessing_layer.feature_layer
+            params: List[torch.Tensor] = []
+            for layer in self.ann_layers:
+                if hasattr(layer, 'weight'):
+                    params.append(layer.weight)
+                    params.append(layer.bias)
+            if self._fused_align:
+                return torch.ops.molann_b200.value_and_grad(
+                    x, cotangent, self.preprocessing_layer.align_layer._align_idx,
+                    self.preprocessing_layer.align_layer.ref_x, flayer._entries, flayer._dim,
+                    flayer.use_angle_value, params, self._act_id)
+            else:
+                return torch.ops.molann_b200.value_and_grad(
+                    x, cotangent, flayer._no_idx, flayer._no_ref, flayer._entries, flayer._dim,
+                    flayer.use_angle_value, params, self._act_id)
 
     def forward(self, x):
         """the forward map ``[l, n_inp, 3] -> [l, k]``"""

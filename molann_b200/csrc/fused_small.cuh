@@ -170,6 +170,10 @@ struct TileGIn {       // feature cotangent reader
   int f;
   int F;
   __device__ __forceinline__ float operator()(int col) const { return base[col * F + f]; }
+  __device__ __forceinline__ void load2(int col, float& a, float& b) const { a = (*this)(col); b = (*this)(col + 1); }
+  __device__ __forceinline__ void load3(int col, float& a, float& b, float& c) const {
+    a = (*this)(col); b = (*this)(col + 1); c = (*this)(col + 2);
+  }
 };
 struct RowAcc {        // plain accumulation into this thread's private gradient row
   float* row;

@@ -3,8 +3,9 @@
 // Tile = 128 frames = 128 threads = 128 TMEM lanes: thread t owns frame t of the tile end to end.
 //   1. TMA bulk copy stages the tile's coordinates (one contiguous byte range of x) into smem;
 //   2. thread-per-frame Kabsch (Jacobi on Horn's 4x4) + feature program -> feature row;
-//   3. the row is split into TF32 hi/lo and written to TMEM as the A operand (tcgen05.st) -- activations
-//      never touch shared memory; weights (hi/lo, chunk-major K-major) sit in smem for the whole kernel;
+//   3. every feature value is split into TF32 hi/lo and written straight to TMEM as the A operand
+//      (tcgen05.st, warp-uniform column) -- features and activations never touch shared memory; weights
+//      (hi/lo, chunk-major K-major) sit in smem for the whole kernel;
 //   4. one thread issues tcgen05.mma (3 per K-step: hi*hi + lo*hi + hi*lo, fp32 accumulate in TMEM),
 //      commits to an mbarrier; every thread reads its accumulator row back (tcgen05.ld), applies
 //      bias + activation, splits, and stores the next layer's A operand;
@@ -24,9 +25,11 @@ constexpr int TC_MAXW = 64;        // widest feature / hidden layer handled by t
 constexpr int TC_TMEM_COLS = 256;  // three 64-column regions (A_hi, A_lo, D) rounded up to a power of two
 
 struct TcLayout {
-  int xs_off, feat_off;              // coordinate tile [F][3n]; feature staging [Kp0][F]
+  int xs_off;                        // coordinate tile [F][3n] (forward kernel)
   int bhi_off[MOLANN_MAX_LAYERS];    // per MMA layer: weights hi / lo, chunk-major [Kp/4][Np][4]
   int blo_off[MOLANN_MAX_LAYERS];
+  int thi_off[MOLANN_MAX_LAYERS];    // transposed weights (backward), chunk-major [Np/4][Kp][4]
+  int tlo_off[MOLANN_MAX_LAYERS];
   int bias_off[MOLANN_MAX_LAYERS];   // padded biases
   int kp[MOLANN_MAX_LAYERS];         // padded K (multiple of 8)
   int np[MOLANN_MAX_LAYERS];         // padded N (multiple of 16)
@@ -56,16 +59,85 @@ __device__ __forceinline__ float act_forward_fast(float v, int act) {
   }
 }
 
+// activation value h and derivative d = act'(v) from ONE exponential.  The derivative is formed from
+// (e, r) directly -- d = 4 e r^2 for tanh -- so saturated units keep full relative accuracy, which
+// 1 - h*h (cancellation on the rounded h) cannot give.
+__device__ __forceinline__ void act_value_and_grad(float v, int act, float& h, float& d) {
+  if (act == ACT_TANH) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(v * 2.8853900817779268f, 126.0f)));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    h = fmaf(-2.0f, r, 1.0f);
+    d = 4.0f * (e * r) * r;
+  } else if (act == ACT_SIGMOID) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(v * -1.4426950408889634f, 126.0f)));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    h = r;
+    d = (e * r) * r;
+  } else if (act == ACT_RELU) {
+    h = fmaxf(v, 0.f);
+    d = v > 0.f ? 1.0f : 0.f;
+  } else {
+    h = v;
+    d = 1.0f;
+  }
+}
+
 // round-to-nearest TF32 split: |x - hi - lo| <= 2^-22 |x| once the MMA truncates lo to TF32
 __device__ __forceinline__ void split_tf32_rn(float x, uint32_t& hi, uint32_t& lo) {
   hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
   lo = __float_as_uint(x - __uint_as_float(hi));
 }
 
+// Feature column writer: value -> TF32 hi/lo -> this thread's TMEM lane (column = feature index).
+struct TmemFeatOut {
+  uint32_t hi_addr, lo_addr;
+  __device__ __forceinline__ void operator()(int col, float v) {
+    uint32_t hi, lo;
+    split_tf32_rn(v, hi, lo);
+    tmem_st1(hi_addr + col, hi);
+    tmem_st1(lo_addr + col, lo);
+  }
+};
+// Feature-cotangent reader straight from the accumulator columns of this thread's TMEM lane.
+struct TmemGIn {
+  uint32_t addr;
+  __device__ __forceinline__ float operator()(int col) const {
+    const float v = tmem_ld1_nowait(addr + col);
+    tmem_wait_ld();
+    return v;
+  }
+  __device__ __forceinline__ void load2(int col, float& a, float& b) const {
+    a = tmem_ld1_nowait(addr + col);
+    b = tmem_ld1_nowait(addr + col + 1);
+    tmem_wait_ld();
+  }
+  __device__ __forceinline__ void load3(int col, float& a, float& b, float& c) const {
+    a = tmem_ld1_nowait(addr + col);
+    b = tmem_ld1_nowait(addr + col + 1);
+    c = tmem_ld1_nowait(addr + col + 2);
+    tmem_wait_ld();
+  }
+};
+
+// zero the first `kp` hi/lo columns of the A operand (padding columns must not hold stale activations)
+__device__ __forceinline__ void zero_a_operand(uint32_t lane_addr, uint32_t col_hi, uint32_t col_lo, int kp) {
+  uint32_t z[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) z[i] = 0u;
+  for (int c = 0; c < kp; c += 16) {
+    tmem_st16(lane_addr + col_hi + c, z);
+    tmem_st16(lane_addr + col_lo + c, z);
+  }
+  tmem_wait_st();
+}
+
 // Split weights of MMA layer k into chunk-major hi/lo smem operands (zero padded to [np][kp]).
 __device__ __forceinline__ void stage_tc_weights(const float* __restrict__ Wg, const float* __restrict__ bg, int K,
                                                  int N, int kp, int np, unsigned char* bhi, unsigned char* blo,
-                                                 float* bias, int tid, int nthreads) {
+                                                 float* bias, int tid, int nthreads, unsigned char* thi = nullptr,
+                                                 unsigned char* tlo = nullptr) {
   for (int idx = tid; idx < np * kp; idx += nthreads) {
     const int n = idx / kp, k = idx - n * kp;
     const float w = (n < N && k < K) ? Wg[(long long)n * K + k] : 0.f;
@@ -75,6 +147,11 @@ __device__ __forceinline__ void stage_tc_weights(const float* __restrict__ Wg, c
     const uint32_t off = chunk_major_offset(n, k, np);
     *reinterpret_cast<uint32_t*>(bhi + off) = hi;
     *reinterpret_cast<uint32_t*>(blo + off) = lo;
+    if (thi != nullptr) {            // W^T as a K-major operand: rows = inputs (kp), contraction = outputs
+      const uint32_t toff = chunk_major_offset(k, n, kp);
+      *reinterpret_cast<uint32_t*>(thi + toff) = hi;
+      *reinterpret_cast<uint32_t*>(tlo + toff) = lo;
+    }
   }
   for (int n = tid; n < np; n += nthreads) bias[n] = (n < N) ? bg[n] : 0.f;
 }
@@ -118,7 +195,6 @@ fused_tc_forward_kernel(const __grid_constant__ DevPlan p, const __grid_constant
   const int n3 = 3 * p.n_inp;
   const int nl = p.n_layers;          // layers 0 .. nl-2 run on tensor cores, layer nl-1 in registers
   float* xs = reinterpret_cast<float*>(smem + lay.xs_off);
-  float* featbuf = reinterpret_cast<float*>(smem + lay.feat_off);
   const int* aidx = reinterpret_cast<const int*>(smem + lay.aidx_off);
   const float* ref = reinterpret_cast<const float*>(smem + lay.ref_off);
   const int* ent = reinterpret_cast<const int*>(smem + lay.ent_off);
@@ -140,7 +216,6 @@ fused_tc_forward_kernel(const __grid_constant__ DevPlan p, const __grid_constant
     }
     for (int o = tid; o < N; o += TC_F) bl[o] = p.b[nl - 1][o];
   }
-  for (int i = tid; i < lay.kp[0] * TC_F; i += TC_F) featbuf[i] = 0.f;      // padded feature rows stay zero
   if (tid == 0) {
     mbar_init(mbar_x, 1);
     mbar_init(mbar_mma, 1);
@@ -179,27 +254,20 @@ fused_tc_forward_kernel(const __grid_constant__ DevPlan p, const __grid_constant
       for (int i = tid; i < nf * n3; i += TC_F) xs[i] = src[i];
       __syncthreads();
     }
-    // ---- geometry: thread t <-> frame t ----
+    // ---- geometry: thread t <-> frame t; features go straight to the A operand in TMEM ----
     {
       const int f = tid < nf ? tid : nf - 1;
       const float* xf = xs + f * n3;
       Rigid rg;
       const bool aligned = p.n_align > 0;
       if (aligned) kabsch<1>(xf, aidx, ref, p.n_align, 0, rg);
-      TileOut out{featbuf, tid, TC_F};
+      __syncwarp();
+      zero_a_operand(lane_addr, COL_AHI, COL_ALO, lay.kp[0]);
+      TmemFeatOut out{lane_addr + COL_AHI, lane_addr + COL_ALO};
       for (int e = 0; e < p.n_entries; ++e) {
         const Entry en = load_entry(ent + ENTRY_INTS * e);
         feature_forward(en, xf, aligned, rg, p.use_angle, out);
       }
-    }
-    // own feature row -> TF32 hi/lo -> TMEM (A operand of layer 0)
-    __syncwarp();
-    for (int c = 0; c < lay.kp[0]; c += 8) {
-      uint32_t hi[8], lo[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) split_tf32_rn(featbuf[(c + i) * TC_F + tid], hi[i], lo[i]);
-      tmem_st8(lane_addr + COL_AHI + c, hi);
-      tmem_st8(lane_addr + COL_ALO + c, lo);
     }
     tmem_wait_st();
     tc_fence_before_sync();
@@ -280,6 +348,316 @@ fused_tc_forward_kernel(const __grid_constant__ DevPlan p, const __grid_constant
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tbase, TC_TMEM_COLS);
+}
+
+// =============================================================================================
+// Value and gradient (forward recompute + d<gy,y>/dx) -- TILES frame tiles per CTA
+// =============================================================================================
+// Each warpgroup (4 warps = 128 threads) owns one 128-frame tile slot end to end and synchronises only
+// with itself (named barrier + its own mbarriers), so the warpgroups of a CTA run phase-shifted and one
+// group's tensor-core work overlaps the other's CUDA-core work while they share one smem copy of the
+// weights (forward operand W and backward operand W^T, both K-major: an MN-major TF32 operand would need
+// the 32B-base 128B swizzle, which no K-major layout of the same bytes matches) and ONE gradient staging
+// tile, handed over with a lock (a warpgroup holds it only from zero-fill to the end of its bulk store).
+struct TcVgLayout {
+  TcLayout base;                       // shared: weights, biases, plan constants
+  int xs_off[4];                       // per tile slot: coordinate tile
+  int gxs_off;                         // shared gradient tile
+  int lock_off;
+  int mbar_off, tptr_off;
+  int total_bytes;
+};
+
+__device__ __forceinline__ void wg_sync(int wg) {
+  asm volatile("bar.sync %0, %1;" ::"r"(wg + 1), "r"(128) : "memory");
+}
+
+template <int TILES>
+__global__ void __launch_bounds__(TILES * TC_F)
+fused_tc_value_grad_kernel(const __grid_constant__ DevPlan p, const __grid_constant__ TcVgLayout vl,
+                           const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ y,
+                           float* __restrict__ gx, long long L, int use_tma) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  constexpr int NT = TILES * TC_F;
+  const TcLayout& lay = vl.base;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int wg = tid >> 7, wt = tid & 127;
+  const int n3 = 3 * p.n_inp;
+  const int nl = p.n_layers;
+  const int nh = nl - 1;               // hidden (tensor-core) layers: 1 or 2
+  float* xs = reinterpret_cast<float*>(smem + vl.xs_off[wg]);
+  float* gxs = reinterpret_cast<float*>(smem + vl.gxs_off);
+  int* gx_lock = reinterpret_cast<int*>(smem + vl.lock_off);
+  const int* aidx = reinterpret_cast<const int*>(smem + lay.aidx_off);
+  const float* ref = reinterpret_cast<const float*>(smem + lay.ref_off);
+  const int* ent = reinterpret_cast<const int*>(smem + lay.ent_off);
+  unsigned long long* mbar_x = reinterpret_cast<unsigned long long*>(smem + vl.mbar_off) + 2 * wg;
+  unsigned long long* mbar_mma = mbar_x + 1;
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(smem + vl.tptr_off);
+
+  stage_tc_consts<NT>(p, lay, smem, tid);
+  for (int k = 0; k < nh; ++k)
+    stage_tc_weights(p.W[k], p.b[k], p.dims[k], p.dims[k + 1], lay.kp[k], lay.np[k], smem + lay.bhi_off[k],
+                     smem + lay.blo_off[k], reinterpret_cast<float*>(smem + lay.bias_off[k]), tid, NT,
+                     smem + lay.thi_off[k], smem + lay.tlo_off[k]);
+  {
+    const int K = p.dims[nl - 1], N = p.dims[nl];
+    float* wl = reinterpret_cast<float*>(smem + lay.wlast_off);
+    float* bl = reinterpret_cast<float*>(smem + lay.blast_off);
+    for (int i = tid; i < N * TC_MAXW; i += NT) {
+      const int o = i / TC_MAXW, j = i - o * TC_MAXW;
+      wl[i] = (j < K) ? p.W[nl - 1][(long long)o * K + j] : 0.f;
+    }
+    for (int o = tid; o < N; o += NT) bl[o] = p.b[nl - 1][o];
+  }
+  if (tid == 0) *gx_lock = 0;
+  if (wt == 0) {
+    mbar_init(mbar_x, 1);
+    mbar_init(mbar_mma, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(tptr, TILES * 256);
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tbase = *tptr + (uint32_t)wg * 256u;
+  const uint32_t lane_addr = tbase + ((uint32_t)((warp & 3) * 32) << 16);
+  constexpr uint32_t COL_AHI = 0, COL_ALO = 64, COL_D = 128, COL_H1 = 192;
+
+  const long long ntiles = (L + TC_F - 1) / TC_F;
+  const uint32_t tile_bytes = (uint32_t)TC_F * (uint32_t)n3 * 4u;
+  const int kout = p.dims[nl];
+  uint32_t phase_x = 0, phase_m = 0;
+  auto is_tma_tile = [&](long long t) { return use_tma && (t + 1) * (long long)TC_F <= L; };
+  auto issue_x = [&](long long t) {
+    if (wt == 0) {
+      mbar_expect_tx(mbar_x, tile_bytes);
+      bulk_g2s(xs, x + t * (long long)TC_F * n3, tile_bytes, mbar_x);
+    }
+  };
+  auto wait_mma = [&]() {
+    mbar_wait(mbar_mma, phase_m);
+    phase_m ^= 1u;
+    tc_fence_after_sync();
+    __syncwarp();
+  };
+  auto publish_a_and_issue = [&](const unsigned char* bh, const unsigned char* bl, int kp_, int np_) {
+    tmem_wait_st();
+    tc_fence_before_sync();
+    wg_sync(wg);
+    if (wt == 0) {
+      tc_fence_after_sync();
+      issue_layer_mma(tbase, COL_AHI, COL_ALO, COL_D, bh, bl, kp_, np_, mbar_mma);
+    }
+  };
+  const long long tstride = (long long)gridDim.x * TILES;
+  long long tile = (long long)blockIdx.x * TILES + wg;
+  if (tile < ntiles && is_tma_tile(tile)) issue_x(tile);
+
+  for (; tile < ntiles; tile += tstride) {
+    const long long f_base = tile * (long long)TC_F;
+    const int nf = (int)((L - f_base) < (long long)TC_F ? (L - f_base) : (long long)TC_F);
+    if (is_tma_tile(tile)) {
+      mbar_wait(mbar_x, phase_x);
+      phase_x ^= 1u;
+    } else {
+      const float* src = x + f_base * n3;
+      for (int i = wt; i < nf * n3; i += TC_F) xs[i] = src[i];
+      wg_sync(wg);
+    }
+    // ---- geometry ----
+    const int f = wt < nf ? wt : nf - 1;
+    const float* xf = xs + f * n3;
+    Rigid rg;
+    const bool aligned = p.n_align > 0;
+    if (aligned) kabsch<1>(xf, aidx, ref, p.n_align, 0, rg);
+    __syncwarp();
+    zero_a_operand(lane_addr, COL_AHI, COL_ALO, lay.kp[0]);
+    {
+      TmemFeatOut out{lane_addr + COL_AHI, lane_addr + COL_ALO};
+      for (int e = 0; e < p.n_entries; ++e) {
+        const Entry en = load_entry(ent + ENTRY_INTS * e);
+        feature_forward(en, xf, aligned, rg, p.use_angle, out);
+      }
+    }
+    publish_a_and_issue(smem + lay.bhi_off[0], smem + lay.blo_off[0], lay.kp[0], lay.np[0]);
+    // ---- first hidden layer (only when there are two): h_1 -> A operand, act'(z_1) parked in TMEM ----
+    if (nh == 2) {
+      wait_mma();
+      const float* bias = reinterpret_cast<const float*>(smem + lay.bias_off[0]);
+      const int np = lay.np[0];
+#pragma unroll
+      for (int c = 0; c < TC_MAXW; c += 16) {
+        if (c < np) {
+          float z[16];
+          tmem_ld16(lane_addr + COL_D + c, z);
+          tmem_wait_ld();
+          uint32_t dv[16], hi[16], lo[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float hh, dd;
+            act_value_and_grad(z[i] + bias[c + i], p.act, hh, dd);
+            dv[i] = __float_as_uint(dd);
+            split_tf32_rn(hh, hi[i], lo[i]);
+          }
+          tmem_st16(lane_addr + COL_H1 + c, dv);
+          tmem_st16(lane_addr + COL_AHI + c, hi);
+          tmem_st16(lane_addr + COL_ALO + c, lo);
+        }
+      }
+      publish_a_and_issue(smem + lay.bhi_off[1], smem + lay.blo_off[1], lay.kp[1], lay.np[1]);
+    }
+    // ---- last hidden layer, streamed 16 columns at a time: y += h W_last^T, gz = (gy W_last) * act'(z) ----
+    float h[TC_MAXW];                    // h := gy W_last (cotangent of the last hidden activation)
+    {
+      const float* wl = reinterpret_cast<const float*>(smem + lay.wlast_off);
+      const float* bl = reinterpret_cast<const float*>(smem + lay.blast_off);
+      const float* bias = reinterpret_cast<const float*>(smem + lay.bias_off[nh - 1]);
+      const int np = lay.np[nh - 1];
+      float go[8], yacc[8];
+#pragma unroll
+      for (int o = 0; o < 8; ++o) {
+        go[o] = (o < kout && wt < nf) ? __ldg(gy + (f_base + wt) * kout + o) : 0.f;
+        yacc[o] = (o < kout) ? bl[o] : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < TC_MAXW; ++j) h[j] = 0.f;
+      for (int o = 0; o < kout; ++o) {
+        const float4* w4 = reinterpret_cast<const float4*>(wl + o * TC_MAXW);
+        const float g_o = (o == 0) ? go[0] : (o == 1) ? go[1] : (o == 2) ? go[2] : (o == 3) ? go[3]
+                        : (o == 4) ? go[4] : (o == 5) ? go[5] : (o == 6) ? go[6] : go[7];
+#pragma unroll
+        for (int j = 0; j < TC_MAXW / 4; ++j) {
+          const float4 w = w4[j];
+          h[4 * j] = fmaf(g_o, w.x, h[4 * j]);
+          h[4 * j + 1] = fmaf(g_o, w.y, h[4 * j + 1]);
+          h[4 * j + 2] = fmaf(g_o, w.z, h[4 * j + 2]);
+          h[4 * j + 3] = fmaf(g_o, w.w, h[4 * j + 3]);
+        }
+      }
+      wait_mma();
+#pragma unroll
+      for (int c = 0; c < TC_MAXW; c += 16) {
+        if (c < np) {
+          float z[16];
+          tmem_ld16(lane_addr + COL_D + c, z);
+          tmem_wait_ld();
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float hh, dd;
+            act_value_and_grad(z[i] + bias[c + i], p.act, hh, dd);
+            z[i] = hh;
+            split_tf32_rn(h[c + i] * dd, hi[i], lo[i]);          // gz of the last hidden layer
+          }
+          tmem_st16(lane_addr + COL_AHI + c, hi);
+          tmem_st16(lane_addr + COL_ALO + c, lo);
+          if (y != nullptr) {
+            for (int o = 0; o < kout; ++o) {
+              const float4* w4 = reinterpret_cast<const float4*>(wl + o * TC_MAXW + c);
+              float a = 0.f;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float4 w = w4[q];
+                a = fmaf(z[4 * q], w.x, a);
+                a = fmaf(z[4 * q + 1], w.y, a);
+                a = fmaf(z[4 * q + 2], w.z, a);
+                a = fmaf(z[4 * q + 3], w.w, a);
+              }
+#pragma unroll
+              for (int oo = 0; oo < 8; ++oo)
+                if (oo == o) yacc[oo] += a;
+            }
+          }
+        } else if (c < lay.np[nh - 1]) {
+        }
+      }
+      if (y != nullptr && wt < nf) {
+#pragma unroll
+        for (int o = 0; o < 8; ++o)
+          if (o < kout) y[(f_base + wt) * kout + o] = yacc[o];
+      }
+    }
+    // ---- backward through the tensor-core layers: gh_k = gz_{k+1} W_k  (operand W^T, K-major) ----
+    for (int k = nh - 1; k >= 0; --k) {
+      const int kb = lay.np[k];            // contraction width (outputs of forward layer k)
+      const int nb = lay.kp[k];            // result width (inputs of forward layer k)
+      publish_a_and_issue(smem + lay.thi_off[k], smem + lay.tlo_off[k], kb, nb);
+      wait_mma();
+      if (k > 0) {               // gz_k = gh_k * act'(z_k) (parked in TMEM) -> A operand of the next contraction
+#pragma unroll
+        for (int c = 0; c < TC_MAXW; c += 16) {
+          if (c < nb) {
+            float gh[16], dk[16];
+            tmem_ld16(lane_addr + COL_D + c, gh);
+            tmem_ld16(lane_addr + COL_H1 + c, dk);
+            tmem_wait_ld();
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) split_tf32_rn(gh[i] * dk[i], hi[i], lo[i]);
+            tmem_st16(lane_addr + COL_AHI + c, hi);
+            tmem_st16(lane_addr + COL_ALO + c, lo);
+          }
+        }
+      }
+    }
+    // the feature cotangent now sits in accumulator columns [COL_D, COL_D + d_feat) of this lane
+    if (TILES > 1) {             // take the shared gradient tile
+      if (wt == 0)
+        while (atomicCAS(gx_lock, 0, 1) != 0) __nanosleep(32);
+      wg_sync(wg);
+    }
+    for (int i = wt; i < TC_F * n3; i += TC_F) gxs[i] = 0.f;
+    wg_sync(wg);
+    {
+      TmemGIn gin{lane_addr + COL_D};
+      RowAcc acc{gxs + wt * n3};
+      float M[9], sg[3];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) M[i] = 0.f;
+      sg[0] = sg[1] = sg[2] = 0.f;
+      for (int e = 0; e < p.n_entries; ++e) {
+        const Entry en = load_entry(ent + ENTRY_INTS * e);
+        feature_backward(en, xf, aligned, rg, p.use_angle, gin, acc, M, sg);
+      }
+      if (aligned) {
+        float dH[9];
+        align_backward_dH(rg, M, dH);
+        const float inv_na = 1.0f / (float)p.n_align;
+        for (int k = 0; k < p.n_align; ++k)
+          acc(aidx[k], align_atom_grad(dH, sg, inv_na, ref[3 * k], ref[3 * k + 1], ref[3 * k + 2]));
+      }
+    }
+    fence_proxy_async_smem();
+    wg_sync(wg);
+    const long long next = tile + tstride;
+    if (next < ntiles && is_tma_tile(next)) issue_x(next);       // xs is free
+    float* dst = gx + f_base * n3;
+    if (is_tma_tile(tile)) {
+      if (wt == 0) {
+        bulk_s2g(dst, gxs, tile_bytes);
+        bulk_commit();
+        bulk_wait_read0();                                       // smem source fully read
+        if (TILES > 1) {
+          __threadfence_block();
+          atomicExch(gx_lock, 0);
+        }
+      }
+      if (TILES == 1) wg_sync(wg);                               // gxs reusable by this group's next tile
+    } else {
+      for (int i = wt; i < nf * n3; i += TC_F) dst[i] = gxs[i];
+      wg_sync(wg);
+      if (TILES > 1 && wt == 0) {
+        __threadfence_block();
+        atomicExch(gx_lock, 0);
+      }
+    }
+  }
+  if (wt == 0) bulk_wait0();
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(*tptr, TILES * 256);
 }
 
 }  // namespace molann

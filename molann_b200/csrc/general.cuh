@@ -20,6 +20,10 @@ struct GlobalOut {
 struct GlobalGIn {
   const float* row;
   __device__ __forceinline__ float operator()(int col) const { return __ldg(row + col); }
+  __device__ __forceinline__ void load2(int col, float& a, float& b) const { a = (*this)(col); b = (*this)(col + 1); }
+  __device__ __forceinline__ void load3(int col, float& a, float& b, float& c) const {
+    a = (*this)(col); b = (*this)(col + 1); c = (*this)(col + 2);
+  }
 };
 struct RedAcc {
   float* row;

@@ -293,7 +293,8 @@ __device__ __forceinline__ void feature_backward(const Entry& e, const float* __
                                                  const Rigid& rg, int use_angle, GIn& gin, Acc& acc,
                                                  float (&M)[9], float (&sg)[3]) {
   if (e.type == FEAT_POSITION) {
-    const float g0 = gin(e.off), g1 = gin(e.off + 1), g2 = gin(e.off + 2);
+    float g0, g1, g2;
+    gin.load3(e.off, g0, g1, g2);
     if (aligned) {
       const V3 p = ld3(xf, e.a0);
       const float dx = p.x - rg.c[0], dy = p.y - rg.c[1], dz = p.z - rg.c[2];
@@ -323,7 +324,8 @@ __device__ __forceinline__ void feature_backward(const Entry& e, const float* __
       gC = -g * S / rho2;
       gS = g * C / rho2;
     } else {
-      const float gc = gin(e.off), gs = gin(e.off + 1);
+      float gc, gs;
+      gin.load2(e.off, gc, gs);
       const float rho3 = rho2 * sqrtf(rho2);
       const float k = (gc * S - gs * C) / rho3;
       gC = S * k;

@@ -282,10 +282,8 @@ TcChoice choose_tc(const MolannPlan* p, bool backward, const DeviceInfo& dev) {
   lay.mbar_off = c.take(16, 16);
   lay.tptr_off = c.take(16, 16);
   lay.xs_off = c.take(TC_F * 3 * p->n_inp * 4, 128);
-  lay.kp[0] = round_up(p->dims[0], 8);
-  lay.feat_off = c.take(lay.kp[0] * TC_F * 4, 128);
   for (int k = 0; k < nl - 1; ++k) {
-    lay.kp[k] = round_up(p->dims[k], 8);
+    lay.kp[k] = round_up(p->dims[k], 16);
     lay.np[k] = round_up(p->dims[k + 1], 16);
     lay.bhi_off[k] = c.take(lay.kp[k] * lay.np[k] * 4, 1024);
     lay.blo_off[k] = c.take(lay.kp[k] * lay.np[k] * 4, 1024);
@@ -321,6 +319,97 @@ int launch_tc_forward(const DevPlan& dp, const TcLayout& lay, const float* x, fl
   const int use_tma = ((reinterpret_cast<uintptr_t>(x) & 15u) == 0) && ((TC_F * 3 * dp.n_inp * 4) % 16 == 0);
   kern<<<(unsigned)grid, TC_F, lay.total_bytes, st>>>(dp, lay, x, y, L, use_tma);
   return post_launch();
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused tensor-core value-and-gradient path (forward recompute + d/dx in one kernel)
+// ---------------------------------------------------------------------------------------------
+struct TcVgChoice {
+  bool ok = false;
+  int tiles = 0;
+  TcVgLayout vl;
+};
+
+TcVgChoice choose_tc_vg(const MolannPlan* p, const DeviceInfo& dev) {
+  TcVgChoice ch;
+  std::memset(&ch.vl, 0, sizeof(ch.vl));
+  if (env_int("MOLANN_B200_TC", 1) == 0 || env_int("MOLANN_B200_PATH", -1) == 0) return ch;
+  const int nl = p->n_layers;
+  if (nl < 2 || nl > 3) return ch;                 // one or two tensor-core layers (h_1 parked in TMEM)
+  for (int k = 0; k < nl; ++k)
+    if (p->dims[k] > TC_MAXW) return ch;
+  if (p->dims[nl] > 8) return ch;
+  if ((long long)p->n_entries * ENTRY_INTS * 4 > 32 * 1024) return ch;
+  const int xs_bytes = TC_F * 3 * p->n_inp * 4;
+  if (xs_bytes > 64 * 1024) return ch;
+  const int want_tiles = env_int("MOLANN_B200_VG_TILES", 2);
+  for (int tiles = (want_tiles == 1 ? 1 : 2); tiles >= 1; --tiles) {
+    TcVgLayout vl;
+    std::memset(&vl, 0, sizeof(vl));
+    TcLayout& lay = vl.base;
+    Carver c;
+    vl.mbar_off = c.take(16 * 4, 16);
+    vl.tptr_off = c.take(16, 16);
+    for (int k = 0; k < nl - 1; ++k) {
+      lay.kp[k] = round_up(p->dims[k], 16);
+      lay.np[k] = round_up(p->dims[k + 1], 16);
+      lay.bhi_off[k] = c.take(lay.kp[k] * lay.np[k] * 4, 1024);
+      lay.blo_off[k] = c.take(lay.kp[k] * lay.np[k] * 4, 1024);
+      lay.bias_off[k] = c.take(lay.np[k] * 4, 16);
+    }
+    lay.wlast_off = c.take(p->dims[nl] * TC_MAXW * 4, 16);
+    lay.blast_off = c.take(p->dims[nl] * 4, 16);
+    lay.aidx_off = c.take((p->n_align > 0 ? p->n_align : 1) * 4, 16);
+    lay.ref_off = c.take((p->n_align > 0 ? 3 * p->n_align : 1) * 4, 16);
+    lay.ent_off = c.take(p->n_entries * ENTRY_INTS * 4, 16);
+    for (int k = 0; k < nl - 1; ++k) {             // W^T operands for the backward contractions
+      lay.thi_off[k] = c.take(lay.kp[k] * lay.np[k] * 4, 1024);
+      lay.tlo_off[k] = c.take(lay.kp[k] * lay.np[k] * 4, 1024);
+    }
+    vl.lock_off = c.take(16, 16);
+    vl.gxs_off = c.take(xs_bytes, 128);            // ONE gradient tile shared by the warpgroups
+    for (int t = 0; t < tiles; ++t) vl.xs_off[t] = c.take(xs_bytes, 128);
+    vl.total_bytes = round_up(c.off, 128);
+    if (tiles == 1) {        // 256 TMEM columns per CTA: at most two CTAs may share an SM
+      const int min_bytes = dev.max_smem_optin / 3 + 1024;
+      if (vl.total_bytes < min_bytes) vl.total_bytes = round_up(min_bytes, 128);
+    } else {                 // 512 TMEM columns: exactly one CTA per SM
+      const int min_bytes = dev.max_smem_optin / 2 + 1024;
+      if (vl.total_bytes < min_bytes) vl.total_bytes = round_up(min_bytes, 128);
+    }
+    if (vl.total_bytes <= dev.max_smem_optin) {
+      ch.ok = true; ch.tiles = tiles; ch.vl = vl;
+      return ch;
+    }
+  }
+  return ch;
+}
+
+template <int TILES>
+int launch_tc_vg(const DevPlan& dp, const TcVgLayout& vl, const float* x, const float* gy, float* y, float* gx,
+                 long long L, const DeviceInfo& dev, cudaStream_t st) {
+  auto kern = fused_tc_value_grad_kernel<TILES>;
+  int s = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, vl.total_bytes));
+  if (s) return s;
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  int occ = dev.smem_per_sm / (vl.total_bytes + 1024);
+  const int occ_cap = (TILES == 1) ? 2 : 1;
+  if (occ < 1) occ = 1;
+  if (occ > occ_cap) occ = occ_cap;
+  const long long ntiles = (L + TC_F - 1) / TC_F;
+  long long grid = (long long)dev.sm_count * occ;
+  const long long need = (ntiles + TILES - 1) / TILES;
+  if (grid > need) grid = need;
+  const int use_tma = ((reinterpret_cast<uintptr_t>(x) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(gx) & 15u) == 0) &&
+                      ((TC_F * 3 * dp.n_inp * 4) % 16 == 0);
+  kern<<<(unsigned)grid, TILES * TC_F, vl.total_bytes, st>>>(dp, vl, x, gy, y, gx, L, use_tma);
+  return post_launch();
+}
+
+int run_tc_vg(const TcVgChoice& ch, const DevPlan& dp, const float* x, const float* gy, float* y, float* gx,
+              long long L, const DeviceInfo& dev, cudaStream_t st) {
+  return ch.tiles == 2 ? launch_tc_vg<2>(dp, ch.vl, x, gy, y, gx, L, dev, st)
+                       : launch_tc_vg<1>(dp, ch.vl, x, gy, y, gx, L, dev, st);
 }
 
 #define SMALL_DISPATCH(ch, FN, ...)                                   \
@@ -522,7 +611,7 @@ int molann_b200_kernel_family(const MolannPlan* plan, int want_backward) {
   if (validate_full(plan) != MOLANN_OK) return -1;
   DeviceInfo dev = device_info();
   if (!dev.ok) { dev.sm_count = 148; dev.max_smem_optin = 232448; dev.smem_per_sm = 233472; }   // B200 figures
-  if (choose_tc(plan, want_backward != 0, dev).ok) return 2;
+  if (want_backward ? choose_tc_vg(plan, dev).ok : choose_tc(plan, false, dev).ok) return 2;
   return choose_small(plan, want_backward != 0, dev).ok ? 1 : 0;
 }
 
@@ -572,6 +661,8 @@ int molann_b200_backward(const MolannPlan* plan, const float* x, const float* gy
   if (gW)
     for (int k = 0; k < plan->n_layers; ++k) want_params = want_params || (gW[k] != nullptr);
   if (!want_params) {
+    const TcVgChoice vg = choose_tc_vg(plan, dev);
+    if (vg.ok) return run_tc_vg(vg, to_dev(plan), x, gy, nullptr, gx, (long long)L, dev, st);
     const SmallChoice ch = choose_small(plan, true, dev);
     if (ch.ok) {
       const DevPlan dp = to_dev(plan);
@@ -579,6 +670,25 @@ int molann_b200_backward(const MolannPlan* plan, const float* x, const float* gy
     }
   }
   return general_backward(plan, x, gy, L, gx, gW, gb, workspace, workspace_bytes, dev, st);
+}
+
+int molann_b200_value_and_grad(const MolannPlan* plan, const float* x, const float* gy, int64_t L, float* y,
+                               float* gx, void* workspace, size_t workspace_bytes, void* stream) {
+  int s = validate_full(plan);
+  if (s) return s;
+  if (plan->n_layers < 1) return MOLANN_ERR_UNSUPPORTED;
+  if (L < 0) return MOLANN_ERR_PLAN;
+  if (L == 0) return MOLANN_OK;
+  if (!x || !gy || !y || !gx) return MOLANN_ERR_NULL;
+  if (misaligned4(x) || misaligned4(gy) || misaligned4(y) || misaligned4(gx)) return MOLANN_ERR_ALIGNMENT;
+  const DeviceInfo dev = device_info();
+  if (!dev.ok) return MOLANN_ERR_CUDA;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const TcVgChoice vg = choose_tc_vg(plan, dev);
+  if (vg.ok) return run_tc_vg(vg, to_dev(plan), x, gy, y, gx, (long long)L, dev, st);   // ONE kernel
+  s = molann_b200_forward(plan, x, L, y, workspace, workspace_bytes, stream);
+  if (s) return s;
+  return molann_b200_backward(plan, x, gy, L, gx, nullptr, nullptr, workspace, workspace_bytes, stream);
 }
 
 int molann_b200_preprocess_forward(const MolannPlan* plan, const float* x, int64_t L, float* feat, void* stream) {

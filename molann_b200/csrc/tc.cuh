@@ -65,6 +65,16 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&u)[8])
                : "memory");
 }
 
+// one column of this thread's lane (the column address is a run-time, warp-uniform value)
+__device__ __forceinline__ void tmem_st1(uint32_t taddr, uint32_t v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(v) : "memory");
+}
+__device__ __forceinline__ float tmem_ld1_nowait(uint32_t taddr) {
+  uint32_t v;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
+  return __uint_as_float(v);
+}
+
 // ---- descriptors -----------------------------------------------------------------------------
 // shared-memory matrix descriptor, K-major, SWIZZLE_NONE, Blackwell version field = 1
 __device__ __forceinline__ uint64_t smem_desc_kmajor(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {

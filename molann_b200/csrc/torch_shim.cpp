@@ -15,6 +15,7 @@
 #include <ATen/ATen.h>
 #include <torch/csrc/autograd/custom_function.h>
 
+#include <tuple>
 #include <vector>
 
 #include "../../include/molann_b200.h"
@@ -223,6 +224,38 @@ std::vector<Tensor> molann_bwd_impl(const Tensor& x, const Tensor& align_idx, co
   return out;
 }
 
+// y = model(x) and gx = d<gy, y>/dx in ONE pass (biasing-force entry point, no autograd graph)
+std::tuple<Tensor, Tensor> value_and_grad_impl(const Tensor& x, const Tensor& gy_in, const Tensor& align_idx,
+                                               const Tensor& ref_x, const Tensor& entries, int64_t d_feat,
+                                               bool use_angle_value, at::TensorList params, int64_t act) {
+  check_x(x, "value_and_grad");
+  c10::cuda::CUDAGuard guard(x.device());
+  PlanHolder h;
+  fill_geometry(h, x, align_idx, ref_x);
+  fill_features(h, x, entries, d_feat, use_angle_value);
+  fill_mlp(h, x, params, act);
+  const int64_t L = x.size(0);
+  const int64_t kout = h.plan.dims[h.plan.n_layers];
+  TORCH_CHECK(gy_in.is_cuda() && gy_in.scalar_type() == at::kFloat && gy_in.dim() == 2 && gy_in.size(0) == L &&
+                  gy_in.size(1) == kout,
+              "molann_b200::value_and_grad: cotangent must be a float32 CUDA tensor of shape [L, ", kout, "]");
+  Tensor gy = gy_in.contiguous();
+  Tensor y = at::empty({L, kout}, x.options());
+  Tensor gx = at::empty_like(x);
+  Tensor ws;
+  void* wsp = nullptr;
+  size_t ws_bytes = 0;
+  if (molann_b200_kernel_family(&h.plan, 1) != 2) {
+    ws_bytes = molann_b200_workspace_bytes(&h.plan, L, 1);
+    ws = at::empty({static_cast<int64_t>(ws_bytes)}, x.options().dtype(at::kByte));
+    wsp = ws.data_ptr();
+  }
+  check_status(molann_b200_value_and_grad(&h.plan, x.data_ptr<float>(), gy.data_ptr<float>(), L, y.data_ptr<float>(),
+                                          gx.data_ptr<float>(), wsp, ws_bytes, cur_stream()),
+               "value_and_grad");
+  return std::make_tuple(y, gx);
+}
+
 // ------------------------------------------------------------------------------------------
 // autograd
 // ------------------------------------------------------------------------------------------
@@ -320,6 +353,8 @@ TORCH_LIBRARY(molann_b200, m) {
   m.def("preprocess(Tensor x, Tensor align_idx, Tensor ref_x, Tensor entries, int d_feat, bool use_angle_value) -> Tensor");
   m.def("molann(Tensor x, Tensor align_idx, Tensor ref_x, Tensor entries, int d_feat, bool use_angle_value, "
         "Tensor[] params, int act) -> Tensor");
+  m.def("value_and_grad(Tensor x, Tensor gy, Tensor align_idx, Tensor ref_x, Tensor entries, int d_feat, "
+        "bool use_angle_value, Tensor[] params, int act) -> (Tensor, Tensor)");
   m.def("launch_count() -> int", &launch_count);
 }
 
@@ -327,6 +362,7 @@ TORCH_LIBRARY_IMPL(molann_b200, CUDA, m) {
   m.impl("align", &align_fwd_impl);
   m.impl("preprocess", &preprocess_fwd_impl);
   m.impl("molann", &molann_fwd_impl);
+  m.impl("value_and_grad", &value_and_grad_impl);
 }
 
 TORCH_LIBRARY_IMPL(molann_b200, Autograd, m) {

@@ -11,7 +11,12 @@ using namespace molann;
 
 namespace {
 struct RowOut { float* row; void operator()(int col, float v) { row[col] = v; } };
-struct RowGIn { const float* row; float operator()(int col) const { return row[col]; } };
+struct RowGIn {
+  const float* row;
+  float operator()(int col) const { return row[col]; }
+  void load2(int col, float& a, float& b) const { a = row[col]; b = row[col + 1]; }
+  void load3(int col, float& a, float& b, float& c) const { a = row[col]; b = row[col + 1]; c = row[col + 2]; }
+};
 struct RowAccH { float* row; void operator()(int a, V3 v) { row[3*a] += v.x; row[3*a+1] += v.y; row[3*a+2] += v.z; } };
 }
 

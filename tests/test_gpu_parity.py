@@ -149,6 +149,28 @@ def test_module_api_forward_and_autograd(name):
         assert float((p.grad.cpu().double() - ref).abs().max() / ref.abs().max()) < 2e-5, k
 
 
+@pytest.mark.parametrize("name", ["C1", "C2", "C3s"])
+def test_value_and_grad_single_pass(name):
+    """The biasing-force entry point: (y, d<cot,y>/dx) from ONE launch where the plan is eligible."""
+    from molann_b200 import _lib
+    spec = S.get_spec(name)
+    g = golden("config_" + name)
+    model, _ = S.build_model(spec)
+    model.load_state_dict({k[4:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd::")}, strict=True)
+    model = model.cuda()
+    x, cot = dev(g["x"]), dev(g["cot"])
+    before = _lib.launch_count()
+    y, gx = model.value_and_grad(x, cot)
+    torch.cuda.synchronize()
+    launches = _lib.launch_count() - before
+    assert_parity(y.cpu(), g["y64"], g["y32"], TOL, "vg y")
+    assert_parity(gx.cpu(), g["gx64"], g["gx32"], TOL, "vg gx")
+    if name == "C2":
+        assert launches == 1
+    ys, gxs = torch.jit.script(model).value_and_grad(x, cot)
+    assert torch.equal(ys, y) and torch.equal(gxs, gx)
+
+
 def test_alignment_layer_standalone_and_composition():
     """AlignmentLayer alone (fwd + autograd) and the unfused composition feature(align(x))."""
     spec = S.get_spec("C2")
@@ -170,7 +192,7 @@ def test_alignment_layer_standalone_and_composition():
     assert_parity(f2.cpu(), g["feat64"], g["feat32"], TOL, "composed feat")
 
 
-@pytest.mark.parametrize("L", [1, 2, 3, 4, 5, 63, 64, 65, 127, 128, 129, 257, 1000])
+@pytest.mark.parametrize("L", [1, 2, 3, 4, 5, 63, 64, 65, 127, 128, 129, 255, 256, 257, 385, 1000])
 def test_ragged_frame_counts(L):
     """Partial tiles, L < tile, L == 3 (the reference's torch.cross quirk case is defined by intent)."""
     for name in ("C1", "C2"):
