@@ -310,6 +310,10 @@ def main():
             return model(x)
 
     def fwd_dx_step():
+        # outputs + coordinate gradient in ONE fused launch (MolANN.value_and_grad, the biasing-force entry)
+        return model.value_and_grad(x, cot)
+
+    def fwd_dx_autograd_step():
         y = model(xg)
         (g,) = torch.autograd.grad(y, xg, cot)
         return g
@@ -335,6 +339,7 @@ def main():
 
     ms_f, launches_f = timed(fwd_step, K, W, True)
     ms_d, launches_d = timed(fwd_dx_step, K, W, True)
+    ms_da, launches_da = timed(fwd_dx_autograd_step, K, W, False)
     clocks = sampler.summary()
     sampler.close()
 
@@ -398,7 +403,11 @@ def main():
         "roofline": roofline(spec.bytes_fwd(), ms_f, launches_f, "fwd"),
         "gpu_launches": int(launches_f), "clocks": clocks,
         "fwd_dx": {"value": value_dx, "unit": UNIT, "ms_per_step": ms_d / K, "gpu_launches": int(launches_d),
-                   "roofline": roofline(spec.bytes_fwd_dx(), ms_d, launches_d, "fwd_dx"), "e2e": e2e_dx},
+                   "api": "MolANN.value_and_grad(x, cotangent)",
+                   "roofline": roofline(spec.bytes_fwd_dx(), ms_d, launches_d, "fwd_dx"), "e2e": e2e_dx,
+                   "via_autograd": {"value": world * frames * K / (ms_da * 1e-3), "ms_per_step": ms_da / K,
+                                    "gpu_launches": int(launches_da),
+                                    "api": "y = model(x); torch.autograd.grad(y, x, cotangent)"}},
         "e2e": e2e,
     }
     if world == 1 and not args.no_cpu_baseline:

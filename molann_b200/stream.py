@@ -64,9 +64,12 @@ class HostPipeline(object):
                 main.wait_event(out_done[b])                    # ybuf[b] drained
             xb = self.xbuf[b][:m]
             if want_grad:
-                xb = xb.detach().requires_grad_(True)
-                y = self.model(xb)
-                (gx,) = torch.autograd.grad(y, xb, self.gbuf[b][:m])
+                if hasattr(self.model, "value_and_grad"):
+                    y, gx = self.model.value_and_grad(xb, self.gbuf[b][:m])
+                else:
+                    xb = xb.detach().requires_grad_(True)
+                    y = self.model(xb)
+                    (gx,) = torch.autograd.grad(y, xb, self.gbuf[b][:m])
                 self.ybuf[b][:m].copy_(y.detach())
                 keep[b] = gx
             else:
