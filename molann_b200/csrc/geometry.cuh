@@ -110,7 +110,7 @@ __device__ __forceinline__ void jacobi_pair(float (&a)[4][4], float (&v)[4][4]) 
 // Dominant (largest-eigenvalue) unit eigenvector of the symmetric matrix whose upper triangle is `a`.
 // Parallel-ordered cyclic Jacobi: a sweep is {(0,1),(2,3)}, {(0,2),(1,3)}, {(0,3),(1,2)}.
 // Must be called by all 32 lanes of a warp (uses a warp vote for a uniform exit).
-__device__ __forceinline__ void dominant_eigvec4(float (&a)[4][4], float (&q)[4]) {
+__device__ __forceinline__ void dominant_eigvec4(float (&a)[4][4], float (&q)[4], bool active = true) {
   float v[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
@@ -118,7 +118,7 @@ __device__ __forceinline__ void dominant_eigvec4(float (&a)[4][4], float (&q)[4]
     for (int j = 0; j < 4; ++j) v[i][j] = (i == j) ? 1.0f : 0.0f;
   // Each lane latches its own convergence, so a frame's result never depends on its warp-mates (frames are
   // bitwise independent of batch composition / sharding); the vote only decides when the warp leaves the loop.
-  bool done = false;
+  bool done = !active;          // lanes that do not need the result never hold the warp in the loop
 #pragma unroll 1
   for (int sweep = 0; sweep < 12; ++sweep) {
     if (!done) {
@@ -147,6 +147,124 @@ __device__ __forceinline__ void dominant_eigvec4(float (&a)[4][4], float (&q)[4]
   for (int r = 0; r < 4; ++r) q[r] *= inv;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Fast path for the same eigenvector: characteristic-polynomial Newton (Theobald's QCP) for the largest
+// eigenvalue, eigenvector from the adjugate of K - lambda I, then ONE first-order correction in the frame
+// rotated by the approximate answer (which squares the error, so the polynomial root only has to be good to
+// ~1e-3).  ~400 instructions instead of ~1300 for converged Jacobi.  Returns false when the correction was
+// not small (near-degenerate top eigenvalue, slow Newton) -- the caller then runs Jacobi for that frame,
+// so accuracy never rests on the fast path alone.  `S` is the covariance scaled to unit Frobenius norm.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void quat_to_rot(const float (&q)[4], float (&R)[9]) {
+  const float qa = q[0], qb = q[1], qc = q[2], qd = q[3];
+  const float aa = qa * qa, bb = qb * qb, cc = qc * qc, dd = qd * qd;
+  const float bc = qb * qc, ad = qa * qd, bd = qb * qd, ac = qa * qc, cd = qc * qd, ab = qa * qb;
+  R[0] = (aa + bb) - (cc + dd);
+  R[1] = 2.f * (bc + ad);
+  R[2] = 2.f * (bd - ac);
+  R[3] = 2.f * (bc - ad);
+  R[4] = (aa - bb) + (cc - dd);
+  R[5] = 2.f * (cd + ab);
+  R[6] = 2.f * (bd + ac);
+  R[7] = 2.f * (cd - ab);
+  R[8] = (aa - bb) - (cc - dd);
+}
+
+__device__ __forceinline__ bool dominant_quat_fast(const float (&S)[9], float (&q)[4]) {
+  const float Sxx = S[0], Sxy = S[1], Sxz = S[2], Syx = S[3], Syy = S[4], Syz = S[5], Szx = S[6], Szy = S[7], Szz = S[8];
+  // Horn's matrix (symmetric, trace 0)
+  const float k00 = Sxx + Syy + Szz, k01 = Syz - Szy, k02 = Szx - Sxz, k03 = Sxy - Syx;
+  const float k11 = Sxx - Syy - Szz, k12 = Sxy + Syx, k13 = Szx + Sxz;
+  const float k22 = -Sxx + Syy - Szz, k23 = Syz + Szy;
+  const float k33 = -Sxx - Syy + Szz;
+  // det(K - lambda I) = l^4 + c2 l^2 + c1 l + c0
+  float ss = Sxx * Sxx;
+  ss = fmaf(Sxy, Sxy, ss); ss = fmaf(Sxz, Sxz, ss); ss = fmaf(Syx, Syx, ss); ss = fmaf(Syy, Syy, ss);
+  ss = fmaf(Syz, Syz, ss); ss = fmaf(Szx, Szx, ss); ss = fmaf(Szy, Szy, ss); ss = fmaf(Szz, Szz, ss);
+  const float c2 = -2.0f * ss;
+  const float detS = Sxx * (Syy * Szz - Syz * Szy) - Sxy * (Syx * Szz - Syz * Szx) + Sxz * (Syx * Szy - Syy * Szx);
+  const float c1 = -8.0f * detS;
+  float c0;
+  {
+    const float s0 = k00 * k11 - k01 * k01, s1 = k00 * k12 - k01 * k02, s2 = k00 * k13 - k01 * k03;
+    const float s3 = k01 * k12 - k11 * k02, s4 = k01 * k13 - k11 * k03, s5 = k02 * k13 - k12 * k03;
+    const float m5 = k22 * k33 - k23 * k23, m4 = k12 * k33 - k13 * k23, m3 = k12 * k23 - k13 * k22;
+    const float m2 = k02 * k33 - k03 * k23, m1 = k02 * k23 - k03 * k22, m0 = k02 * k13 - k03 * k12;
+    c0 = s0 * m5 - s1 * m4 + s2 * m3 + s3 * m2 - s4 * m1 + s5 * m0;
+  }
+  // Newton from the upper bound sqrt(3) ||S||_F (monotone from above: all roots are real)
+  float lam = 1.7320508f;
+#pragma unroll
+  for (int it = 0; it < 6; ++it) {
+    const float l2 = lam * lam;
+    const float P = fmaf(fmaf(l2 + c2, lam, c1), lam, c0);
+    const float dP = fmaf(fmaf(4.0f, l2, 2.0f * c2), lam, c1);
+    lam -= __fdividef(P, dP);
+  }
+  // adjugate of B = K - lambda I (symmetric); its columns are all proportional to the eigenvector
+  const float b00 = k00 - lam, b11 = k11 - lam, b22 = k22 - lam, b33 = k33 - lam;
+  const float s0 = b00 * b11 - k01 * k01, s1 = b00 * k12 - k01 * k02, s2 = b00 * k13 - k01 * k03;
+  const float s3 = k01 * k12 - b11 * k02, s4 = k01 * k13 - b11 * k03, s5 = k02 * k13 - k12 * k03;
+  const float m5 = b22 * b33 - k23 * k23, m4 = k12 * b33 - k13 * k23, m3 = k12 * k23 - k13 * b22;
+  const float m2 = k02 * b33 - k03 * k23, m1 = k02 * k23 - k03 * b22, m0 = k02 * k13 - k03 * k12;
+  const float a00 = b11 * m5 - k12 * m4 + k13 * m3;
+  const float a01 = -k01 * m5 + k02 * m4 - k03 * m3;
+  const float a02 = k13 * s5 - k23 * s4 + b33 * s3;
+  const float a03 = -k12 * s5 + b22 * s4 - k23 * s3;
+  const float a11 = b00 * m5 - k02 * m2 + k03 * m1;
+  const float a12 = -k03 * s5 + k23 * s2 - b33 * s1;
+  const float a13 = k02 * s5 - b22 * s2 + k23 * s1;
+  const float a22 = k03 * s4 - k13 * s2 + b33 * s0;
+  const float a23 = -k02 * s4 + k12 * s2 - k23 * s0;
+  const float a33 = k02 * s3 - k12 * s1 + b22 * s0;
+  // column with the largest diagonal entry (|a_ii| ~ q_i^2 >= 1/4 of the trace)
+  float q0[4] = {a00, a01, a02, a03};
+  float best = fabsf(a00);
+  if (fabsf(a11) > best) { best = fabsf(a11); q0[0] = a01; q0[1] = a11; q0[2] = a12; q0[3] = a13; }
+  if (fabsf(a22) > best) { best = fabsf(a22); q0[0] = a02; q0[1] = a12; q0[2] = a22; q0[3] = a23; }
+  if (fabsf(a33) > best) { best = fabsf(a33); q0[0] = a03; q0[1] = a13; q0[2] = a23; q0[3] = a33; }
+  {
+    const float n2 = fmaf(q0[0], q0[0], fmaf(q0[1], q0[1], fmaf(q0[2], q0[2], q0[3] * q0[3])));
+    const float inv = rsqrtf(n2);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) q0[r] *= inv;
+  }
+  // first-order correction: with S' = R0^T S the residual rotation vector d solves (tr(P) I - P) d = vee(S')/2,
+  // P = sym(S'); the corrected quaternion is (1, d) * q0.
+  float R0[9];
+  quat_to_rot(q0, R0);
+  float T[9];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) T[3 * i + k] = fmaf(R0[i], S[k], fmaf(R0[3 + i], S[3 + k], R0[6 + i] * S[6 + k]));
+  const float p01 = 0.5f * (T[1] + T[3]), p02 = 0.5f * (T[2] + T[6]), p12 = 0.5f * (T[5] + T[7]);
+  const float e00 = T[4] + T[8], e11 = T[0] + T[8], e22 = T[0] + T[4];     // tr(P) - P_ii
+  const float r0 = 0.5f * (T[5] - T[7]), r1 = 0.5f * (T[6] - T[2]), r2 = 0.5f * (T[1] - T[3]);
+  const float g00 = e11 * e22 - p12 * p12;
+  const float g01 = p01 * e22 + p02 * p12;         // cofactors of [[e00,-p01,-p02],[-p01,e11,-p12],[-p02,-p12,e22]]
+  const float g02 = p01 * p12 + p02 * e11;
+  const float g11 = e00 * e22 - p02 * p02;
+  const float g12 = e00 * p12 + p01 * p02;
+  const float g22 = e00 * e11 - p01 * p01;
+  const float det = e00 * g00 - p01 * g01 - p02 * g02;
+  const float idet = __fdividef(1.0f, det);
+  const float d0 = (g00 * r0 + g01 * r1 + g02 * r2) * idet;
+  const float d1 = (g01 * r0 + g11 * r1 + g12 * r2) * idet;
+  const float d2 = (g02 * r0 + g12 * r1 + g22 * r2) * idet;
+  const float dn2 = fmaf(d0, d0, fmaf(d1, d1, d2 * d2));
+  // (1, d) * (a, v) = (a - d.v,  v + a d + d x v)
+  const float a = q0[0], vx = q0[1], vy = q0[2], vz = q0[3];
+  float qa = a - (d0 * vx + d1 * vy + d2 * vz);
+  float qx = vx + a * d0 + (d1 * vz - d2 * vy);
+  float qy = vy + a * d1 + (d2 * vx - d0 * vz);
+  float qz = vz + a * d2 + (d0 * vy - d1 * vx);
+  const float inv = rsqrtf(fmaf(qa, qa, fmaf(qx, qx, fmaf(qy, qy, qz * qz))));
+  q[0] = qa * inv; q[1] = qx * inv; q[2] = qy * inv; q[3] = qz * inv;
+  return dn2 < 1e-6f;             // false also for NaN
+}
+
 struct Rigid {
   float c[3];   // centroid of the alignment selection
   float R[9];   // row-major rotation, z = (x - c) R
@@ -155,52 +273,72 @@ struct Rigid {
 
 // Optimal superposition of frame `xf` ([n,3]) onto the centred reference.  All lanes of the group
 // return the same result.  aidx / refx may live in shared or global memory.
+//
+// One pass over the selection: sums are taken relative to a pivot atom p = x[A_0] (d_k = x_k - p), which
+// keeps fp32 accurate for frames far from the origin; since the reference is centred (sum_k y_k = 0),
+//   H = sum_k (x_k - c)^T y_k = sum_k d_k^T y_k      and      c = p + mean_k d_k.
 template <int G>
-__device__ __forceinline__ void kabsch(const float* __restrict__ xf, const int* __restrict__ aidx,
-                                       const float* __restrict__ refx, int n_align, int lane, Rigid& rg) {
+__device__ __forceinline__ void kabsch_moments(const float* __restrict__ xf, const int* __restrict__ aidx,
+                                               const float* __restrict__ refx, int n_align, int lane, Rigid& rg) {
+  const float* p0 = xf + 3 * aidx[0];
+  const float pvx = p0[0], pvy = p0[1], pvz = p0[2];
   float sx = 0.f, sy = 0.f, sz = 0.f;
-  for (int k = lane; k < n_align; k += G) {
-    const float* p = xf + 3 * aidx[k];
-    sx += p[0]; sy += p[1]; sz += p[2];
-  }
-  const float inv_n = 1.0f / (float)n_align;
-  rg.c[0] = gsum<G>(sx) * inv_n;
-  rg.c[1] = gsum<G>(sy) * inv_n;
-  rg.c[2] = gsum<G>(sz) * inv_n;
   float h[9];
 #pragma unroll
   for (int i = 0; i < 9; ++i) h[i] = 0.f;
   for (int k = lane; k < n_align; k += G) {
     const float* p = xf + 3 * aidx[k];
-    const float px = p[0] - rg.c[0], py = p[1] - rg.c[1], pz = p[2] - rg.c[2];
+    const float px = p[0] - pvx, py = p[1] - pvy, pz = p[2] - pvz;
     const float y0 = refx[3 * k], y1 = refx[3 * k + 1], y2 = refx[3 * k + 2];
+    sx += px; sy += py; sz += pz;
     h[0] = fmaf(px, y0, h[0]); h[1] = fmaf(px, y1, h[1]); h[2] = fmaf(px, y2, h[2]);
     h[3] = fmaf(py, y0, h[3]); h[4] = fmaf(py, y1, h[4]); h[5] = fmaf(py, y2, h[5]);
     h[6] = fmaf(pz, y0, h[6]); h[7] = fmaf(pz, y1, h[7]); h[8] = fmaf(pz, y2, h[8]);
   }
+  const float inv_n = 1.0f / (float)n_align;
+  rg.c[0] = fmaf(gsum<G>(sx), inv_n, pvx);
+  rg.c[1] = fmaf(gsum<G>(sy), inv_n, pvy);
+  rg.c[2] = fmaf(gsum<G>(sz), inv_n, pvz);
 #pragma unroll
   for (int i = 0; i < 9; ++i) rg.H[i] = gsum<G>(h[i]);
-  const float Sxx = rg.H[0], Sxy = rg.H[1], Sxz = rg.H[2];
-  const float Syx = rg.H[3], Syy = rg.H[4], Syz = rg.H[5];
-  const float Szx = rg.H[6], Szy = rg.H[7], Szz = rg.H[8];
-  float a[4][4];
-  a[0][0] = Sxx + Syy + Szz; a[0][1] = Syz - Szy; a[0][2] = Szx - Sxz; a[0][3] = Sxy - Syx;
-  a[1][1] = Sxx - Syy - Szz; a[1][2] = Sxy + Syx; a[1][3] = Szx + Sxz;
-  a[2][2] = -Sxx + Syy - Szz; a[2][3] = Syz + Szy;
-  a[3][3] = -Sxx - Syy + Szz;
-  a[1][0] = a[2][0] = a[2][1] = a[3][0] = a[3][1] = a[3][2] = 0.f;   // lower triangle unused
+}
+
+// rg.R from rg.H.  Must be called by all 32 lanes of a warp (the Jacobi fallback votes).
+__device__ __forceinline__ void kabsch_rotation(Rigid& rg) {
+  float nrm2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) nrm2 = fmaf(rg.H[i], rg.H[i], nrm2);
+  const float inv = rsqrtf(nrm2);
+  float S[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) S[i] = rg.H[i] * inv;
   float q[4];
-  dominant_eigvec4(a, q);
-  const float qa = q[0], qb = q[1], qc = q[2], qd = q[3];
-  rg.R[0] = qa * qa + qb * qb - qc * qc - qd * qd;
-  rg.R[1] = 2.f * (qb * qc + qa * qd);
-  rg.R[2] = 2.f * (qb * qd - qa * qc);
-  rg.R[3] = 2.f * (qb * qc - qa * qd);
-  rg.R[4] = qa * qa - qb * qb + qc * qc - qd * qd;
-  rg.R[5] = 2.f * (qc * qd + qa * qb);
-  rg.R[6] = 2.f * (qb * qd + qa * qc);
-  rg.R[7] = 2.f * (qc * qd - qa * qb);
-  rg.R[8] = qa * qa - qb * qb - qc * qc + qd * qd;
+  const bool ok = dominant_quat_fast(S, q);
+  if (!__all_sync(0xffffffffu, ok)) {        // rare: near-degenerate frames take the Jacobi route
+    const float Sxx = rg.H[0], Sxy = rg.H[1], Sxz = rg.H[2];
+    const float Syx = rg.H[3], Syy = rg.H[4], Syz = rg.H[5];
+    const float Szx = rg.H[6], Szy = rg.H[7], Szz = rg.H[8];
+    float a[4][4];
+    a[0][0] = Sxx + Syy + Szz; a[0][1] = Syz - Szy; a[0][2] = Szx - Sxz; a[0][3] = Sxy - Syx;
+    a[1][1] = Sxx - Syy - Szz; a[1][2] = Sxy + Syx; a[1][3] = Szx + Sxz;
+    a[2][2] = -Sxx + Syy - Szz; a[2][3] = Syz + Szy;
+    a[3][3] = -Sxx - Syy + Szz;
+    a[1][0] = a[2][0] = a[2][1] = a[3][0] = a[3][1] = a[3][2] = 0.f;   // lower triangle unused
+    float qj[4];
+    dominant_eigvec4(a, qj, !ok);
+    if (!ok) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) q[r] = qj[r];
+    }
+  }
+  quat_to_rot(q, rg.R);
+}
+
+template <int G>
+__device__ __forceinline__ void kabsch(const float* __restrict__ xf, const int* __restrict__ aidx,
+                                       const float* __restrict__ refx, int n_align, int lane, Rigid& rg) {
+  kabsch_moments<G>(xf, aidx, refx, n_align, lane, rg);
+  kabsch_rotation(rg);
 }
 
 // z = (p - c) R

@@ -103,6 +103,21 @@ void emu_align_backward(int n_inp, int n_align, const int* aidx, const float* re
   }
 }
 
+// rotation of every frame (row-major R, z = (x - c) R) and whether the fast polynomial path accepted it
+void emu_kabsch(int n_inp, int n_align, const int* aidx, const float* ref, const float* x, long long L, float* Rout,
+                int* fast_ok) {
+  for (long long f = 0; f < L; ++f) {
+    const float* xf = x + f * 3 * n_inp;
+    Rigid rg;
+    kabsch<1>(xf, aidx, ref, n_align, 0, rg);
+    for (int i = 0; i < 9; ++i) Rout[9 * f + i] = rg.R[i];
+    float n2 = 0.f, S[9], q[4];
+    for (int i = 0; i < 9; ++i) n2 += rg.H[i] * rg.H[i];
+    for (int i = 0; i < 9; ++i) S[i] = rg.H[i] / sqrtf(n2);
+    fast_ok[f] = dominant_quat_fast(S, q) ? 1 : 0;
+  }
+}
+
 float emu_act_forward(float v, int act) { return act_forward(v, act); }
 float emu_act_grad(float h, int act) { return act_grad_from_output(h, act); }
 

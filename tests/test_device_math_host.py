@@ -90,6 +90,48 @@ def test_alignment_standalone_and_reflection_frames(emu):
         assert float(frame_rel_err(gx, gx64)[ok].median()) < 1e-5
 
 
+def _svd_rotation64(x, aidx, ref):
+    xs = x[:, aidx, :].astype(np.float64)
+    xt = xs - xs.mean(1, keepdims=True)
+    H = np.einsum("nka,kb->nab", xt, ref.astype(np.float64))
+    U, s, Vt = np.linalg.svd(H)
+    d = np.sign(np.linalg.det(U @ Vt))
+    D = np.zeros_like(H)
+    D[:, 0, 0] = 1
+    D[:, 1, 1] = 1
+    D[:, 2, 2] = d
+    return U @ D @ Vt, (s[:, 1] + s[:, 2] * d) / s[:, 0]
+
+
+def test_fast_rotation_path_accuracy_and_fallback(emu):
+    """The polynomial (QCP) + first-order-correction path must (a) be the one taken on well-conditioned
+    trajectories, (b) agree with the fp64 SVD route of the reference (ann.py:188-195) to fp32 rounding, and
+    (c) hand near-degenerate frames to the Jacobi fallback instead of returning a poor rotation."""
+    spec = S.get_spec("C2")
+    aidx, ref, _, _, _ = spec_program(spec)
+    a = np.asarray(aidx, np.int32)
+    r = np.ascontiguousarray(ref.numpy(), np.float32)
+    L = 20000
+    x = S.make_frames(spec, L, seed=99).numpy()
+    Rk = np.zeros((L, 9), np.float32)
+    ok = np.zeros(L, np.int32)
+    emu.emu_kabsch(x.shape[1], len(a), ptr(a), ptr(r), ptr(x), ctypes.c_longlong(L), ptr(Rk), ptr(ok))
+    R64, gap = _svd_rotation64(x, aidx, r)
+    assert ok.mean() > 0.999
+    assert np.abs(Rk.reshape(L, 3, 3) - R64).max() < 1.5e-6
+    # random point clouds: many reflections / small gaps -> fallback must keep the answer right
+    rng = np.random.RandomState(5)
+    x2 = (rng.randn(L, x.shape[1], 3) * 2 + 10).astype(np.float32)
+    emu.emu_kabsch(x.shape[1], len(a), ptr(a), ptr(r), ptr(x2), ctypes.c_longlong(L), ptr(Rk), ptr(ok))
+    R64, gap = _svd_rotation64(x2, aidx, r)
+    err = np.abs(Rk.reshape(L, 3, 3) - R64).max((1, 2))
+    assert 0.5 < ok.mean() < 1.0                       # both paths exercised
+    cond = np.abs(gap) > 0.05
+    assert err[cond].max() < 2e-5
+    assert err[cond & (ok == 1)].max() < 2e-5
+    assert np.isfinite(Rk).all()
+
+
 def test_activations(emu):
     emu.emu_act_forward.restype = ctypes.c_float
     emu.emu_act_forward.argtypes = [ctypes.c_float, ctypes.c_int]
