@@ -1,0 +1,547 @@
+// fused_ws.cuh -- warp-specialised fused forward kernel for small systems (the C2 class:
+// n_inp small, feature / hidden widths <= 64, <= 8 outputs, 1 or 2 hidden layers).
+//
+// One persistent CTA per SM; tiles of 128 frames flow through a pipeline of ROLES that run concurrently on
+// different tiles and hand over through mbarriers and TMEM:
+//
+//   producer (1 thread)   TMA bulk copy of the tile's contiguous byte range of x into a 3-deep smem ring
+//   G  (NG x 4 warps)     thread = frame: pivoted moments, rotation (polynomial path, Jacobi fallback),
+//                         feature program; features leave as TF32 hi/lo rows of the A operand in TMEM.
+//                         The geometry is one long dependent chain per frame, so NG warpgroups work on NG
+//                         different tiles at once (it needs no TMEM until its last step)
+//   MMA-1 (1 thread)      tcgen05.mma 3xTF32  D1 = A1 * W1^T      (A from TMEM, W in smem for the whole kernel)
+//   E1 (4 warps)          thread = frame: D1 -> bias + activation -> TF32 hi/lo -> A2 operand in TMEM
+//   MMA-2 (1 thread)      D2 = A2 * W2^T
+//   E2 (4 warps)          thread = frame: D2 -> bias + activation -> last (narrow) layer as a register dot
+//                         product -> y
+//
+// Why: the single-role kernel (fused_tc.cuh) is bound by instruction issue and dependency latency with two
+// warps per scheduler (profiles/r1_c: issue 43 %, stall "wait" 35 %), and every tile serialises on the two
+// MMA round trips.  Here each scheduler holds a G, an E1 and an E2 warp with different pipe mixes (FMA chains /
+// MUFU-heavy), the MMA latency is hidden behind the other roles' work on other tiles, and no CTA-wide barrier
+// is left in the steady state.
+//
+// TMEM map (512 columns): A1 double-buffered (2 x 2*kp0), A2 double-buffered when it fits (2 x 2*kp1),
+// D1, D2 single (their consumers copy them to registers at once and release them).
+// Weights and biases are pre-multiplied by the activation's exponent scale (tanh: 2 log2 e) while they are
+// staged, so the epilogue is  e = ex2(acc + b');  h = 1 - 2 / (1 + e).
+#pragma once
+#include "common.cuh"
+#include "geometry.cuh"
+#include "tc.cuh"
+#include "fused_tc.cuh"
+
+namespace molann {
+
+constexpr int WS_F = 128;
+constexpr int WS_NG = 2;                     // geometry warpgroups (tiles in flight in the G stage)
+constexpr int WS_XBUF = WS_NG + 2;           // coordinate-tile ring
+constexpr int WS_WARPS = 4 * WS_NG + 4 + 4 + 3;   // G + E1 + E2 + producer + 2 MMA issuers
+constexpr int WS_THREADS = WS_WARPS * 32;
+constexpr int WS_W_E1 = 4 * WS_NG, WS_W_E2 = WS_W_E1 + 4, WS_W_PROD = WS_W_E2 + 4, WS_W_MMA1 = WS_W_PROD + 1,
+              WS_W_MMA2 = WS_W_PROD + 2;
+
+struct WsLayout {
+  TcLayout base;                             // weights / biases / plan constants (xs_off, mbar_off unused)
+  int xs_off[WS_XBUF];
+  int mbar_off, tptr_off;
+  int ref4_off;                              // reference rows padded to float4
+  int aoff_off;                              // 3 * align_idx (element offsets into a frame)
+  int n_a2buf;                               // 1 or 2 A2 buffers
+  int col_a1[2], col_a2[2], col_d1, col_d2;  // TMEM column bases
+  int tmem_cols;
+  int total_bytes;
+};
+
+__device__ __forceinline__ void mbar_arrive(void* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// wait with a suspend-time hint: the thread sleeps in hardware until the phase completes (or the hint
+// expires) instead of burning issue slots that the working roles on the same scheduler need
+__device__ __forceinline__ void mbar_wait_hint(void* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WS_WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra WS_DONE_%=;\n\t"
+      "bra WS_WAIT_%=;\n\t"
+      "WS_DONE_%=:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity), "r"(0x989680u)
+      : "memory");
+}
+
+__host__ __device__ inline float ws_scale_for_act(int act) {
+  return act == ACT_TANH ? 2.8853900817779268f : (act == ACT_SIGMOID ? -1.4426950408889634f : 1.0f);
+}
+
+// activation on a pre-scaled pre-activation
+template <int ACT>
+__device__ __forceinline__ float ws_act(float zs) {
+  if (ACT == ACT_TANH) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(zs));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return fmaf(-2.0f, r, 1.0f);
+  } else if (ACT == ACT_SIGMOID) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(zs));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return r;
+  } else if (ACT == ACT_RELU) {
+    return fmaxf(zs, 0.f);
+  }
+  return zs;
+}
+
+// weights of MMA layer k, multiplied by `scale`, split into chunk-major hi/lo operands
+__device__ __forceinline__ void ws_stage_weights(const float* __restrict__ Wg, const float* __restrict__ bg, int K, int N,
+                                                 int kp, int np, float scale, unsigned char* bhi, unsigned char* blo,
+                                                 float* bias, int tid, int nthreads) {
+  for (int idx = tid; idx < np * kp; idx += nthreads) {
+    const int n = idx / kp, k = idx - n * kp;
+    const float w = (n < N && k < K) ? scale * Wg[(long long)n * K + k] : 0.f;
+    uint32_t hi, lo;
+    split_tf32_rn(w, hi, lo);
+    lo = (lo + 0x1000u) & 0xffffe000u;
+    const uint32_t off = chunk_major_offset(n, k, np);
+    *reinterpret_cast<uint32_t*>(bhi + off) = hi;
+    *reinterpret_cast<uint32_t*>(blo + off) = lo;
+  }
+  for (int n = tid; n < np; n += nthreads) bias[n] = (n < N) ? scale * bg[n] : 0.f;
+}
+
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st2(uint32_t taddr, uint32_t a, uint32_t b) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(taddr), "r"(a), "r"(b) : "memory");
+}
+// N consecutive columns (N = 3 * atoms of a group: 24, 12, 6 or 3) as the widest stores that tile it
+template <int N>
+__device__ __forceinline__ void tmem_st_cols(uint32_t taddr, const uint32_t (&v)[N]) {
+  int c = 0;
+  if (N - c >= 16) {
+    tmem_st16(taddr + c, *reinterpret_cast<const uint32_t(*)[16]>(&v[c]));
+    c += 16;
+  }
+  if (N - c >= 8) {
+    tmem_st8(taddr + c, *reinterpret_cast<const uint32_t(*)[8]>(&v[c]));
+    c += 8;
+  }
+  if (N - c >= 4) {
+    tmem_st4(taddr + c, v[c], v[c + 1], v[c + 2], v[c + 3]);
+    c += 4;
+  }
+  if (N - c >= 2) {
+    tmem_st2(taddr + c, v[c], v[c + 1]);
+    c += 2;
+  }
+  if (N - c >= 1) tmem_st1(taddr + c, v[c]);
+}
+
+// ---- E1: accumulator -> activation -> next layer's A operand, 16 columns at a time -------------------
+// (rolled loops: each role streams its own code, and the three roles of a scheduler must share the
+// instruction caches -- see profiles/r1_d: "no instruction" was the top stall with unrolled epilogues)
+template <int ACT>
+__device__ __forceinline__ void ws_hidden_epilogue(uint32_t lane_d, uint32_t lane_ahi, uint32_t lane_alo,
+                                                   const float* __restrict__ bias, int np, void* bar_d_free,
+                                                   void* bar_a_empty, uint32_t par_a_empty, void* bar_a_full) {
+  float z[16], zn[16];
+  tmem_ld16(lane_d, z);
+#pragma unroll 1
+  for (int c0 = 0; c0 < np; c0 += 16) {
+    tmem_wait_ld();
+    if (c0 + 16 < np) {
+      tmem_ld16(lane_d + c0 + 16, zn);         // next chunk in flight while this one is processed
+    } else {                                   // the accumulator is in registers: the next tile's MMA may start
+      tc_fence_before_sync();
+      mbar_arrive(bar_d_free);
+    }
+    const float4* b4 = reinterpret_cast<const float4*>(bias + c0);
+    uint32_t hi[16], lo[16];
+#pragma unroll
+    for (int c = 0; c < 16; c += 4) {
+      const float4 b = b4[c >> 2];
+      split_tf32_rn(ws_act<ACT>(z[c] + b.x), hi[c], lo[c]);
+      split_tf32_rn(ws_act<ACT>(z[c + 1] + b.y), hi[c + 1], lo[c + 1]);
+      split_tf32_rn(ws_act<ACT>(z[c + 2] + b.z), hi[c + 2], lo[c + 2]);
+      split_tf32_rn(ws_act<ACT>(z[c + 3] + b.w), hi[c + 3], lo[c + 3]);
+    }
+    if (c0 == 0) {                             // the MMA that last read this A2 buffer is complete
+      mbar_wait_hint(bar_a_empty, par_a_empty);
+      tc_fence_after_sync();
+    }
+    tmem_st16(lane_ahi + c0, hi);
+    tmem_st16(lane_alo + c0, lo);
+#pragma unroll
+    for (int c = 0; c < 16; ++c) z[c] = zn[c];
+  }
+  tmem_wait_st();
+  tc_fence_before_sync();
+  mbar_arrive(bar_a_full);
+}
+
+// ---- E2: accumulator -> activation -> last layer (register dot products) -> y ---------------------
+template <int ACT>
+__device__ __forceinline__ void ws_final_epilogue(uint32_t lane_d, const float* __restrict__ bias, int np,
+                                                  void* bar_d_free, const float* __restrict__ wl,
+                                                  const float* __restrict__ bl, int kout, float* __restrict__ yrow,
+                                                  bool valid) {
+  float acc[8];
+#pragma unroll
+  for (int o = 0; o < 8; ++o) acc[o] = (o < kout) ? bl[o] : 0.f;
+  float z[16], zn[16];
+  tmem_ld16(lane_d, z);
+#pragma unroll 1
+  for (int c0 = 0; c0 < np; c0 += 16) {
+    tmem_wait_ld();
+    if (c0 + 16 < np) {
+      tmem_ld16(lane_d + c0 + 16, zn);
+    } else {
+      tc_fence_before_sync();
+      mbar_arrive(bar_d_free);
+    }
+    const float4* b4 = reinterpret_cast<const float4*>(bias + c0);
+#pragma unroll
+    for (int c = 0; c < 16; c += 4) {
+      const float4 b = b4[c >> 2];
+      z[c] = ws_act<ACT>(z[c] + b.x);
+      z[c + 1] = ws_act<ACT>(z[c + 1] + b.y);
+      z[c + 2] = ws_act<ACT>(z[c + 2] + b.z);
+      z[c + 3] = ws_act<ACT>(z[c + 3] + b.w);
+    }
+    if (kout == 2) {                            // the common case: two collective variables
+      const float4* w0 = reinterpret_cast<const float4*>(wl + c0);
+      const float4* w1 = reinterpret_cast<const float4*>(wl + TC_MAXW + c0);
+      float a0 = 0.f, a1 = 0.f, d0 = 0.f, d1 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 u = w0[j], v = w1[j];
+        a0 = fmaf(z[4 * j], u.x, a0); d0 = fmaf(z[4 * j + 1], u.y, d0);
+        a0 = fmaf(z[4 * j + 2], u.z, a0); d0 = fmaf(z[4 * j + 3], u.w, d0);
+        a1 = fmaf(z[4 * j], v.x, a1); d1 = fmaf(z[4 * j + 1], v.y, d1);
+        a1 = fmaf(z[4 * j + 2], v.z, a1); d1 = fmaf(z[4 * j + 3], v.w, d1);
+      }
+      acc[0] += a0 + d0;
+      acc[1] += a1 + d1;
+    } else {
+#pragma unroll
+      for (int o = 0; o < 8; ++o) {
+        if (o < kout) {
+          const float4* w4 = reinterpret_cast<const float4*>(wl + o * TC_MAXW + c0);
+          float a0 = 0.f, d0 = 0.f;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 w = w4[j];
+            a0 = fmaf(z[4 * j], w.x, a0); d0 = fmaf(z[4 * j + 1], w.y, d0);
+            a0 = fmaf(z[4 * j + 2], w.z, a0); d0 = fmaf(z[4 * j + 3], w.w, d0);
+          }
+          acc[o] += a0 + d0;
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 16; ++c) z[c] = zn[c];
+  }
+  if (valid) {
+    if (kout == 2) {
+      *reinterpret_cast<float2*>(yrow) = make_float2(acc[0], acc[1]);
+    } else {
+#pragma unroll
+      for (int o = 0; o < 8; ++o)
+        if (o < kout) yrow[o] = acc[o];
+    }
+  }
+}
+
+// ---- G: NA position entries (3 NA feature columns) straight into the A operand ---------------------
+// z = (x - c) R = x R - t with t = c R.
+template <int NA>
+__device__ __forceinline__ void ws_position_group(const float* __restrict__ xf, const int* __restrict__ ent, int e0,
+                                                  const float (&R)[9], float t0, float t1, float t2,
+                                                  uint32_t lane_ahi, uint32_t lane_alo) {
+  uint32_t hi[3 * NA], lo[3 * NA];
+#pragma unroll
+  for (int i = 0; i < NA; ++i) {
+    const float* p = xf + 3 * ent[ENTRY_INTS * (e0 + i) + 1];
+    const float px = p[0], py = p[1], pz = p[2];
+    const float zx = fmaf(px, R[0], fmaf(py, R[3], fmaf(pz, R[6], -t0)));
+    const float zy = fmaf(px, R[1], fmaf(py, R[4], fmaf(pz, R[7], -t1)));
+    const float zz = fmaf(px, R[2], fmaf(py, R[5], fmaf(pz, R[8], -t2)));
+    split_tf32_rn(zx, hi[3 * i], lo[3 * i]);
+    split_tf32_rn(zy, hi[3 * i + 1], lo[3 * i + 1]);
+    split_tf32_rn(zz, hi[3 * i + 2], lo[3 * i + 2]);
+  }
+  tmem_st_cols<3 * NA>(lane_ahi + 3 * e0, hi);
+  tmem_st_cols<3 * NA>(lane_alo + 3 * e0, lo);
+}
+
+__device__ __forceinline__ void ws_position_features(const float* __restrict__ xf, const int* __restrict__ ent,
+                                                     int n_lead, const Rigid& rg, uint32_t lane_ahi,
+                                                     uint32_t lane_alo) {
+  const float t0 = fmaf(rg.c[0], rg.R[0], fmaf(rg.c[1], rg.R[3], rg.c[2] * rg.R[6]));
+  const float t1 = fmaf(rg.c[0], rg.R[1], fmaf(rg.c[1], rg.R[4], rg.c[2] * rg.R[7]));
+  const float t2 = fmaf(rg.c[0], rg.R[2], fmaf(rg.c[1], rg.R[5], rg.c[2] * rg.R[8]));
+  int e0 = 0;
+#pragma unroll 1
+  for (; e0 + 4 <= n_lead; e0 += 4) ws_position_group<4>(xf, ent, e0, rg.R, t0, t1, t2, lane_ahi, lane_alo);
+  if (e0 + 2 <= n_lead) {
+    ws_position_group<2>(xf, ent, e0, rg.R, t0, t1, t2, lane_ahi, lane_alo);
+    e0 += 2;
+  }
+  if (e0 < n_lead) ws_position_group<1>(xf, ent, e0, rg.R, t0, t1, t2, lane_ahi, lane_alo);
+}
+
+// =============================================================================================
+template <int ACT>
+__global__ void __launch_bounds__(WS_THREADS, 1)
+fused_ws_forward_kernel(const __grid_constant__ DevPlan p, const __grid_constant__ WsLayout wl,
+                        const float* __restrict__ x, float* __restrict__ y, long long L) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const TcLayout& lay = wl.base;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n3 = 3 * p.n_inp;
+  const int nl = p.n_layers;
+  const int nh = nl - 1;                      // 1 or 2 tensor-core layers
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + wl.mbar_off);
+  unsigned long long* x_full = bars;                   // [WS_XBUF]
+  unsigned long long* x_empty = bars + WS_XBUF;        // [WS_XBUF]
+  unsigned long long* a1_full = bars + 2 * WS_XBUF;    // [2]
+  unsigned long long* a1_empty = a1_full + 2;          // [2]
+  unsigned long long* a2_full = a1_empty + 2;          // [2]
+  unsigned long long* a2_empty = a2_full + 2;          // [2]
+  unsigned long long* d1_full = a2_empty + 2;
+  unsigned long long* d1_free = d1_full + 1;
+  unsigned long long* d2_full = d1_free + 1;
+  unsigned long long* d2_free = d2_full + 1;
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(smem + wl.tptr_off);
+
+  // ---- one-time staging (all threads) ----
+  {
+    const float scale = ws_scale_for_act(ACT);
+    for (int k = 0; k < nh; ++k)
+      ws_stage_weights(p.W[k], p.b[k], p.dims[k], p.dims[k + 1], lay.kp[k], lay.np[k], scale, smem + lay.bhi_off[k],
+                       smem + lay.blo_off[k], reinterpret_cast<float*>(smem + lay.bias_off[k]), tid, WS_THREADS);
+    const int K = p.dims[nl - 1], N = p.dims[nl];
+    float* wlast = reinterpret_cast<float*>(smem + lay.wlast_off);
+    float* blast = reinterpret_cast<float*>(smem + lay.blast_off);
+    for (int i = tid; i < N * TC_MAXW; i += WS_THREADS) {
+      const int o = i / TC_MAXW, j = i - o * TC_MAXW;
+      wlast[i] = (j < K) ? p.W[nl - 1][(long long)o * K + j] : 0.f;
+    }
+    for (int o = tid; o < N; o += WS_THREADS) blast[o] = p.b[nl - 1][o];
+    int* aoff = reinterpret_cast<int*>(smem + wl.aoff_off);
+    float4* ref4 = reinterpret_cast<float4*>(smem + wl.ref4_off);
+    int* ent = reinterpret_cast<int*>(smem + lay.ent_off);
+    for (int i = tid; i < p.n_align; i += WS_THREADS) {
+      aoff[i] = 3 * p.align_idx[i];
+      ref4[i] = make_float4(p.ref_x[3 * i], p.ref_x[3 * i + 1], p.ref_x[3 * i + 2], 0.f);
+    }
+    for (int i = tid; i < ENTRY_INTS * p.n_entries; i += WS_THREADS) ent[i] = p.entries[i];
+  }
+  if (tid == 0) {
+    for (int b = 0; b < WS_XBUF; ++b) {
+      mbar_init(&x_full[b], 1);
+      mbar_init(&x_empty[b], WS_F);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&a1_full[b], WS_F);
+      mbar_init(&a1_empty[b], 1);
+      mbar_init(&a2_full[b], WS_F);
+      mbar_init(&a2_empty[b], 1);
+    }
+    mbar_init(d1_full, 1);
+    mbar_init(d1_free, WS_F);
+    mbar_init(d2_full, 1);
+    mbar_init(d2_free, WS_F);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(tptr, (uint32_t)wl.tmem_cols);
+  fence_proxy_async_smem();                   // weight operands are read by the tensor core (async proxy)
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tbase = *tptr;
+  const uint32_t lane_base = tbase + ((uint32_t)((warp & 3) * 32) << 16);
+
+  const long long ntiles = (L + WS_F - 1) / WS_F;
+  const uint32_t tile_bytes = (uint32_t)WS_F * (uint32_t)n3 * 4u;
+  const long long first = blockIdx.x, stride = gridDim.x;
+  // with one hidden layer the only accumulator is "D2" and E1 / MMA-2 have nothing to do
+  const int col_dlast = wl.col_d2;
+
+  if (warp == WS_W_PROD) {
+    // ================= producer =================
+    int i = 0;
+    for (long long tile = first; tile < ntiles; tile += stride, ++i) {
+      const int b = i % WS_XBUF;
+      const uint32_t par = (uint32_t)((i / WS_XBUF) & 1);
+      float* dst = reinterpret_cast<float*>(smem + wl.xs_off[b]);
+      const long long f_base = tile * (long long)WS_F;
+      const bool full = f_base + WS_F <= L;
+      if (lane == 0) mbar_wait_hint(&x_empty[b], par ^ 1u);
+      __syncwarp();
+      if (full) {
+        if (lane == 0) {
+          mbar_expect_tx(&x_full[b], tile_bytes);
+          bulk_g2s(dst, x + f_base * n3, tile_bytes, &x_full[b]);
+        }
+      } else {                                 // ragged last tile: plain coalesced copy by the warp
+        const int nf = (int)(L - f_base);
+        const float* src = x + f_base * n3;
+        for (int j = lane; j < nf * n3; j += 32) dst[j] = src[j];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&x_full[b]);
+      }
+    }
+  } else if (warp == WS_W_MMA1) {
+    // ================= MMA issuer, layer 1 =================
+    if (lane == 0) {
+      int i = 0;
+      for (long long tile = first; tile < ntiles; tile += stride, ++i) {
+        const int ab = i & 1;
+        mbar_wait_hint(&a1_full[ab], (uint32_t)((i >> 1) & 1));
+        mbar_wait_hint(nh == 2 ? d1_free : d2_free, (uint32_t)((i & 1) ^ 1));
+        tc_fence_after_sync();
+        const uint32_t colA = (uint32_t)wl.col_a1[ab];
+        const uint32_t colD = (uint32_t)(nh == 2 ? wl.col_d1 : col_dlast);
+        issue_layer_mma(tbase, colA, colA + lay.kp[0], colD, smem + lay.bhi_off[0], smem + lay.blo_off[0], lay.kp[0],
+                        lay.np[0], &a1_empty[ab]);
+        mma_commit(nh == 2 ? d1_full : d2_full);
+      }
+    }
+  } else if (warp == WS_W_MMA2) {
+    // ================= MMA issuer, layer 2 =================
+    if (lane == 0 && nh == 2) {
+      int i = 0;
+      for (long long tile = first; tile < ntiles; tile += stride, ++i) {
+        const int ab = i % wl.n_a2buf;
+        mbar_wait_hint(&a2_full[ab], (uint32_t)((i / wl.n_a2buf) & 1));
+        mbar_wait_hint(d2_free, (uint32_t)((i & 1) ^ 1));
+        tc_fence_after_sync();
+        const uint32_t colA = (uint32_t)wl.col_a2[ab];
+        issue_layer_mma(tbase, colA, colA + lay.kp[1], (uint32_t)wl.col_d2, smem + lay.bhi_off[1],
+                        smem + lay.blo_off[1], lay.kp[1], lay.np[1], &a2_empty[ab]);
+        mma_commit(d2_full);
+      }
+    }
+  } else if (warp < WS_W_E1) {
+    // ================= G: geometry + features; warpgroup g takes local tiles g, g + NG, ... =================
+    const int g = warp >> 2;
+    const int ft = tid & (WS_F - 1);            // frame within the tile
+    const int* aoff = reinterpret_cast<const int*>(smem + wl.aoff_off);
+    const float4* ref4 = reinterpret_cast<const float4*>(smem + wl.ref4_off);
+    const int* ent = reinterpret_cast<const int*>(smem + lay.ent_off);
+    const bool aligned = p.n_align > 0;
+    const int kp0 = lay.kp[0];
+    int n_lead = 0;                              // leading position entries take the unrolled path
+    while (n_lead < p.n_entries && ent[ENTRY_INTS * n_lead] == FEAT_POSITION) ++n_lead;
+    const bool mixed = n_lead < p.n_entries;
+    int i = g;
+    for (long long tile = first + (long long)g * stride; tile < ntiles; tile += WS_NG * stride, i += WS_NG) {
+      const int b = i % WS_XBUF;
+      const long long f_base = tile * (long long)WS_F;
+      const int nf = (int)((L - f_base) < (long long)WS_F ? (L - f_base) : (long long)WS_F);
+      const int f = ft < nf ? ft : nf - 1;
+      const float* xf = reinterpret_cast<const float*>(smem + wl.xs_off[b]) + f * n3;
+      mbar_wait_hint(&x_full[b], (uint32_t)((i / WS_XBUF) & 1));
+      Rigid rg;
+      if (aligned) {
+        // moments relative to the pivot atom (see kabsch_moments), reference rows as float4
+        const float* p0 = xf + aoff[0];
+        const float pvx = p0[0], pvy = p0[1], pvz = p0[2];
+        float sx = 0.f, sy = 0.f, sz = 0.f;
+        float h[9];
+#pragma unroll
+        for (int q = 0; q < 9; ++q) h[q] = 0.f;
+#pragma unroll 1
+        for (int k = 0; k < p.n_align; ++k) {
+          const float* pk = xf + aoff[k];
+          const float4 yk = ref4[k];
+          const float px = pk[0] - pvx, py = pk[1] - pvy, pz = pk[2] - pvz;
+          sx += px; sy += py; sz += pz;
+          h[0] = fmaf(px, yk.x, h[0]); h[1] = fmaf(px, yk.y, h[1]); h[2] = fmaf(px, yk.z, h[2]);
+          h[3] = fmaf(py, yk.x, h[3]); h[4] = fmaf(py, yk.y, h[4]); h[5] = fmaf(py, yk.z, h[5]);
+          h[6] = fmaf(pz, yk.x, h[6]); h[7] = fmaf(pz, yk.y, h[7]); h[8] = fmaf(pz, yk.z, h[8]);
+        }
+        const float inv_n = 1.0f / (float)p.n_align;
+        rg.c[0] = fmaf(sx, inv_n, pvx);
+        rg.c[1] = fmaf(sy, inv_n, pvy);
+        rg.c[2] = fmaf(sz, inv_n, pvz);
+#pragma unroll
+        for (int q = 0; q < 9; ++q) rg.H[q] = h[q];
+        kabsch_rotation(rg);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 9; ++q) rg.R[q] = (q == 0 || q == 4 || q == 8) ? 1.f : 0.f;
+        rg.c[0] = rg.c[1] = rg.c[2] = 0.f;
+      }
+      const int ab = i & 1;
+      const uint32_t lane_ahi = lane_base + (uint32_t)wl.col_a1[ab];
+      const uint32_t lane_alo = lane_ahi + (uint32_t)kp0;
+      mbar_wait_hint(&a1_empty[ab], (uint32_t)(((i >> 1) & 1) ^ 1));
+      tc_fence_after_sync();
+      if (mixed) {
+        zero_a_operand(lane_base, (uint32_t)wl.col_a1[ab], (uint32_t)wl.col_a1[ab] + kp0, kp0);
+      } else {                                   // only the padding columns [d_feat, kp0) need zeros
+        for (int c = p.d_feat; c < kp0; ++c) {
+          tmem_st1(lane_ahi + c, 0u);
+          tmem_st1(lane_alo + c, 0u);
+        }
+      }
+      if (n_lead > 0) ws_position_features(xf, ent, n_lead, rg, lane_ahi, lane_alo);
+      if (mixed) {
+        TmemFeatOut out{lane_ahi, lane_alo};
+        for (int e = n_lead; e < p.n_entries; ++e) {
+          const Entry en = load_entry(ent + ENTRY_INTS * e);
+          feature_forward(en, xf, aligned, rg, p.use_angle, out);
+        }
+      }
+      tmem_wait_st();
+      tc_fence_before_sync();
+      mbar_arrive(&a1_full[ab]);
+      mbar_arrive(&x_empty[b]);
+    }
+  } else if (warp < WS_W_E2) {
+    // ================= E1 =================
+    if (nh == 2) {
+      const float* bias = reinterpret_cast<const float*>(smem + lay.bias_off[0]);
+      int i = 0;
+      for (long long tile = first; tile < ntiles; tile += stride, ++i) {
+        const int ab = i % wl.n_a2buf;
+        const uint32_t par_e = (uint32_t)(((i / wl.n_a2buf) & 1) ^ 1);
+        const uint32_t lane_ahi = lane_base + (uint32_t)wl.col_a2[ab];
+        const uint32_t lane_alo = lane_ahi + (uint32_t)lay.kp[1];
+        mbar_wait_hint(d1_full, (uint32_t)(i & 1));
+        tc_fence_after_sync();
+        ws_hidden_epilogue<ACT>(lane_base + wl.col_d1, lane_ahi, lane_alo, bias, lay.np[0], d1_free, &a2_empty[ab],
+                                par_e, &a2_full[ab]);
+      }
+    }
+  } else if (warp < WS_W_PROD) {
+    // ================= E2 =================
+    const float* bias = reinterpret_cast<const float*>(smem + lay.bias_off[nh - 1]);
+    const float* wlast = reinterpret_cast<const float*>(smem + lay.wlast_off);
+    const float* blast = reinterpret_cast<const float*>(smem + lay.blast_off);
+    const int kout = p.dims[nl];
+    const int np = lay.np[nh - 1];
+    const int ft = tid & (WS_F - 1);            // frame within the tile
+    int i = 0;
+    for (long long tile = first; tile < ntiles; tile += stride, ++i) {
+      const long long f_base = tile * (long long)WS_F;
+      const bool valid = f_base + ft < L;
+      float* yrow = y + (f_base + ft) * kout;
+      mbar_wait_hint(d2_full, (uint32_t)(i & 1));
+      tc_fence_after_sync();
+      ws_final_epilogue<ACT>(lane_base + col_dlast, bias, np, d2_free, wlast, blast, kout, yrow, valid);
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tbase, (uint32_t)wl.tmem_cols);
+}
+
+}  // namespace molann

@@ -195,8 +195,8 @@ __device__ __forceinline__ bool dominant_quat_fast(const float (&S)[9], float (&
   }
   // Newton from the upper bound sqrt(3) ||S||_F (monotone from above: all roots are real)
   float lam = 1.7320508f;
-#pragma unroll
-  for (int it = 0; it < 6; ++it) {
+#pragma unroll 1
+  for (int it = 0; it < 6; ++it) {          // rolled: the fused kernels are instruction-fetch sensitive
     const float l2 = lam * lam;
     const float P = fmaf(fmaf(l2 + c2, lam, c1), lam, c0);
     const float dP = fmaf(fmaf(4.0f, l2, 2.0f * c2), lam, c1);
@@ -303,6 +303,31 @@ __device__ __forceinline__ void kabsch_moments(const float* __restrict__ xf, con
   for (int i = 0; i < 9; ++i) rg.H[i] = gsum<G>(h[i]);
 }
 
+// Jacobi route for the frames the fast path declined (kept out of line: it is rare, and the hot path of the
+// fused kernels should stay short and contiguous for the instruction cache).
+#ifndef MOLANN_HOST_EMULATION
+__device__ __noinline__
+#else
+inline
+#endif
+void kabsch_rotation_jacobi(const float* __restrict__ H, bool need, float* __restrict__ qout) {
+  const float Sxx = H[0], Sxy = H[1], Sxz = H[2];
+  const float Syx = H[3], Syy = H[4], Syz = H[5];
+  const float Szx = H[6], Szy = H[7], Szz = H[8];
+  float a[4][4];
+  a[0][0] = Sxx + Syy + Szz; a[0][1] = Syz - Szy; a[0][2] = Szx - Sxz; a[0][3] = Sxy - Syx;
+  a[1][1] = Sxx - Syy - Szz; a[1][2] = Sxy + Syx; a[1][3] = Szx + Sxz;
+  a[2][2] = -Sxx + Syy - Szz; a[2][3] = Syz + Szy;
+  a[3][3] = -Sxx - Syy + Szz;
+  a[1][0] = a[2][0] = a[2][1] = a[3][0] = a[3][1] = a[3][2] = 0.f;   // lower triangle unused
+  float qj[4];
+  dominant_eigvec4(a, qj, need);
+  if (need) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) qout[r] = qj[r];
+  }
+}
+
 // rg.R from rg.H.  Must be called by all 32 lanes of a warp (the Jacobi fallback votes).
 __device__ __forceinline__ void kabsch_rotation(Rigid& rg) {
   float nrm2 = 0.f;
@@ -314,23 +339,7 @@ __device__ __forceinline__ void kabsch_rotation(Rigid& rg) {
   for (int i = 0; i < 9; ++i) S[i] = rg.H[i] * inv;
   float q[4];
   const bool ok = dominant_quat_fast(S, q);
-  if (!__all_sync(0xffffffffu, ok)) {        // rare: near-degenerate frames take the Jacobi route
-    const float Sxx = rg.H[0], Sxy = rg.H[1], Sxz = rg.H[2];
-    const float Syx = rg.H[3], Syy = rg.H[4], Syz = rg.H[5];
-    const float Szx = rg.H[6], Szy = rg.H[7], Szz = rg.H[8];
-    float a[4][4];
-    a[0][0] = Sxx + Syy + Szz; a[0][1] = Syz - Szy; a[0][2] = Szx - Sxz; a[0][3] = Sxy - Syx;
-    a[1][1] = Sxx - Syy - Szz; a[1][2] = Sxy + Syx; a[1][3] = Szx + Sxz;
-    a[2][2] = -Sxx + Syy - Szz; a[2][3] = Syz + Szy;
-    a[3][3] = -Sxx - Syy + Szz;
-    a[1][0] = a[2][0] = a[2][1] = a[3][0] = a[3][1] = a[3][2] = 0.f;   // lower triangle unused
-    float qj[4];
-    dominant_eigvec4(a, qj, !ok);
-    if (!ok) {
-#pragma unroll
-      for (int r = 0; r < 4; ++r) q[r] = qj[r];
-    }
-  }
+  if (!__all_sync(0xffffffffu, ok)) kabsch_rotation_jacobi(rg.H, !ok, q);   // rare: near-degenerate frames
   quat_to_rot(q, rg.R);
 }
 

@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "fused_small.cuh"
 #include "fused_tc.cuh"
+#include "fused_ws.cuh"
 #include "general.cuh"
 
 using namespace molann;
@@ -319,6 +320,100 @@ int launch_tc_forward(const DevPlan& dp, const TcLayout& lay, const float* x, fl
   const int use_tma = ((reinterpret_cast<uintptr_t>(x) & 15u) == 0) && ((TC_F * 3 * dp.n_inp * 4) % 16 == 0);
   kern<<<(unsigned)grid, TC_F, lay.total_bytes, st>>>(dp, lay, x, y, L, use_tma);
   return post_launch();
+}
+
+// ---------------------------------------------------------------------------------------------
+// warp-specialised fused forward (fused_ws.cuh): the default for the small-system class
+// ---------------------------------------------------------------------------------------------
+struct WsChoice {
+  bool ok = false;
+  WsLayout wl;
+};
+
+// MOLANN_B200_WS = 0 falls back to the single-role tensor-core kernel (A/B testing).
+WsChoice choose_ws(const MolannPlan* p, const float* x, const DeviceInfo& dev) {
+  WsChoice ch;
+  std::memset(&ch.wl, 0, sizeof(ch.wl));
+  if (env_int("MOLANN_B200_WS", 1) == 0 || env_int("MOLANN_B200_TC", 1) == 0 || env_int("MOLANN_B200_PATH", -1) == 0)
+    return ch;
+  const int nl = p->n_layers;
+  if (nl < 2 || nl > 3) return ch;
+  for (int k = 0; k < nl; ++k)
+    if (p->dims[k] > TC_MAXW) return ch;
+  if (p->dims[nl] > 8) return ch;
+  if ((long long)p->n_entries * ENTRY_INTS * 4 > 32 * 1024) return ch;
+  if ((reinterpret_cast<uintptr_t>(x) & 15u) != 0) return ch;          // TMA bulk source alignment
+  const long long tile_bytes = (long long)WS_F * 3 * p->n_inp * 4;
+  WsLayout& wl = ch.wl;
+  TcLayout& lay = wl.base;
+  Carver c;
+  wl.mbar_off = c.take(8 * 32, 16);
+  wl.tptr_off = c.take(16, 16);
+  for (int k = 0; k < nl - 1; ++k) {
+    lay.kp[k] = round_up(p->dims[k], 16);
+    lay.np[k] = round_up(p->dims[k + 1], 16);
+    lay.bhi_off[k] = c.take(lay.kp[k] * lay.np[k] * 4, 1024);
+    lay.blo_off[k] = c.take(lay.kp[k] * lay.np[k] * 4, 1024);
+    lay.bias_off[k] = c.take(lay.np[k] * 4, 16);
+  }
+  lay.wlast_off = c.take(p->dims[nl] * TC_MAXW * 4, 16);
+  lay.blast_off = c.take(p->dims[nl] * 4, 16);
+  wl.aoff_off = c.take((p->n_align > 0 ? p->n_align : 1) * 4, 16);
+  wl.ref4_off = c.take((p->n_align > 0 ? p->n_align : 1) * 16, 16);
+  lay.ent_off = c.take(p->n_entries * ENTRY_INTS * 4, 16);
+  for (int b = 0; b < WS_XBUF; ++b) {
+    if (c.off + tile_bytes > dev.max_smem_optin) return ch;
+    wl.xs_off[b] = c.take((int)tile_bytes, 128);
+  }
+  wl.total_bytes = round_up(c.off, 128);
+  if (wl.total_bytes > dev.max_smem_optin) return ch;
+  // TMEM columns
+  const int kp0 = lay.kp[0], np0 = lay.np[0];
+  int col = 0;
+  wl.col_a1[0] = col; col += 2 * kp0;
+  wl.col_a1[1] = col; col += 2 * kp0;
+  if (nl == 3) {
+    const int kp1 = lay.kp[1], np1 = lay.np[1];
+    wl.n_a2buf = (col + 4 * kp1 + np0 + np1 <= 512) ? 2 : 1;
+    wl.col_a2[0] = col; col += 2 * kp1;
+    wl.col_a2[1] = wl.col_a2[0];
+    if (wl.n_a2buf == 2) { wl.col_a2[1] = col; col += 2 * kp1; }
+    wl.col_d1 = col; col += np0;
+    wl.col_d2 = col; col += np1;
+  } else {
+    wl.n_a2buf = 1;
+    wl.col_d1 = col;
+    wl.col_d2 = col; col += np0;
+  }
+  if (col > 512) return ch;
+  int cols = 32;
+  while (cols < col) cols <<= 1;
+  wl.tmem_cols = cols;
+  ch.ok = true;
+  return ch;
+}
+
+template <int ACT>
+int launch_ws_forward_act(const DevPlan& dp, const WsLayout& wl, const float* x, float* y, long long L,
+                          const DeviceInfo& dev, cudaStream_t st) {
+  auto kern = fused_ws_forward_kernel<ACT>;
+  int s = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, wl.total_bytes));
+  if (s) return s;
+  const long long ntiles = (L + WS_F - 1) / WS_F;
+  long long grid = dev.sm_count;                       // persistent: one CTA per SM
+  if (grid > ntiles) grid = ntiles;
+  kern<<<(unsigned)grid, WS_THREADS, wl.total_bytes, st>>>(dp, wl, x, y, L);
+  return post_launch();
+}
+
+int launch_ws_forward(const DevPlan& dp, const WsLayout& wl, const float* x, float* y, long long L,
+                      const DeviceInfo& dev, cudaStream_t st) {
+  switch (dp.act) {
+    case ACT_TANH: return launch_ws_forward_act<ACT_TANH>(dp, wl, x, y, L, dev, st);
+    case ACT_RELU: return launch_ws_forward_act<ACT_RELU>(dp, wl, x, y, L, dev, st);
+    case ACT_SIGMOID: return launch_ws_forward_act<ACT_SIGMOID>(dp, wl, x, y, L, dev, st);
+    default: return launch_ws_forward_act<ACT_IDENTITY>(dp, wl, x, y, L, dev, st);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -634,6 +729,8 @@ int molann_b200_forward(const MolannPlan* plan, const float* x, int64_t L, float
   const DeviceInfo dev = device_info();
   if (!dev.ok) return MOLANN_ERR_CUDA;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const WsChoice ws = choose_ws(plan, x, dev);
+  if (ws.ok) return launch_ws_forward(to_dev(plan), ws.wl, x, y, (long long)L, dev, st);
   const TcChoice tc = choose_tc(plan, false, dev);
   if (tc.ok) return launch_tc_forward(to_dev(plan), tc.lay, x, y, (long long)L, dev, st);
   const SmallChoice ch = choose_small(plan, false, dev);

@@ -46,15 +46,17 @@ def test_native_library_is_loaded_and_counts_launches():
     assert int(torch.ops.molann_b200.launch_count()) == _lib.launch_count()
 
 
-@pytest.mark.parametrize("path", ["auto", "ffma", "general"])
+@pytest.mark.parametrize("path", ["auto", "tc_single", "ffma", "general"])
 @pytest.mark.parametrize("name", ["C1", "C2", "C3s"])
 def test_cabi_against_reference_goldens(name, path, monkeypatch):
-    """auto = best fused kernel (tcgen05 3xTF32 MLP where eligible), ffma = fused CUDA-core kernel,
-    general = warp-per-frame geometry + layered GEMMs."""
+    """auto = best fused kernel (warp-specialised tcgen05 3xTF32 pipeline where eligible), tc_single = the
+    single-role tcgen05 kernel, ffma = fused CUDA-core kernel, general = warp-per-frame geometry + layered GEMMs."""
     if path == "general":
         monkeypatch.setenv("MOLANN_B200_PATH", "0")
     if path == "ffma":
         monkeypatch.setenv("MOLANN_B200_TC", "0")
+    if path == "tc_single":
+        monkeypatch.setenv("MOLANN_B200_WS", "0")
     spec = S.get_spec(name)
     g = golden("config_" + name)
     ws, bs = golden_weights(g, len(spec.layer_dims) - 1)
@@ -64,7 +66,7 @@ def test_cabi_against_reference_goldens(name, path, monkeypatch):
     assert plan.lib.molann_b200_path_for(ctypes.byref(plan.p), 0) == want
     if name == "C2":
         fam = plan.lib.molann_b200_kernel_family(ctypes.byref(plan.p), 0)
-        assert fam == {"auto": 2, "ffma": 1, "general": 0}[path]
+        assert fam == {"auto": 2, "tc_single": 2, "ffma": 1, "general": 0}[path]
     x = dev(g["x"])
     y = plan.forward(x)
     assert_parity(y.cpu(), g["y64"], g["y32"], TOL, "%s y" % name)
@@ -249,6 +251,52 @@ def test_other_activations(act):
         assert float((err > 2e-5).float().mean()) < 0.02
     else:
         assert_parity(gx.cpu(), gx64, None, 2e-5, act + " gx")
+
+
+@pytest.mark.parametrize("ws", ["1", "0"])
+@pytest.mark.parametrize("variant", ["one_hidden", "three_outputs", "narrow_wide", "mixed_program", "no_alignment",
+                                     "sigmoid_mixed"])
+def test_tensor_core_kernel_variants(variant, ws, monkeypatch):
+    """Shapes of the small-system class other than C2: one hidden layer, hidden width that is not a multiple
+    of 64, up to 8 outputs, feature programs that mix position entries with internal coordinates (unrolled
+    position path + interpreter), no alignment layer.  ws=1: warp-specialised pipeline, ws=0: single-role kernel."""
+    monkeypatch.setenv("MOLANN_B200_WS", ws)
+    spec = S.get_spec("C2")
+    if variant == "one_hidden":
+        spec.layer_dims = [30, 48, 2]
+    elif variant == "three_outputs":
+        spec.layer_dims = [30, 64, 64, 3]
+    elif variant == "narrow_wide":
+        spec.layer_dims = [30, 16, 64, 8]
+    elif variant in ("mixed_program", "sigmoid_mixed"):
+        spec.features = [("p", "position", [1, 4, 5, 6, 8]), ("d", "dihedral", [4, 6, 8, 14]), ("b", "bond", [8, 10]),
+                         ("a", "angle", [6, 8, 14]), ("p2", "position", [16, 18])]
+        spec.layer_dims = [spec.feature_dim(), 32, 40, 2]
+        if variant == "sigmoid_mixed":
+            spec.activation = "sigmoid"
+    elif variant == "no_alignment":
+        spec.align_ix = None
+        spec.trans_sigma, spec.rotate = 0.0, False
+    model, _ = S.build_model(spec, init_seed=3)
+    sd = model.state_dict()
+    nl = len(spec.layer_dims) - 1
+    ws_ = [sd["ann_layers.%dth_layer.weight" % (k + 1)] for k in range(nl)]
+    bs_ = [sd["ann_layers.%dth_layer.bias" % (k + 1)] for k in range(nl)]
+    L = 777
+    x = S.make_frames(spec, L, seed=12)
+    cot = torch.randn(L, spec.out_dim(), generator=torch.Generator().manual_seed(6))
+    y64, gx64 = oracle_value_and_grad(oracle_model(spec, ws_, bs_), x, cot)
+    y32, gx32 = oracle_value_and_grad(oracle_model(spec, ws_, bs_, torch.float32), x, cot, torch.float32)
+    model = model.cuda()
+    from molann_b200 import _lib
+    before = _lib.launch_count()
+    with torch.no_grad():
+        y = model(dev(x))
+    assert _lib.launch_count() == before + 1
+    assert_parity(y.cpu(), y64, y32, TOL, variant + " y")
+    y2, gx = model.value_and_grad(dev(x), dev(cot))
+    assert_parity(y2.cpu(), y64, y32, TOL, variant + " y (value_and_grad)")
+    assert_parity(gx.cpu(), gx64, gx32, 2e-5, variant + " gx")
 
 
 def test_mixed_feature_program_with_alignment():
