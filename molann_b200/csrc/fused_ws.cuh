@@ -6,14 +6,18 @@
 //
 //   producer (1 thread)   TMA bulk copy of the tile's contiguous byte range of x into a 3-deep smem ring
 //   G  (NG x 4 warps)     thread = frame: pivoted moments, rotation (polynomial path, Jacobi fallback),
-//                         feature program; features leave as TF32 hi/lo rows of the A operand in TMEM.
+//                         feature program; features leave as TF32 hi/lo rows of the layer-1 A operand, a
+//                         canonical K-major tile in SHARED memory (A1 in smem frees the TMEM columns that let
+//                         A2 and both accumulators be double-buffered).
 //                         The geometry is one long dependent chain per frame, so NG warpgroups work on NG
 //                         different tiles at once (it needs no TMEM until its last step)
 //   MMA-1 (1 thread)      tcgen05.mma 3xTF32  D1 = A1 * W1^T      (A from TMEM, W in smem for the whole kernel)
-//   E1 (4 warps)          thread = frame: D1 -> bias + activation -> TF32 hi/lo -> A2 operand in TMEM
+//   E1 (2 x 4 warps)      thread = frame: D1 -> bias + activation -> TF32 hi/lo -> A2 operand in TMEM
+//                         (two warpgroups alternate tiles; each owns one D1 and one A2 buffer)
 //   MMA-2 (1 thread)      D2 = A2 * W2^T
-//   E2 (4 warps)          thread = frame: D2 -> bias + activation -> last (narrow) layer as a register dot
+//   E2 (2 x 4 warps)      thread = frame: D2 -> bias + activation -> last (narrow) layer as a register dot
 //                         product -> y
+// 28 warps = 7 per scheduler; registers are re-balanced between the roles with setmaxnreg.
 //
 // Why: the single-role kernel (fused_tc.cuh) is bound by instruction issue and dependency latency with two
 // warps per scheduler (profiles/r1_c: issue 43 %, stall "wait" 35 %), and every tile serialises on the two
@@ -21,8 +25,10 @@
 // MUFU-heavy), the MMA latency is hidden behind the other roles' work on other tiles, and no CTA-wide barrier
 // is left in the steady state.
 //
-// TMEM map (512 columns): A1 double-buffered (2 x 2*kp0), A2 double-buffered when it fits (2 x 2*kp1),
-// D1, D2 single (their consumers copy them to registers at once and release them).
+// TMEM map (512 columns): A2 double-buffered (2 x 2*kp1) and the accumulators D1, D2 double-buffered, so that the
+// MMA of tile i+1 runs while the epilogue still reads tile i (with single accumulators the epilogue and its
+// MMA simply alternated, and with a single A2 the epilogue waited for the previous tile's MMA:
+// tests/cuda/ws_trace.cu).  A1 (double-buffered) lives in shared memory.
 // Weights and biases are pre-multiplied by the activation's exponent scale (tanh: 2 log2 e) while they are
 // staged, so the epilogue is  e = ex2(acc + b');  h = 1 - 2 / (1 + e).
 #pragma once
@@ -35,11 +41,36 @@ namespace molann {
 
 constexpr int WS_F = 128;
 constexpr int WS_NG = 2;                     // geometry warpgroups (tiles in flight in the G stage)
-constexpr int WS_XBUF = WS_NG + 2;           // coordinate-tile ring
-constexpr int WS_WARPS = 4 * WS_NG + 4 + 4 + 3;   // G + E1 + E2 + producer + 2 MMA issuers
+constexpr int WS_XBUF = WS_NG + 1;           // coordinate-tile ring
+constexpr int WS_NE = 2;                     // warpgroups per epilogue role (alternate tiles, one D buffer each)
+constexpr int WS_WARPS = 4 * WS_NG + 8 * WS_NE + 4;   // G + E1 + E2 + control warpgroup (producer, 2 MMA issuers, idle)
 constexpr int WS_THREADS = WS_WARPS * 32;
-constexpr int WS_W_E1 = 4 * WS_NG, WS_W_E2 = WS_W_E1 + 4, WS_W_PROD = WS_W_E2 + 4, WS_W_MMA1 = WS_W_PROD + 1,
-              WS_W_MMA2 = WS_W_PROD + 2;
+constexpr int WS_W_E1 = 4 * WS_NG, WS_W_E2 = WS_W_E1 + 4 * WS_NE, WS_W_PROD = WS_W_E2 + 4 * WS_NE,
+              WS_W_MMA1 = WS_W_PROD + 1, WS_W_MMA2 = WS_W_PROD + 2;
+// register budget per role (setmaxnreg; the kernel is compiled for 65536 / WS_THREADS = 72 per thread):
+// 8 G warps x 96 + 16 E warps x 64 + 4 control warps x 56 = 64512 <= 65536
+constexpr int WS_REGS_G = 96, WS_REGS_E = 64, WS_REGS_CTRL = 56;
+
+// Development aid (tests/cuda/ws_trace.cu): per-role, per-tile clock64() stamps of CTA 0.  Compiled out of the product.
+#ifdef MOLANN_WS_TRACE
+__device__ long long g_ws_trace[8 * 64 * 8];
+#define WS_EVT(role, i, ev)                                                                    \
+  do {                                                                                         \
+    if (blockIdx.x == 0 && (i) < 64 && (threadIdx.x & 31) == 0 && ((threadIdx.x >> 5) & 3) == 0) \
+      g_ws_trace[((role) * 64 + (i)) * 8 + (ev)] = clock64();                                  \
+  } while (0)
+#define WS_EVT_L0(role, i, ev)                                                        \
+  do {                                                                                \
+    if (blockIdx.x == 0 && (i) < 64) g_ws_trace[((role) * 64 + (i)) * 8 + (ev)] = clock64(); \
+  } while (0)
+#else
+#define WS_EVT(role, i, ev) \
+  do {                      \
+  } while (0)
+#define WS_EVT_L0(role, i, ev) \
+  do {                         \
+  } while (0)
+#endif
 
 struct WsLayout {
   TcLayout base;                             // weights / biases / plan constants (xs_off, mbar_off unused)
@@ -48,7 +79,9 @@ struct WsLayout {
   int ref4_off;                              // reference rows padded to float4
   int aoff_off;                              // 3 * align_idx (element offsets into a frame)
   int n_a2buf;                               // 1 or 2 A2 buffers
-  int col_a1[2], col_a2[2], col_d1, col_d2;  // TMEM column bases
+  int n_dbuf;                                // 1 or 2 buffers per accumulator
+  int a1s_off[2];                            // layer-1 A operand buffers in SHARED memory (hi block, lo block)
+  int col_a2[2], col_d1[2], col_d2[2];       // TMEM column bases
   int tmem_cols;
   int total_bytes;
 };
@@ -62,10 +95,12 @@ __device__ __forceinline__ void mbar_wait_hint(void* bar, uint32_t parity) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
-      "WS_WAIT_%=:\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
       "@p bra WS_DONE_%=;\n\t"
-      "bra WS_WAIT_%=;\n\t"
+      "WS_WAIT_%=:\n\t"
+      "nanosleep.u32 64;\n\t"             // retries were a third of all issued instructions (profiles/r1_f)
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@!p bra WS_WAIT_%=;\n\t"
       "WS_DONE_%=:\n\t"
       "}" ::"r"(smem_u32(bar)),
       "r"(parity), "r"(0x989680u)
@@ -142,21 +177,103 @@ __device__ __forceinline__ void tmem_st_cols(uint32_t taddr, const uint32_t (&v)
   if (N - c >= 1) tmem_st1(taddr + c, v[c]);
 }
 
+// one lane of a converged warp
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred;
+}
+
+// D[:, n0 : n0+nn] = A[128 x kp] * B[n0 : n0+nn, :]^T with the 3xTF32 expansion (no commit).
+// B is chunk-major [(k/4)][np][4]: rows n0.. of every K-chunk start n0 * 16 bytes in.
+// Called by the WHOLE (converged) issuer warp; only `leader` issues.  Keeping the descriptor arithmetic
+// warp-uniform lets ptxas hold it in uniform registers and emit back-to-back UTCHMMA; issuing from inside a
+// divergent `if (lane == 0)` cost ~14 instructions (~85 cycles) per MMA and made the issuer the pipeline's
+// bottleneck (tests/cuda/ws_trace.cu).
+__device__ __forceinline__ void ws_issue_mma_cols(uint32_t leader, uint32_t tbase, uint32_t colA_hi, uint32_t colA_lo,
+                                                  uint32_t colD, const unsigned char* bhi, const unsigned char* blo,
+                                                  int kp, int np, int n0, int nn) {
+  const uint32_t idesc = idesc_tf32(WS_F, nn);
+  const uint32_t bhi_a = smem_u32(bhi) + (uint32_t)n0 * 16u, blo_a = smem_u32(blo) + (uint32_t)n0 * 16u;
+  const uint32_t step = 2u * (uint32_t)np * 16u;        // two 16-byte K-chunks per MMA (K = 8)
+  const uint32_t lbo = (uint32_t)np * 16u;
+#pragma unroll 4
+  for (int j = 0; j < kp / 8; ++j) {
+    const uint64_t bh = smem_desc_kmajor(bhi_a + j * step, lbo, 128);
+    const uint64_t bl = smem_desc_kmajor(blo_a + j * step, lbo, 128);
+    if (leader) {
+      mma_tf32_ts(tbase + colD + n0, tbase + colA_lo + 8 * j, bh, idesc, j > 0);      // small terms first
+      mma_tf32_ts(tbase + colD + n0, tbase + colA_hi + 8 * j, bl, idesc, 1);
+      mma_tf32_ts(tbase + colD + n0, tbase + colA_hi + 8 * j, bh, idesc, 1);
+    }
+  }
+}
+
+// Whole-layer issue, descriptors formed on the fly (the control warps run on a 40-register budget).
+// TS form: A (hi / lo column blocks) in TMEM.  SS form: A in shared memory, canonical K-major tile
+// (hi block at `a_smem`, lo block kp * 512 bytes further; K-step = two 2048-byte K-chunks).
+__device__ __forceinline__ void ws_issue_layer_ts(uint32_t leader, uint32_t a_hi, uint32_t a_lo, uint32_t d,
+                                                  const unsigned char* bhi, const unsigned char* blo, int kp, int np) {
+  const uint32_t idesc = idesc_tf32(WS_F, np);
+  const uint32_t bhi_a = smem_u32(bhi), blo_a = smem_u32(blo);
+  const uint32_t step = 2u * (uint32_t)np * 16u, lbo = (uint32_t)np * 16u;
+#pragma unroll 2
+  for (int j = 0; j < kp / 8; ++j) {
+    const uint64_t bh = smem_desc_kmajor(bhi_a + j * step, lbo, 128);
+    const uint64_t bl = smem_desc_kmajor(blo_a + j * step, lbo, 128);
+    if (leader) {
+      mma_tf32_ts(d, a_lo + 8 * j, bh, idesc, j > 0);      // small terms first
+      mma_tf32_ts(d, a_hi + 8 * j, bl, idesc, 1);
+      mma_tf32_ts(d, a_hi + 8 * j, bh, idesc, 1);
+    }
+  }
+}
+__device__ __forceinline__ void ws_issue_layer_ss(uint32_t leader, const unsigned char* a_smem, uint32_t d,
+                                                  const unsigned char* bhi, const unsigned char* blo, int kp, int np) {
+  const uint32_t idesc = idesc_tf32(WS_F, np);
+  const uint32_t bhi_a = smem_u32(bhi), blo_a = smem_u32(blo);
+  const uint32_t ahi_a = smem_u32(a_smem), alo_a = ahi_a + (uint32_t)kp * (WS_F * 4u);
+  const uint32_t step = 2u * (uint32_t)np * 16u, lbo = (uint32_t)np * 16u;
+#pragma unroll 2
+  for (int j = 0; j < kp / 8; ++j) {
+    const uint64_t bh = smem_desc_kmajor(bhi_a + j * step, lbo, 128);
+    const uint64_t bl = smem_desc_kmajor(blo_a + j * step, lbo, 128);
+    const uint64_t ah = smem_desc_kmajor(ahi_a + j * (2u * WS_F * 16u), WS_F * 16u, 128);
+    const uint64_t al = smem_desc_kmajor(alo_a + j * (2u * WS_F * 16u), WS_F * 16u, 128);
+    if (leader) {
+      mma_tf32_ss(d, al, bh, idesc, j > 0);                // small terms first
+      mma_tf32_ss(d, ah, bl, idesc, 1);
+      mma_tf32_ss(d, ah, bh, idesc, 1);
+    }
+  }
+}
+
 // ---- E1: accumulator -> activation -> next layer's A operand, 16 columns at a time -------------------
-// (rolled loops: each role streams its own code, and the three roles of a scheduler must share the
-// instruction caches -- see profiles/r1_d: "no instruction" was the top stall with unrolled epilogues)
+// Rolled loops: each role streams its own code and the roles of a scheduler share the instruction caches
+// (profiles/r1_d: "no instruction" was the top stall with unrolled epilogues).
 template <int ACT>
 __device__ __forceinline__ void ws_hidden_epilogue(uint32_t lane_d, uint32_t lane_ahi, uint32_t lane_alo,
-                                                   const float* __restrict__ bias, int np, void* bar_d_free,
-                                                   void* bar_a_empty, uint32_t par_a_empty, void* bar_a_full) {
-  float z[16], zn[16];
-  tmem_ld16(lane_d, z);
+                                                   const float* __restrict__ bias, int np,
+                                                   unsigned long long* bar_d_full, unsigned long long* bar_d_free,
+                                                   uint32_t par_d, void* bar_a_empty, uint32_t par_a_empty,
+                                                   void* bar_a_full, int it) {
 #pragma unroll 1
   for (int c0 = 0; c0 < np; c0 += 16) {
+    if (c0 == 0) {
+      mbar_wait_hint(bar_d_full, par_d);
+      tc_fence_after_sync();
+      WS_EVT(2, it, 0);
+    }
+    float z[16];
+    tmem_ld16(lane_d + c0, z);
     tmem_wait_ld();
-    if (c0 + 16 < np) {
-      tmem_ld16(lane_d + c0 + 16, zn);         // next chunk in flight while this one is processed
-    } else {                                   // the accumulator is in registers: the next tile's MMA may start
+    if (c0 + 16 >= np) {                       // the accumulator has been read: its buffer may be overwritten
       tc_fence_before_sync();
       mbar_arrive(bar_d_free);
     }
@@ -173,34 +290,38 @@ __device__ __forceinline__ void ws_hidden_epilogue(uint32_t lane_d, uint32_t lan
     if (c0 == 0) {                             // the MMA that last read this A2 buffer is complete
       mbar_wait_hint(bar_a_empty, par_a_empty);
       tc_fence_after_sync();
+      WS_EVT(2, it, 1);
     }
     tmem_st16(lane_ahi + c0, hi);
     tmem_st16(lane_alo + c0, lo);
-#pragma unroll
-    for (int c = 0; c < 16; ++c) z[c] = zn[c];
   }
   tmem_wait_st();
   tc_fence_before_sync();
   mbar_arrive(bar_a_full);
+  WS_EVT(2, it, 3);
 }
 
 // ---- E2: accumulator -> activation -> last layer (register dot products) -> y ---------------------
 template <int ACT>
 __device__ __forceinline__ void ws_final_epilogue(uint32_t lane_d, const float* __restrict__ bias, int np,
-                                                  void* bar_d_free, const float* __restrict__ wl,
+                                                  unsigned long long* bar_d_full, unsigned long long* bar_d_free,
+                                                  uint32_t par_d, const float* __restrict__ wl,
                                                   const float* __restrict__ bl, int kout, float* __restrict__ yrow,
-                                                  bool valid) {
+                                                  bool valid, int it) {
   float acc[8];
 #pragma unroll
   for (int o = 0; o < 8; ++o) acc[o] = (o < kout) ? bl[o] : 0.f;
-  float z[16], zn[16];
-  tmem_ld16(lane_d, z);
 #pragma unroll 1
   for (int c0 = 0; c0 < np; c0 += 16) {
+    if (c0 == 0) {
+      mbar_wait_hint(bar_d_full, par_d);
+      tc_fence_after_sync();
+      WS_EVT(3, it, 0);
+    }
+    float z[16];
+    tmem_ld16(lane_d + c0, z);
     tmem_wait_ld();
-    if (c0 + 16 < np) {
-      tmem_ld16(lane_d + c0 + 16, zn);
-    } else {
+    if (c0 + 16 >= np) {
       tc_fence_before_sync();
       mbar_arrive(bar_d_free);
     }
@@ -243,9 +364,8 @@ __device__ __forceinline__ void ws_final_epilogue(uint32_t lane_d, const float* 
         }
       }
     }
-#pragma unroll
-    for (int c = 0; c < 16; ++c) z[c] = zn[c];
   }
+  WS_EVT(3, it, 2);
   if (valid) {
     if (kout == 2) {
       *reinterpret_cast<float2*>(yrow) = make_float2(acc[0], acc[1]);
@@ -257,12 +377,29 @@ __device__ __forceinline__ void ws_final_epilogue(uint32_t lane_d, const float* 
   }
 }
 
-// ---- G: NA position entries (3 NA feature columns) straight into the A operand ---------------------
-// z = (x - c) R = x R - t with t = c R.
+// ---- G: features -> layer-1 A operand in SHARED memory ---------------------------------------------
+// The operand is the canonical K-major, no-swizzle tile: element (row r, column k) of a block lives at
+// ((k / 4) * 128 + r) * 16 + (k % 4) * 4 bytes (8 x 16 B core matrices; LBO = 2048 B between K-chunks,
+// SBO = 128 B between 8-row groups).  Thread r owns row r, so a warp's 16-byte stores to one K-chunk cover
+// 512 contiguous bytes (conflict-free).  Keeping A1 out of TMEM is what lets A2 and both accumulators be
+// double-buffered in the 512 TMEM columns.
+struct SmemFeatOut {
+  unsigned char* hi_row;       // block base + r * 16
+  unsigned char* lo_row;
+  __device__ __forceinline__ void operator()(int col, float v) {
+    uint32_t hi, lo;
+    split_tf32_rn(v, hi, lo);
+    const int off = (col >> 2) * (WS_F * 16) + (col & 3) * 4;
+    *reinterpret_cast<uint32_t*>(hi_row + off) = hi;
+    *reinterpret_cast<uint32_t*>(lo_row + off) = lo;
+  }
+};
+
+// z = (x - c) R = x R - t with t = c R, for NA position entries starting at entry e0 (3 NA columns from 3 e0)
 template <int NA>
 __device__ __forceinline__ void ws_position_group(const float* __restrict__ xf, const int* __restrict__ ent, int e0,
                                                   const float (&R)[9], float t0, float t1, float t2,
-                                                  uint32_t lane_ahi, uint32_t lane_alo) {
+                                                  SmemFeatOut& out) {
   uint32_t hi[3 * NA], lo[3 * NA];
 #pragma unroll
   for (int i = 0; i < NA; ++i) {
@@ -275,24 +412,38 @@ __device__ __forceinline__ void ws_position_group(const float* __restrict__ xf, 
     split_tf32_rn(zy, hi[3 * i + 1], lo[3 * i + 1]);
     split_tf32_rn(zz, hi[3 * i + 2], lo[3 * i + 2]);
   }
-  tmem_st_cols<3 * NA>(lane_ahi + 3 * e0, hi);
-  tmem_st_cols<3 * NA>(lane_alo + 3 * e0, lo);
+  // 3 NA columns starting at a multiple of 12 (chunk aligned); groups of fewer than 4 atoms are zero-padded to
+  // whole 16-byte K-chunks (the zeros are operand padding, or are overwritten by the entries that follow) so that
+  // every store is a conflict-free STS.128
+  constexpr int NC = (3 * NA + 3) / 4;
+  const int off = (3 * e0 >> 2) * (WS_F * 16);
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    uint32_t h4[4], l4[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      h4[q] = (4 * c + q < 3 * NA) ? hi[4 * c + q] : 0u;
+      l4[q] = (4 * c + q < 3 * NA) ? lo[4 * c + q] : 0u;
+    }
+    *reinterpret_cast<uint4*>(out.hi_row + off + c * (WS_F * 16)) = make_uint4(h4[0], h4[1], h4[2], h4[3]);
+    *reinterpret_cast<uint4*>(out.lo_row + off + c * (WS_F * 16)) = make_uint4(l4[0], l4[1], l4[2], l4[3]);
+  }
 }
 
-__device__ __forceinline__ void ws_position_features(const float* __restrict__ xf, const int* __restrict__ ent,
-                                                     int n_lead, const Rigid& rg, uint32_t lane_ahi,
-                                                     uint32_t lane_alo) {
+// returns the first column not yet written
+__device__ __forceinline__ int ws_position_features(const float* __restrict__ xf, const int* __restrict__ ent,
+                                                    int n_lead, const Rigid& rg, SmemFeatOut& out) {
   const float t0 = fmaf(rg.c[0], rg.R[0], fmaf(rg.c[1], rg.R[3], rg.c[2] * rg.R[6]));
   const float t1 = fmaf(rg.c[0], rg.R[1], fmaf(rg.c[1], rg.R[4], rg.c[2] * rg.R[7]));
   const float t2 = fmaf(rg.c[0], rg.R[2], fmaf(rg.c[1], rg.R[5], rg.c[2] * rg.R[8]));
   int e0 = 0;
 #pragma unroll 1
-  for (; e0 + 4 <= n_lead; e0 += 4) ws_position_group<4>(xf, ent, e0, rg.R, t0, t1, t2, lane_ahi, lane_alo);
-  if (e0 + 2 <= n_lead) {
-    ws_position_group<2>(xf, ent, e0, rg.R, t0, t1, t2, lane_ahi, lane_alo);
-    e0 += 2;
-  }
-  if (e0 < n_lead) ws_position_group<1>(xf, ent, e0, rg.R, t0, t1, t2, lane_ahi, lane_alo);
+  for (; e0 + 4 <= n_lead; e0 += 4) ws_position_group<4>(xf, ent, e0, rg.R, t0, t1, t2, out);
+  const int rem = n_lead - e0;
+  if (rem == 3) ws_position_group<3>(xf, ent, e0, rg.R, t0, t1, t2, out);
+  else if (rem == 2) ws_position_group<2>(xf, ent, e0, rg.R, t0, t1, t2, out);
+  else if (rem == 1) ws_position_group<1>(xf, ent, e0, rg.R, t0, t1, t2, out);
+  return (3 * n_lead + 3) & ~3;
 }
 
 // =============================================================================================
@@ -313,10 +464,10 @@ fused_ws_forward_kernel(const __grid_constant__ DevPlan p, const __grid_constant
   unsigned long long* a1_empty = a1_full + 2;          // [2]
   unsigned long long* a2_full = a1_empty + 2;          // [2]
   unsigned long long* a2_empty = a2_full + 2;          // [2]
-  unsigned long long* d1_full = a2_empty + 2;
-  unsigned long long* d1_free = d1_full + 1;
-  unsigned long long* d2_full = d1_free + 1;
-  unsigned long long* d2_free = d2_full + 1;
+  unsigned long long* d1_full = a2_empty + 2;          // [2]: accumulator buffers
+  unsigned long long* d1_free = d1_full + 2;           // [2]
+  unsigned long long* d2_full = d1_free + 2;           // [2]
+  unsigned long long* d2_free = d2_full + 2;           // [2]
   uint32_t* tptr = reinterpret_cast<uint32_t*>(smem + wl.tptr_off);
 
   // ---- one-time staging (all threads) ----
@@ -353,25 +504,33 @@ fused_ws_forward_kernel(const __grid_constant__ DevPlan p, const __grid_constant
       mbar_init(&a2_full[b], WS_F);
       mbar_init(&a2_empty[b], 1);
     }
-    mbar_init(d1_full, 1);
-    mbar_init(d1_free, WS_F);
-    mbar_init(d2_full, 1);
-    mbar_init(d2_free, WS_F);
+    for (int h = 0; h < 2; ++h) {
+      mbar_init(&d1_full[h], 1);
+      mbar_init(&d1_free[h], WS_F);
+      mbar_init(&d2_full[h], 1);
+      mbar_init(&d2_free[h], WS_F);
+    }
     fence_mbar_init();
   }
-  if (warp == 0) tmem_alloc(tptr, (uint32_t)wl.tmem_cols);
+  if (warp == 0) tmem_alloc(tptr, 512u);      // all of it (one CTA per SM): the base address is then 0
   fence_proxy_async_smem();                   // weight operands are read by the tensor core (async proxy)
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  const uint32_t tbase = *tptr;
+  if (*tptr != 0u) __trap();                  // a full-TMEM allocation starts at column 0, lane 0
+  // a literal base keeps every tcgen05 address warp-uniform for ptxas (uniform registers, no R2UR per MMA)
+  constexpr uint32_t tbase = 0u;
   const uint32_t lane_base = tbase + ((uint32_t)((warp & 3) * 32) << 16);
 
   const long long ntiles = (L + WS_F - 1) / WS_F;
   const uint32_t tile_bytes = (uint32_t)WS_F * (uint32_t)n3 * 4u;
   const long long first = blockIdx.x, stride = gridDim.x;
   // with one hidden layer the only accumulator is "D2" and E1 / MMA-2 have nothing to do
-  const int col_dlast = wl.col_d2;
+  const int ndb = wl.n_dbuf;
+
+  if (warp >= WS_W_PROD) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WS_REGS_CTRL));
+  else if (warp >= WS_W_E1) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WS_REGS_E));
+  else asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(WS_REGS_G));
 
   if (warp == WS_W_PROD) {
     // ================= producer =================
@@ -382,7 +541,10 @@ fused_ws_forward_kernel(const __grid_constant__ DevPlan p, const __grid_constant
       float* dst = reinterpret_cast<float*>(smem + wl.xs_off[b]);
       const long long f_base = tile * (long long)WS_F;
       const bool full = f_base + WS_F <= L;
-      if (lane == 0) mbar_wait_hint(&x_empty[b], par ^ 1u);
+      if (lane == 0) {
+        mbar_wait_hint(&x_empty[b], par ^ 1u);
+        WS_EVT_L0(6, i, 0);
+      }
       __syncwarp();
       if (full) {
         if (lane == 0) {
@@ -398,34 +560,50 @@ fused_ws_forward_kernel(const __grid_constant__ DevPlan p, const __grid_constant
       }
     }
   } else if (warp == WS_W_MMA1) {
-    // ================= MMA issuer, layer 1 =================
-    if (lane == 0) {
+    // ================= MMA issuer, layer 1 (whole warp runs the loop, one elected lane issues) =================
+    {
+      const uint32_t leader = elect_one();
       int i = 0;
       for (long long tile = first; tile < ntiles; tile += stride, ++i) {
         const int ab = i & 1;
+        const int db = i % ndb;
+        const uint32_t dpar = (uint32_t)((i / ndb) & 1);
+        unsigned long long* dfree = (nh == 2 ? d1_free : d2_free) + db;
+        unsigned long long* dfull = (nh == 2 ? d1_full : d2_full) + db;
+        const uint32_t colD = (uint32_t)(nh == 2 ? wl.col_d1[db] : wl.col_d2[db]);
         mbar_wait_hint(&a1_full[ab], (uint32_t)((i >> 1) & 1));
-        mbar_wait_hint(nh == 2 ? d1_free : d2_free, (uint32_t)((i & 1) ^ 1));
+        if (leader) WS_EVT_L0(4, i, 0);
+        mbar_wait_hint(dfree, dpar ^ 1u);
         tc_fence_after_sync();
-        const uint32_t colA = (uint32_t)wl.col_a1[ab];
-        const uint32_t colD = (uint32_t)(nh == 2 ? wl.col_d1 : col_dlast);
-        issue_layer_mma(tbase, colA, colA + lay.kp[0], colD, smem + lay.bhi_off[0], smem + lay.blo_off[0], lay.kp[0],
-                        lay.np[0], &a1_empty[ab]);
-        mma_commit(nh == 2 ? d1_full : d2_full);
+        if (leader) WS_EVT_L0(4, i, 1);
+        ws_issue_layer_ss(leader, smem + wl.a1s_off[ab], tbase + colD, smem + lay.bhi_off[0], smem + lay.blo_off[0],
+                          lay.kp[0], lay.np[0]);
+        if (leader) mma_commit(dfull);
+        if (leader) WS_EVT_L0(4, i, 2);
+        if (leader) mma_commit(&a1_empty[ab]);
+        __syncwarp();
       }
     }
   } else if (warp == WS_W_MMA2) {
     // ================= MMA issuer, layer 2 =================
-    if (lane == 0 && nh == 2) {
+    if (nh == 2) {
+      const uint32_t leader = elect_one();
       int i = 0;
       for (long long tile = first; tile < ntiles; tile += stride, ++i) {
         const int ab = i % wl.n_a2buf;
-        mbar_wait_hint(&a2_full[ab], (uint32_t)((i / wl.n_a2buf) & 1));
-        mbar_wait_hint(d2_free, (uint32_t)((i & 1) ^ 1));
-        tc_fence_after_sync();
         const uint32_t colA = (uint32_t)wl.col_a2[ab];
-        issue_layer_mma(tbase, colA, colA + lay.kp[1], (uint32_t)wl.col_d2, smem + lay.bhi_off[1],
-                        smem + lay.blo_off[1], lay.kp[1], lay.np[1], &a2_empty[ab]);
-        mma_commit(d2_full);
+        mbar_wait_hint(&a2_full[ab], (uint32_t)((i / wl.n_a2buf) & 1));
+        if (leader) WS_EVT_L0(5, i, 0);
+        const int db = i % ndb;
+        mbar_wait_hint(&d2_free[db], (uint32_t)(((i / ndb) & 1) ^ 1));
+        tc_fence_after_sync();
+        if (leader) WS_EVT_L0(5, i, 1);
+        ws_issue_layer_ts(leader, tbase + colA, tbase + colA + lay.kp[1], tbase + (uint32_t)wl.col_d2[db],
+                          smem + lay.bhi_off[1], smem + lay.blo_off[1], lay.kp[1], lay.np[1]);
+        if (leader) mma_commit(&d2_full[db]);
+        if (leader) WS_EVT_L0(5, i, 2);
+        if (leader) mma_commit(&a2_empty[ab]);
+        __syncwarp();
       }
     }
   } else if (warp < WS_W_E1) {
@@ -448,6 +626,7 @@ fused_ws_forward_kernel(const __grid_constant__ DevPlan p, const __grid_constant
       const int f = ft < nf ? ft : nf - 1;
       const float* xf = reinterpret_cast<const float*>(smem + wl.xs_off[b]) + f * n3;
       mbar_wait_hint(&x_full[b], (uint32_t)((i / WS_XBUF) & 1));
+      WS_EVT(g, i, 0);
       Rigid rg;
       if (aligned) {
         // moments relative to the pivot atom (see kabsch_moments), reference rows as float4
@@ -480,45 +659,45 @@ fused_ws_forward_kernel(const __grid_constant__ DevPlan p, const __grid_constant
         rg.c[0] = rg.c[1] = rg.c[2] = 0.f;
       }
       const int ab = i & 1;
-      const uint32_t lane_ahi = lane_base + (uint32_t)wl.col_a1[ab];
-      const uint32_t lane_alo = lane_ahi + (uint32_t)kp0;
-      mbar_wait_hint(&a1_empty[ab], (uint32_t)(((i >> 1) & 1) ^ 1));
-      tc_fence_after_sync();
-      if (mixed) {
-        zero_a_operand(lane_base, (uint32_t)wl.col_a1[ab], (uint32_t)wl.col_a1[ab] + kp0, kp0);
-      } else {                                   // only the padding columns [d_feat, kp0) need zeros
-        for (int c = p.d_feat; c < kp0; ++c) {
-          tmem_st1(lane_ahi + c, 0u);
-          tmem_st1(lane_alo + c, 0u);
+      unsigned char* a1buf = smem + wl.a1s_off[ab];
+      SmemFeatOut out{a1buf + ft * 16, a1buf + kp0 * (WS_F * 4) + ft * 16};
+      WS_EVT(g, i, 1);
+      mbar_wait_hint(&a1_empty[ab], (uint32_t)(((i >> 1) & 1) ^ 1));   // the MMA that read this buffer is complete
+      WS_EVT(g, i, 2);
+      int cdone = 0;
+      if (n_lead > 0) cdone = ws_position_features(xf, ent, n_lead, rg, out);
+      {                                            // zero whole K-chunks up to kp0 (padding; the interpreter overwrites)
+        const int cz = mixed ? ((3 * n_lead + 3) & ~3) : cdone;
+        for (int c = cz; c < kp0; c += 4) {
+          *reinterpret_cast<uint4*>(out.hi_row + (c >> 2) * (WS_F * 16)) = make_uint4(0u, 0u, 0u, 0u);
+          *reinterpret_cast<uint4*>(out.lo_row + (c >> 2) * (WS_F * 16)) = make_uint4(0u, 0u, 0u, 0u);
         }
       }
-      if (n_lead > 0) ws_position_features(xf, ent, n_lead, rg, lane_ahi, lane_alo);
       if (mixed) {
-        TmemFeatOut out{lane_ahi, lane_alo};
         for (int e = n_lead; e < p.n_entries; ++e) {
           const Entry en = load_entry(ent + ENTRY_INTS * e);
           feature_forward(en, xf, aligned, rg, p.use_angle, out);
         }
       }
-      tmem_wait_st();
-      tc_fence_before_sync();
+      fence_proxy_async_smem();                  // generic-proxy stores -> visible to the tensor core's async proxy
       mbar_arrive(&a1_full[ab]);
       mbar_arrive(&x_empty[b]);
+      WS_EVT(g, i, 3);
     }
   } else if (warp < WS_W_E2) {
     // ================= E1 =================
     if (nh == 2) {
       const float* bias = reinterpret_cast<const float*>(smem + lay.bias_off[0]);
-      int i = 0;
-      for (long long tile = first; tile < ntiles; tile += stride, ++i) {
+      const int w = (warp - WS_W_E1) >> 2;       // this warpgroup takes local tiles w, w + NE, ...
+      int i = w;
+      for (long long tile = first + (long long)w * stride; tile < ntiles; tile += WS_NE * stride, i += WS_NE) {
         const int ab = i % wl.n_a2buf;
         const uint32_t par_e = (uint32_t)(((i / wl.n_a2buf) & 1) ^ 1);
         const uint32_t lane_ahi = lane_base + (uint32_t)wl.col_a2[ab];
         const uint32_t lane_alo = lane_ahi + (uint32_t)lay.kp[1];
-        mbar_wait_hint(d1_full, (uint32_t)(i & 1));
-        tc_fence_after_sync();
-        ws_hidden_epilogue<ACT>(lane_base + wl.col_d1, lane_ahi, lane_alo, bias, lay.np[0], d1_free, &a2_empty[ab],
-                                par_e, &a2_full[ab]);
+        const int db = i % ndb;
+        ws_hidden_epilogue<ACT>(lane_base + wl.col_d1[db], lane_ahi, lane_alo, bias, lay.np[0], &d1_full[db],
+                                &d1_free[db], (uint32_t)((i / ndb) & 1), &a2_empty[ab], par_e, &a2_full[ab], i);
       }
     }
   } else if (warp < WS_W_PROD) {
@@ -529,19 +708,20 @@ fused_ws_forward_kernel(const __grid_constant__ DevPlan p, const __grid_constant
     const int kout = p.dims[nl];
     const int np = lay.np[nh - 1];
     const int ft = tid & (WS_F - 1);            // frame within the tile
-    int i = 0;
-    for (long long tile = first; tile < ntiles; tile += stride, ++i) {
+    const int w = (warp - WS_W_E2) >> 2;
+    int i = w;
+    for (long long tile = first + (long long)w * stride; tile < ntiles; tile += WS_NE * stride, i += WS_NE) {
       const long long f_base = tile * (long long)WS_F;
       const bool valid = f_base + ft < L;
       float* yrow = y + (f_base + ft) * kout;
-      mbar_wait_hint(d2_full, (uint32_t)(i & 1));
-      tc_fence_after_sync();
-      ws_final_epilogue<ACT>(lane_base + col_dlast, bias, np, d2_free, wlast, blast, kout, yrow, valid);
+      const int db = i % ndb;
+      ws_final_epilogue<ACT>(lane_base + wl.col_d2[db], bias, np, &d2_full[db], &d2_free[db], (uint32_t)((i / ndb) & 1),
+                             wlast, blast, kout, yrow, valid, i);
     }
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tbase, (uint32_t)wl.tmem_cols);
+  if (warp == 0) tmem_dealloc(tbase, 512u);
 }
 
 }  // namespace molann

@@ -303,6 +303,9 @@ __device__ __forceinline__ void kabsch_moments(const float* __restrict__ xf, con
   for (int i = 0; i < 9; ++i) rg.H[i] = gsum<G>(h[i]);
 }
 
+struct Quat4 {
+  float a, b, c, d;
+};
 // Jacobi route for the frames the fast path declined (kept out of line: it is rare, and the hot path of the
 // fused kernels should stay short and contiguous for the instruction cache).
 #ifndef MOLANN_HOST_EMULATION
@@ -310,10 +313,8 @@ __device__ __noinline__
 #else
 inline
 #endif
-void kabsch_rotation_jacobi(const float* __restrict__ H, bool need, float* __restrict__ qout) {
-  const float Sxx = H[0], Sxy = H[1], Sxz = H[2];
-  const float Syx = H[3], Syy = H[4], Syz = H[5];
-  const float Szx = H[6], Szy = H[7], Szz = H[8];
+Quat4 kabsch_rotation_jacobi(float Sxx, float Sxy, float Sxz, float Syx, float Syy, float Syz, float Szx, float Szy,
+                             float Szz, bool need) {
   float a[4][4];
   a[0][0] = Sxx + Syy + Szz; a[0][1] = Syz - Szy; a[0][2] = Szx - Sxz; a[0][3] = Sxy - Syx;
   a[1][1] = Sxx - Syy - Szz; a[1][2] = Sxy + Syx; a[1][3] = Szx + Sxz;
@@ -322,10 +323,9 @@ void kabsch_rotation_jacobi(const float* __restrict__ H, bool need, float* __res
   a[1][0] = a[2][0] = a[2][1] = a[3][0] = a[3][1] = a[3][2] = 0.f;   // lower triangle unused
   float qj[4];
   dominant_eigvec4(a, qj, need);
-  if (need) {
-#pragma unroll
-    for (int r = 0; r < 4; ++r) qout[r] = qj[r];
-  }
+  Quat4 r;
+  r.a = qj[0]; r.b = qj[1]; r.c = qj[2]; r.d = qj[3];
+  return r;
 }
 
 // rg.R from rg.H.  Must be called by all 32 lanes of a warp (the Jacobi fallback votes).
@@ -339,7 +339,11 @@ __device__ __forceinline__ void kabsch_rotation(Rigid& rg) {
   for (int i = 0; i < 9; ++i) S[i] = rg.H[i] * inv;
   float q[4];
   const bool ok = dominant_quat_fast(S, q);
-  if (!__all_sync(0xffffffffu, ok)) kabsch_rotation_jacobi(rg.H, !ok, q);   // rare: near-degenerate frames
+  if (!__all_sync(0xffffffffu, ok)) {          // rare: near-degenerate frames (arguments by value: no stack traffic)
+    const Quat4 qj = kabsch_rotation_jacobi(rg.H[0], rg.H[1], rg.H[2], rg.H[3], rg.H[4], rg.H[5], rg.H[6], rg.H[7],
+                                            rg.H[8], !ok);
+    if (!ok) { q[0] = qj.a; q[1] = qj.b; q[2] = qj.c; q[3] = qj.d; }
+  }
   quat_to_rot(q, rg.R);
 }
 

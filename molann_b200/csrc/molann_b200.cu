@@ -361,34 +361,40 @@ WsChoice choose_ws(const MolannPlan* p, const float* x, const DeviceInfo& dev) {
   wl.aoff_off = c.take((p->n_align > 0 ? p->n_align : 1) * 4, 16);
   wl.ref4_off = c.take((p->n_align > 0 ? p->n_align : 1) * 16, 16);
   lay.ent_off = c.take(p->n_entries * ENTRY_INTS * 4, 16);
+  for (int b = 0; b < 2; ++b) wl.a1s_off[b] = c.take(2 * round_up(p->dims[0], 16) * WS_F * 4, 1024);
   for (int b = 0; b < WS_XBUF; ++b) {
     if (c.off + tile_bytes > dev.max_smem_optin) return ch;
     wl.xs_off[b] = c.take((int)tile_bytes, 128);
   }
   wl.total_bytes = round_up(c.off, 128);
   if (wl.total_bytes > dev.max_smem_optin) return ch;
-  // TMEM columns
-  const int kp0 = lay.kp[0], np0 = lay.np[0];
+  // TMEM columns (A1 lives in shared memory): in order of value, double-buffered accumulators, second A2 buffer
+  const int np0 = lay.np[0];
+  const int kp1 = nl == 3 ? lay.kp[1] : 0, np1 = nl == 3 ? lay.np[1] : 0;
+  const int fixed = 2 * kp1;
+  const int dcols = np0 + np1;
+  wl.n_dbuf = (fixed + 2 * dcols <= 512) ? 2 : 1;
+  wl.n_a2buf = (nl == 3 && fixed + wl.n_dbuf * dcols + 2 * kp1 <= 512) ? 2 : 1;
+  if (fixed + dcols > 512) return ch;
   int col = 0;
-  wl.col_a1[0] = col; col += 2 * kp0;
-  wl.col_a1[1] = col; col += 2 * kp0;
   if (nl == 3) {
-    const int kp1 = lay.kp[1], np1 = lay.np[1];
-    wl.n_a2buf = (col + 4 * kp1 + np0 + np1 <= 512) ? 2 : 1;
     wl.col_a2[0] = col; col += 2 * kp1;
     wl.col_a2[1] = wl.col_a2[0];
     if (wl.n_a2buf == 2) { wl.col_a2[1] = col; col += 2 * kp1; }
-    wl.col_d1 = col; col += np0;
-    wl.col_d2 = col; col += np1;
+    for (int b = 0; b < 2; ++b) {
+      if (b < wl.n_dbuf) { wl.col_d1[b] = col; col += np0; } else wl.col_d1[b] = wl.col_d1[0];
+    }
+    for (int b = 0; b < 2; ++b) {
+      if (b < wl.n_dbuf) { wl.col_d2[b] = col; col += np1; } else wl.col_d2[b] = wl.col_d2[0];
+    }
   } else {
-    wl.n_a2buf = 1;
-    wl.col_d1 = col;
-    wl.col_d2 = col; col += np0;
+    for (int b = 0; b < 2; ++b) {
+      if (b < wl.n_dbuf) { wl.col_d2[b] = col; col += np0; } else wl.col_d2[b] = wl.col_d2[0];
+      wl.col_d1[b] = wl.col_d2[b];
+    }
   }
   if (col > 512) return ch;
-  int cols = 32;
-  while (cols < col) cols <<= 1;
-  wl.tmem_cols = cols;
+  wl.tmem_cols = 512;
   ch.ok = true;
   return ch;
 }
