@@ -156,10 +156,29 @@ __device__ __forceinline__ void stage_tc_weights(const float* __restrict__ Wg, c
   for (int n = tid; n < np; n += nthreads) bias[n] = (n < N) ? bg[n] : 0.f;
 }
 
-// One thread: D[128 x np] = A[128 x kp] * B^T with the 3xTF32 expansion, then commit to `mbar`.
-__device__ __forceinline__ void issue_layer_mma(uint32_t tbase, uint32_t colA_hi, uint32_t colA_lo, uint32_t colD,
+// one lane of a converged warp
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred;
+}
+
+// D[128 x np] = A[128 x kp] * B^T with the 3xTF32 expansion, then commit to `mbar`.
+// Called by ONE WHOLE (converged) warp; the elected lane issues.  The TMEM base is passed through a shuffle so
+// that ptxas knows it is warp-uniform: the address arithmetic then stays in uniform registers and the
+// tcgen05.mma instructions issue back to back.  (Issued from a divergent `if (tid == 0)` every MMA cost ~14
+// instructions / ~85 cycles of ELECT / R2UR.BROADCAST glue: tests/cuda/ws_trace.cu.)
+__device__ __forceinline__ void issue_layer_mma(uint32_t tbase_any, uint32_t colA_hi, uint32_t colA_lo, uint32_t colD,
                                                 const unsigned char* bhi, const unsigned char* blo, int kp, int np,
                                                 void* mbar) {
+  const uint32_t tbase = __shfl_sync(0xffffffffu, tbase_any, 0);
+  const uint32_t leader = elect_one();
   const uint32_t idesc = idesc_tf32(TC_F, np);
   const uint32_t bhi_a = smem_u32(bhi), blo_a = smem_u32(blo);
   const uint32_t step = 2u * (uint32_t)np * 16u;        // two 16-byte K-chunks per MMA (K = 8)
@@ -167,11 +186,14 @@ __device__ __forceinline__ void issue_layer_mma(uint32_t tbase, uint32_t colA_hi
   for (int j = 0; j < kp / 8; ++j) {
     const uint64_t bh = smem_desc_kmajor(bhi_a + j * step, lbo, 128);
     const uint64_t bl = smem_desc_kmajor(blo_a + j * step, lbo, 128);
-    mma_tf32_ts(tbase + colD, tbase + colA_lo + 8 * j, bh, idesc, j > 0);      // small terms first
-    mma_tf32_ts(tbase + colD, tbase + colA_hi + 8 * j, bl, idesc, 1);
-    mma_tf32_ts(tbase + colD, tbase + colA_hi + 8 * j, bh, idesc, 1);
+    if (leader) {
+      mma_tf32_ts(tbase + colD, tbase + colA_lo + 8 * j, bh, idesc, j > 0);      // small terms first
+      mma_tf32_ts(tbase + colD, tbase + colA_hi + 8 * j, bl, idesc, 1);
+      mma_tf32_ts(tbase + colD, tbase + colA_hi + 8 * j, bh, idesc, 1);
+    }
   }
-  mma_commit(mbar);
+  if (leader) mma_commit(mbar);
+  __syncwarp();
 }
 
 template <int NT>
@@ -274,7 +296,7 @@ fused_tc_forward_kernel(const __grid_constant__ DevPlan p, const __grid_constant
     __syncthreads();
     const long long next = tile + gridDim.x;
     if (next < ntiles && is_tma_tile(next)) issue_x(next);        // xs is free: overlap with the MLP
-    if (tid == 0) {
+    if (warp == 0) {
       tc_fence_after_sync();
       issue_layer_mma(tbase, COL_AHI, COL_ALO, COL_D, smem + lay.bhi_off[0], smem + lay.blo_off[0], lay.kp[0],
                       lay.np[0], mbar_mma);
@@ -315,7 +337,7 @@ fused_tc_forward_kernel(const __grid_constant__ DevPlan p, const __grid_constant
         tmem_wait_st();
         tc_fence_before_sync();
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0) {
           tc_fence_after_sync();
           issue_layer_mma(tbase, COL_AHI, COL_ALO, COL_D, smem + lay.bhi_off[k + 1], smem + lay.blo_off[k + 1],
                           lay.kp[k + 1], lay.np[k + 1], mbar_mma);
@@ -446,7 +468,7 @@ fused_tc_value_grad_kernel(const __grid_constant__ DevPlan p, const __grid_const
     tmem_wait_st();
     tc_fence_before_sync();
     wg_sync(wg);
-    if (wt == 0) {
+    if ((wt >> 5) == 0) {                 // first warp of the warpgroup, converged
       tc_fence_after_sync();
       issue_layer_mma(tbase, COL_AHI, COL_ALO, COL_D, bh, bl, kp_, np_, mbar_mma);
     }

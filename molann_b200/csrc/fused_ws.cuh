@@ -177,19 +177,6 @@ __device__ __forceinline__ void tmem_st_cols(uint32_t taddr, const uint32_t (&v)
   if (N - c >= 1) tmem_st1(taddr + c, v[c]);
 }
 
-// one lane of a converged warp
-__device__ __forceinline__ uint32_t elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P;\n\t"
-      "elect.sync _|P, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, P;\n\t"
-      "}"
-      : "=r"(pred));
-  return pred;
-}
-
 // D[:, n0 : n0+nn] = A[128 x kp] * B[n0 : n0+nn, :]^T with the 3xTF32 expansion (no commit).
 // B is chunk-major [(k/4)][np][4]: rows n0.. of every K-chunk start n0 * 16 bytes in.
 // Called by the WHOLE (converged) issuer warp; only `leader` issues.  Keeping the descriptor arithmetic
@@ -523,8 +510,12 @@ fused_ws_forward_kernel(const __grid_constant__ DevPlan p, const __grid_constant
   const uint32_t lane_base = tbase + ((uint32_t)((warp & 3) * 32) << 16);
 
   const long long ntiles = (L + WS_F - 1) / WS_F;
-  const uint32_t tile_bytes = (uint32_t)WS_F * (uint32_t)n3 * 4u;
+  const uint32_t tile_bytes = (uint32_t)WS_F * (uint32_t)n3 * 4u;      // a multiple of 16
   const long long first = blockIdx.x, stride = gridDim.x;
+  // x only has to be 4-byte aligned: the bulk copy starts at the 16-byte boundary below the tile (every tile has
+  // the same misalignment because tile_bytes % 16 == 0) and the readers skip the first `xoff` bytes.  One kernel
+  // for every alignment keeps a frame's result independent of how the batch was sliced.
+  const uint32_t xoff = (uint32_t)(reinterpret_cast<uintptr_t>(x) & 15u);
   // with one hidden layer the only accumulator is "D2" and E1 / MMA-2 have nothing to do
   const int ndb = wl.n_dbuf;
 
@@ -540,7 +531,8 @@ fused_ws_forward_kernel(const __grid_constant__ DevPlan p, const __grid_constant
       const uint32_t par = (uint32_t)((i / WS_XBUF) & 1);
       float* dst = reinterpret_cast<float*>(smem + wl.xs_off[b]);
       const long long f_base = tile * (long long)WS_F;
-      const bool full = f_base + WS_F <= L;
+      // a misaligned copy reads up to 16 bytes past the tile: fine inside the batch, not on its last tile
+      const bool full = f_base + WS_F <= L && (xoff == 0u || f_base + WS_F < L);
       if (lane == 0) {
         mbar_wait_hint(&x_empty[b], par ^ 1u);
         WS_EVT_L0(6, i, 0);
@@ -548,13 +540,16 @@ fused_ws_forward_kernel(const __grid_constant__ DevPlan p, const __grid_constant
       __syncwarp();
       if (full) {
         if (lane == 0) {
-          mbar_expect_tx(&x_full[b], tile_bytes);
-          bulk_g2s(dst, x + f_base * n3, tile_bytes, &x_full[b]);
+          const uint32_t bytes = (tile_bytes + xoff + 15u) & ~15u;
+          mbar_expect_tx(&x_full[b], bytes);
+          bulk_g2s(dst, reinterpret_cast<const unsigned char*>(x + f_base * n3) - xoff, bytes, &x_full[b]);
         }
-      } else {                                 // ragged last tile: plain coalesced copy by the warp
-        const int nf = (int)(L - f_base);
+      } else {                                 // last tile (ragged, or misaligned): plain coalesced copy by the warp
+        const long long rest = L - f_base;
+        const int nf = (int)(rest < (long long)WS_F ? rest : (long long)WS_F);
         const float* src = x + f_base * n3;
-        for (int j = lane; j < nf * n3; j += 32) dst[j] = src[j];
+        float* dsto = dst + (xoff >> 2);
+        for (int j = lane; j < nf * n3; j += 32) dsto[j] = src[j];
         __syncwarp();
         if (lane == 0) mbar_arrive(&x_full[b]);
       }
@@ -624,7 +619,7 @@ fused_ws_forward_kernel(const __grid_constant__ DevPlan p, const __grid_constant
       const long long f_base = tile * (long long)WS_F;
       const int nf = (int)((L - f_base) < (long long)WS_F ? (L - f_base) : (long long)WS_F);
       const int f = ft < nf ? ft : nf - 1;
-      const float* xf = reinterpret_cast<const float*>(smem + wl.xs_off[b]) + f * n3;
+      const float* xf = reinterpret_cast<const float*>(smem + wl.xs_off[b] + xoff) + f * n3;
       mbar_wait_hint(&x_full[b], (uint32_t)((i / WS_XBUF) & 1));
       WS_EVT(g, i, 0);
       Rigid rg;

@@ -342,7 +342,8 @@ WsChoice choose_ws(const MolannPlan* p, const float* x, const DeviceInfo& dev) {
     if (p->dims[k] > TC_MAXW) return ch;
   if (p->dims[nl] > 8) return ch;
   if ((long long)p->n_entries * ENTRY_INTS * 4 > 32 * 1024) return ch;
-  if ((reinterpret_cast<uintptr_t>(x) & 15u) != 0) return ch;          // TMA bulk source alignment
+  (void)x;                                            // any 4-byte aligned x: the kernel copies from the 16-byte
+                                                      // boundary below each tile
   const long long tile_bytes = (long long)WS_F * 3 * p->n_inp * 4;
   WsLayout& wl = ch.wl;
   TcLayout& lay = wl.base;
@@ -363,8 +364,8 @@ WsChoice choose_ws(const MolannPlan* p, const float* x, const DeviceInfo& dev) {
   lay.ent_off = c.take(p->n_entries * ENTRY_INTS * 4, 16);
   for (int b = 0; b < 2; ++b) wl.a1s_off[b] = c.take(2 * round_up(p->dims[0], 16) * WS_F * 4, 1024);
   for (int b = 0; b < WS_XBUF; ++b) {
-    if (c.off + tile_bytes > dev.max_smem_optin) return ch;
-    wl.xs_off[b] = c.take((int)tile_bytes, 128);
+    if (c.off + tile_bytes + 16 > dev.max_smem_optin) return ch;
+    wl.xs_off[b] = c.take((int)tile_bytes + 16, 128);
   }
   wl.total_bytes = round_up(c.off, 128);
   if (wl.total_bytes > dev.max_smem_optin) return ch;

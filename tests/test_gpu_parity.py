@@ -209,6 +209,25 @@ def test_ragged_frame_counts(L):
         assert_parity(plan.backward(dev(x), dev(cot)).cpu(), gx64, None, 2e-5, "%s L=%d gx" % (name, L))
 
 
+def test_slices_of_a_batch_are_bitwise_identical():
+    """A frame's output must not depend on where its batch was cut (offset views are 8 / 4 bytes off the
+    16-byte grid, ragged tails, single frames): shards, chunks and re-batched frames reproduce bit for bit."""
+    spec = S.get_spec("C2")
+    model, _ = S.build_model(spec)
+    model = model.cuda()
+    x = S.make_frames(spec, 3000, device="cuda", seed=77)
+    flat = torch.zeros(3000 * 66 + 3, device="cuda")
+    with torch.no_grad():
+        y = model(x)
+        for a, n in ((1, 128), (3, 1000), (2, 129), (127, 1), (129, 257), (5, 2995)):
+            assert torch.equal(model(x[a:a + n]), y[a:a + n]), (a, n)
+        for shift in (1, 2, 3):                       # 4-, 8-, 12-byte misaligned copies of the whole batch
+            xv = flat[shift:shift + 3000 * 66].view(3000, 22, 3)
+            xv.copy_(x)
+            assert xv.data_ptr() % 16 == 4 * shift
+            assert torch.equal(model(xv), y), shift
+
+
 def test_empty_batch():
     spec = S.get_spec("C2")
     model, _ = S.build_model(spec)
@@ -226,6 +245,8 @@ def test_unaligned_input_pointer_takes_the_non_tma_path():
     xv = base[1:].view(g["x"].shape)                  # 4-byte aligned only
     xv.copy_(dev(g["x"]))
     assert xv.data_ptr() % 16 != 0
+    # the forward kernel bulk-copies from the 16-byte boundary below each tile: same kernel, same bits
+    assert torch.equal(plan.forward(xv), plan.forward(dev(g["x"])))
     assert_parity(plan.forward(xv).cpu(), g["y64"], g["y32"], TOL, "unaligned y")
     assert_parity(plan.backward(xv, dev(g["cot"])).cpu(), g["gx64"], g["gx32"], TOL, "unaligned gx")
 
