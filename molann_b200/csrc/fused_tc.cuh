@@ -62,7 +62,9 @@ __device__ __forceinline__ float act_forward_fast(float v, int act) {
 // activation value h and derivative d = act'(v) from ONE exponential.  The derivative is formed from
 // (e, r) directly -- d = 4 e r^2 for tanh -- so saturated units keep full relative accuracy, which
 // 1 - h*h (cancellation on the rounded h) cannot give.
-__device__ __forceinline__ void act_value_and_grad(float v, int act, float& h, float& d) {
+template <int ACT>
+__device__ __forceinline__ void act_value_and_grad_t(float v, float& h, float& d) {
+  constexpr int act = ACT;
   if (act == ACT_TANH) {
     float e, r;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(v * 2.8853900817779268f, 126.0f)));
@@ -394,7 +396,22 @@ __device__ __forceinline__ void wg_sync(int wg) {
   asm volatile("bar.sync %0, %1;" ::"r"(wg + 1), "r"(128) : "memory");
 }
 
-template <int TILES>
+#ifdef MOLANN_WS_TRACE
+__device__ long long g_vg_trace[64 * 16];
+#define VG_EVT(it, ev)                                                                       \
+  do {                                                                                       \
+    if (blockIdx.x == 0 && threadIdx.x == 0 && (it) < 64) g_vg_trace[(it) * 16 + (ev)] = clock64(); \
+  } while (0)
+#else
+#define VG_EVT(it, ev) \
+  do {                 \
+  } while (0)
+#endif
+
+// ACT is a template parameter: with the activation chosen at run time every element carried its own branch, the
+// 16 elements of a chunk could not overlap, and the two epilogues took 8k + 11k of a tile's 42k cycles
+// (tests/cuda/ws_trace.cu).
+template <int TILES, int ACT>
 __global__ void __launch_bounds__(TILES * TC_F)
 fused_tc_value_grad_kernel(const __grid_constant__ DevPlan p, const __grid_constant__ TcVgLayout vl,
                            const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ y,
@@ -477,7 +494,10 @@ fused_tc_value_grad_kernel(const __grid_constant__ DevPlan p, const __grid_const
   long long tile = (long long)blockIdx.x * TILES + wg;
   if (tile < ntiles && is_tma_tile(tile)) issue_x(tile);
 
+  int vg_it = -1;
   for (; tile < ntiles; tile += tstride) {
+    ++vg_it;
+    VG_EVT(vg_it, 0);
     const long long f_base = tile * (long long)TC_F;
     const int nf = (int)((L - f_base) < (long long)TC_F ? (L - f_base) : (long long)TC_F);
     if (is_tma_tile(tile)) {
@@ -488,6 +508,7 @@ fused_tc_value_grad_kernel(const __grid_constant__ DevPlan p, const __grid_const
       for (int i = wt; i < nf * n3; i += TC_F) xs[i] = src[i];
       wg_sync(wg);
     }
+    VG_EVT(vg_it, 1);
     // ---- geometry ----
     const int f = wt < nf ? wt : nf - 1;
     const float* xf = xs + f * n3;
@@ -495,6 +516,7 @@ fused_tc_value_grad_kernel(const __grid_constant__ DevPlan p, const __grid_const
     const bool aligned = p.n_align > 0;
     if (aligned) kabsch<1>(xf, aidx, ref, p.n_align, 0, rg);
     __syncwarp();
+    VG_EVT(vg_it, 2);
     zero_a_operand(lane_addr, COL_AHI, COL_ALO, lay.kp[0]);
     {
       TmemFeatOut out{lane_addr + COL_AHI, lane_addr + COL_ALO};
@@ -503,10 +525,12 @@ fused_tc_value_grad_kernel(const __grid_constant__ DevPlan p, const __grid_const
         feature_forward(en, xf, aligned, rg, p.use_angle, out);
       }
     }
+    VG_EVT(vg_it, 3);
     publish_a_and_issue(smem + lay.bhi_off[0], smem + lay.blo_off[0], lay.kp[0], lay.np[0]);
     // ---- first hidden layer (only when there are two): h_1 -> A operand, act'(z_1) parked in TMEM ----
     if (nh == 2) {
       wait_mma();
+      VG_EVT(vg_it, 4);
       const float* bias = reinterpret_cast<const float*>(smem + lay.bias_off[0]);
       const int np = lay.np[0];
 #pragma unroll
@@ -519,7 +543,7 @@ fused_tc_value_grad_kernel(const __grid_constant__ DevPlan p, const __grid_const
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             float hh, dd;
-            act_value_and_grad(z[i] + bias[c + i], p.act, hh, dd);
+            act_value_and_grad_t<ACT>(z[i] + bias[c + i], hh, dd);
             dv[i] = __float_as_uint(dd);
             split_tf32_rn(hh, hi[i], lo[i]);
           }
@@ -528,6 +552,7 @@ fused_tc_value_grad_kernel(const __grid_constant__ DevPlan p, const __grid_const
           tmem_st16(lane_addr + COL_ALO + c, lo);
         }
       }
+      VG_EVT(vg_it, 5);
       publish_a_and_issue(smem + lay.bhi_off[1], smem + lay.blo_off[1], lay.kp[1], lay.np[1]);
     }
     // ---- last hidden layer, streamed 16 columns at a time: y += h W_last^T, gz = (gy W_last) * act'(z) ----
@@ -545,20 +570,24 @@ fused_tc_value_grad_kernel(const __grid_constant__ DevPlan p, const __grid_const
       }
 #pragma unroll
       for (int j = 0; j < TC_MAXW; ++j) h[j] = 0.f;
-      for (int o = 0; o < kout; ++o) {
-        const float4* w4 = reinterpret_cast<const float4*>(wl + o * TC_MAXW);
-        const float g_o = (o == 0) ? go[0] : (o == 1) ? go[1] : (o == 2) ? go[2] : (o == 3) ? go[3]
-                        : (o == 4) ? go[4] : (o == 5) ? go[5] : (o == 6) ? go[6] : go[7];
 #pragma unroll
-        for (int j = 0; j < TC_MAXW / 4; ++j) {
-          const float4 w = w4[j];
-          h[4 * j] = fmaf(g_o, w.x, h[4 * j]);
-          h[4 * j + 1] = fmaf(g_o, w.y, h[4 * j + 1]);
-          h[4 * j + 2] = fmaf(g_o, w.z, h[4 * j + 2]);
-          h[4 * j + 3] = fmaf(g_o, w.w, h[4 * j + 3]);
+      for (int o = 0; o < 8; ++o) {
+        if (o < kout) {
+          const float4* w4 = reinterpret_cast<const float4*>(wl + o * TC_MAXW);
+          const float g_o = go[o];
+#pragma unroll
+          for (int j = 0; j < TC_MAXW / 4; ++j) {
+            const float4 w = w4[j];
+            h[4 * j] = fmaf(g_o, w.x, h[4 * j]);
+            h[4 * j + 1] = fmaf(g_o, w.y, h[4 * j + 1]);
+            h[4 * j + 2] = fmaf(g_o, w.z, h[4 * j + 2]);
+            h[4 * j + 3] = fmaf(g_o, w.w, h[4 * j + 3]);
+          }
         }
       }
+      VG_EVT(vg_it, 6);
       wait_mma();
+      VG_EVT(vg_it, 7);
 #pragma unroll
       for (int c = 0; c < TC_MAXW; c += 16) {
         if (c < np) {
@@ -569,27 +598,28 @@ fused_tc_value_grad_kernel(const __grid_constant__ DevPlan p, const __grid_const
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             float hh, dd;
-            act_value_and_grad(z[i] + bias[c + i], p.act, hh, dd);
+            act_value_and_grad_t<ACT>(z[i] + bias[c + i], hh, dd);
             z[i] = hh;
             split_tf32_rn(h[c + i] * dd, hi[i], lo[i]);          // gz of the last hidden layer
           }
           tmem_st16(lane_addr + COL_AHI + c, hi);
           tmem_st16(lane_addr + COL_ALO + c, lo);
           if (y != nullptr) {
-            for (int o = 0; o < kout; ++o) {
-              const float4* w4 = reinterpret_cast<const float4*>(wl + o * TC_MAXW + c);
-              float a = 0.f;
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const float4 w = w4[q];
-                a = fmaf(z[4 * q], w.x, a);
-                a = fmaf(z[4 * q + 1], w.y, a);
-                a = fmaf(z[4 * q + 2], w.z, a);
-                a = fmaf(z[4 * q + 3], w.w, a);
+            for (int o = 0; o < 8; ++o) {
+              if (o < kout) {
+                const float4* w4 = reinterpret_cast<const float4*>(wl + o * TC_MAXW + c);
+                float a = 0.f, b = 0.f;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const float4 w = w4[q];
+                  a = fmaf(z[4 * q], w.x, a);
+                  b = fmaf(z[4 * q + 1], w.y, b);
+                  a = fmaf(z[4 * q + 2], w.z, a);
+                  b = fmaf(z[4 * q + 3], w.w, b);
+                }
+                yacc[o] += a + b;
               }
-#pragma unroll
-              for (int oo = 0; oo < 8; ++oo)
-                if (oo == o) yacc[oo] += a;
             }
           }
         } else if (c < lay.np[nh - 1]) {
@@ -601,6 +631,7 @@ fused_tc_value_grad_kernel(const __grid_constant__ DevPlan p, const __grid_const
           if (o < kout) y[(f_base + wt) * kout + o] = yacc[o];
       }
     }
+    VG_EVT(vg_it, 8);
     // ---- backward through the tensor-core layers: gh_k = gz_{k+1} W_k  (operand W^T, K-major) ----
     for (int k = nh - 1; k >= 0; --k) {
       const int kb = lay.np[k];            // contraction width (outputs of forward layer k)
@@ -624,14 +655,17 @@ fused_tc_value_grad_kernel(const __grid_constant__ DevPlan p, const __grid_const
         }
       }
     }
+    VG_EVT(vg_it, 9);
     // the feature cotangent now sits in accumulator columns [COL_D, COL_D + d_feat) of this lane
     if (TILES > 1) {             // take the shared gradient tile
       if (wt == 0)
         while (atomicCAS(gx_lock, 0, 1) != 0) __nanosleep(32);
       wg_sync(wg);
     }
+    VG_EVT(vg_it, 10);
     for (int i = wt; i < TC_F * n3; i += TC_F) gxs[i] = 0.f;
     wg_sync(wg);
+    VG_EVT(vg_it, 11);
     {
       TmemGIn gin{lane_addr + COL_D};
       RowAcc acc{gxs + wt * n3};
@@ -651,6 +685,7 @@ fused_tc_value_grad_kernel(const __grid_constant__ DevPlan p, const __grid_const
           acc(aidx[k], align_atom_grad(dH, sg, inv_na, ref[3 * k], ref[3 * k + 1], ref[3 * k + 2]));
       }
     }
+    VG_EVT(vg_it, 12);
     fence_proxy_async_smem();
     wg_sync(wg);
     const long long next = tile + tstride;

@@ -487,10 +487,10 @@ TcVgChoice choose_tc_vg(const MolannPlan* p, const DeviceInfo& dev) {
   return ch;
 }
 
-template <int TILES>
+template <int TILES, int ACT>
 int launch_tc_vg(const DevPlan& dp, const TcVgLayout& vl, const float* x, const float* gy, float* y, float* gx,
                  long long L, const DeviceInfo& dev, cudaStream_t st) {
-  auto kern = fused_tc_value_grad_kernel<TILES>;
+  auto kern = fused_tc_value_grad_kernel<TILES, ACT>;
   int s = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, vl.total_bytes));
   if (s) return s;
   cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -510,8 +510,19 @@ int launch_tc_vg(const DevPlan& dp, const TcVgLayout& vl, const float* x, const 
 
 int run_tc_vg(const TcVgChoice& ch, const DevPlan& dp, const float* x, const float* gy, float* y, float* gx,
               long long L, const DeviceInfo& dev, cudaStream_t st) {
-  return ch.tiles == 2 ? launch_tc_vg<2>(dp, ch.vl, x, gy, y, gx, L, dev, st)
-                       : launch_tc_vg<1>(dp, ch.vl, x, gy, y, gx, L, dev, st);
+#define VG_CASE(A)                                                              \
+  case A:                                                                       \
+    return ch.tiles == 2 ? launch_tc_vg<2, A>(dp, ch.vl, x, gy, y, gx, L, dev, st) \
+                         : launch_tc_vg<1, A>(dp, ch.vl, x, gy, y, gx, L, dev, st);
+  switch (dp.act) {
+    VG_CASE(ACT_TANH)
+    VG_CASE(ACT_RELU)
+    VG_CASE(ACT_SIGMOID)
+    default:
+      return ch.tiles == 2 ? launch_tc_vg<2, ACT_IDENTITY>(dp, ch.vl, x, gy, y, gx, L, dev, st)
+                           : launch_tc_vg<1, ACT_IDENTITY>(dp, ch.vl, x, gy, y, gx, L, dev, st);
+  }
+#undef VG_CASE
 }
 
 #define SMALL_DISPATCH(ch, FN, ...)                                   \

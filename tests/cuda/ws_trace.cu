@@ -67,5 +67,25 @@ int main() {
     }
     printf("\n");
   }
+  // ---- value-and-gradient kernel (single-role, 2 tiles per CTA): phase stamps of warpgroup 0 of CTA 0 ----
+  {
+    float *dgy, *dgx;
+    cudaMalloc(&dgy, (size_t)L * 2 * 4); cudaMalloc(&dgx, x.size() * 4);
+    cudaMemset(dgy, 0, (size_t)L * 2 * 4);
+    for (int it = 0; it < 3; ++it) molann_b200_value_and_grad(&p, dx, dgy, L, dy, dgx, nullptr, 0, nullptr);
+    cudaEventRecord(e0);
+    int st = molann_b200_value_and_grad(&p, dx, dgy, L, dy, dgx, nullptr, 0, nullptr);
+    cudaEventRecord(e1); cudaDeviceSynchronize();
+    cudaEventElapsedTime(&ms, e0, e1);
+    printf("# value_and_grad status %d  %.3f ms  %.3f G frames/s\n", st, ms, L / ms * 1e-6);
+    static long long vt[64 * 16];
+    cudaMemcpyFromSymbol(vt, molann::g_vg_trace, sizeof(vt));
+    const char* ev[13] = {"start", "x", "kabsch", "feat", "mma1", "E1", "gyW", "mma2", "E2", "bwdMMA+E3", "lock", "zero", "featbwd"};
+    for (int i = 4; i < 10; ++i) {
+      printf("vg tile %2d:", i);
+      for (int e = 1; e < 13; ++e) printf(" %s +%lld", ev[e], vt[i * 16 + e] - vt[i * 16 + e - 1]);
+      printf("  | total %lld\n", vt[(i + 1) * 16] - vt[i * 16]);
+    }
+  }
   return 0;
 }
