@@ -389,11 +389,17 @@ def main():
     value_dx = world * frames * K / (ms_d * 1e-3)
 
     def roofline(bytes_per_frame, ms_total, launches, which):
+        # SURVEY 8(d) honesty guard: credit min(algorithmic bytes, DRAM bytes ncu measured for this launch shape),
+        # so a kernel is never credited for bytes it did not move (write-backs still in L2 at kernel end count
+        # against us).  The ncu figure only applies to the launch shape it was captured on.
         per_launch_s = ms_total * 1e-3 / K
-        achieved = bytes_per_frame * frames / per_launch_s / 1e9
+        alg = bytes_per_frame * frames
+        traffic = ncu_traffic(spec.name, which) if frames == spec.default_frames else None
+        credited = min(alg, traffic) if traffic else alg
+        achieved = credited / per_launch_s / 1e9
         return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(spec.name, which), "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": bytes_per_frame * frames, "kernel_launches_per_step": launches / K,
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
+                "credited_bytes_per_launch": credited, "kernel_launches_per_step": launches / K,
                 "frac_of_nominal_8TBs": achieved / 8000.0}
 
     line = {
