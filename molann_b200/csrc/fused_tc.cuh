@@ -123,6 +123,114 @@ struct TmemGIn {
   }
 };
 
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st2(uint32_t taddr, uint32_t a, uint32_t b) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(taddr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, float (&r)[12], int at) {
+  uint32_t u[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
+               : "r"(taddr)
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r[at + i] = __uint_as_float(u[i]);
+}
+__device__ __forceinline__ void tmem_ld4_nowait(uint32_t taddr, float (&r)[12], int at) {
+  uint32_t u[4];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3])
+               : "r"(taddr)
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 4; ++i) r[at + i] = __uint_as_float(u[i]);
+}
+// N consecutive columns (N = 12, 6 or 3: the columns of 4, 2 or 1 position entries) as the widest stores that tile it
+template <int N>
+__device__ __forceinline__ void tmem_st_cols(uint32_t taddr, const uint32_t (&v)[N]) {
+  int c = 0;
+  if (N - c >= 8) {
+    tmem_st8(taddr + c, *reinterpret_cast<const uint32_t(*)[8]>(&v[c]));
+    c += 8;
+  }
+  if (N - c >= 4) {
+    tmem_st4(taddr + c, v[c], v[c + 1], v[c + 2], v[c + 3]);
+    c += 4;
+  }
+  if (N - c >= 2) {
+    tmem_st2(taddr + c, v[c], v[c + 1]);
+    c += 2;
+  }
+  if (N - c >= 1) tmem_st1(taddr + c, v[c]);
+}
+
+// Leading position entries, forward: z = (x - c) R = x R - t (t = c R) for NA entries from entry e0, split into
+// TF32 hi/lo and stored as 3 NA columns of this thread's A-operand lane.
+template <int NA>
+__device__ __forceinline__ void tc_position_group(const float* __restrict__ xf, const int* __restrict__ ent, int e0,
+                                                  const float (&R)[9], float t0, float t1, float t2,
+                                                  uint32_t lane_ahi, uint32_t lane_alo) {
+  uint32_t hi[3 * NA], lo[3 * NA];
+#pragma unroll
+  for (int i = 0; i < NA; ++i) {
+    const float* p = xf + 3 * ent[ENTRY_INTS * (e0 + i) + 1];
+    const float px = p[0], py = p[1], pz = p[2];
+    split_tf32_rn(fmaf(px, R[0], fmaf(py, R[3], fmaf(pz, R[6], -t0))), hi[3 * i], lo[3 * i]);
+    split_tf32_rn(fmaf(px, R[1], fmaf(py, R[4], fmaf(pz, R[7], -t1))), hi[3 * i + 1], lo[3 * i + 1]);
+    split_tf32_rn(fmaf(px, R[2], fmaf(py, R[5], fmaf(pz, R[8], -t2))), hi[3 * i + 2], lo[3 * i + 2]);
+  }
+  tmem_st_cols<3 * NA>(lane_ahi + 3 * e0, hi);
+  tmem_st_cols<3 * NA>(lane_alo + 3 * e0, lo);
+}
+__device__ __forceinline__ void tc_position_features(const float* __restrict__ xf, const int* __restrict__ ent,
+                                                     int n_lead, const Rigid& rg, uint32_t lane_ahi, uint32_t lane_alo) {
+  const float t0 = fmaf(rg.c[0], rg.R[0], fmaf(rg.c[1], rg.R[3], rg.c[2] * rg.R[6]));
+  const float t1 = fmaf(rg.c[0], rg.R[1], fmaf(rg.c[1], rg.R[4], rg.c[2] * rg.R[7]));
+  const float t2 = fmaf(rg.c[0], rg.R[2], fmaf(rg.c[1], rg.R[5], rg.c[2] * rg.R[8]));
+  int e0 = 0;
+#pragma unroll 1
+  for (; e0 + 4 <= n_lead; e0 += 4) tc_position_group<4>(xf, ent, e0, rg.R, t0, t1, t2, lane_ahi, lane_alo);
+  if (e0 + 2 <= n_lead) {
+    tc_position_group<2>(xf, ent, e0, rg.R, t0, t1, t2, lane_ahi, lane_alo);
+    e0 += 2;
+  }
+  if (e0 < n_lead) tc_position_group<1>(xf, ent, e0, rg.R, t0, t1, t2, lane_ahi, lane_alo);
+}
+
+// Leading position entries, backward (aligned model): the cotangent columns of NA entries are read from this
+// thread's accumulator lane in one go; per entry  M += (x - c)^T g,  t = g R^T,  sg += t,  gx[a0] += t.
+template <int NA, class Acc>
+__device__ __forceinline__ void tc_position_group_bwd(const float* __restrict__ xf, const int* __restrict__ ent, int e0,
+                                                      const Rigid& rg, uint32_t lane_d, Acc& acc, float (&M)[9],
+                                                      float (&sg)[3]) {
+  float g[12];
+  if (NA == 4) {
+    tmem_ld8_nowait(lane_d + 3 * e0, g, 0);
+    tmem_ld4_nowait(lane_d + 3 * e0 + 8, g, 8);
+  } else {
+#pragma unroll
+    for (int c = 0; c < 3 * NA; ++c) g[c] = tmem_ld1_nowait(lane_d + 3 * e0 + c);
+  }
+  tmem_wait_ld();
+#pragma unroll
+  for (int i = 0; i < NA; ++i) {
+    const int a0 = ent[ENTRY_INTS * (e0 + i) + 1];
+    const float* p = xf + 3 * a0;
+    const float dx = p[0] - rg.c[0], dy = p[1] - rg.c[1], dz = p[2] - rg.c[2];
+    const float g0 = g[3 * i], g1 = g[3 * i + 1], g2 = g[3 * i + 2];
+    M[0] = fmaf(dx, g0, M[0]); M[1] = fmaf(dx, g1, M[1]); M[2] = fmaf(dx, g2, M[2]);
+    M[3] = fmaf(dy, g0, M[3]); M[4] = fmaf(dy, g1, M[4]); M[5] = fmaf(dy, g2, M[5]);
+    M[6] = fmaf(dz, g0, M[6]); M[7] = fmaf(dz, g1, M[7]); M[8] = fmaf(dz, g2, M[8]);
+    V3 t;
+    rot_transpose_apply(rg, g0, g1, g2, t.x, t.y, t.z);
+    sg[0] += t.x; sg[1] += t.y; sg[2] += t.z;
+    acc(a0, t);
+  }
+}
+
 // zero the first `kp` hi/lo columns of the A operand (padding columns must not hold stale activations)
 __device__ __forceinline__ void zero_a_operand(uint32_t lane_addr, uint32_t col_hi, uint32_t col_lo, int kp) {
   uint32_t z[16];
@@ -494,6 +602,9 @@ fused_tc_value_grad_kernel(const __grid_constant__ DevPlan p, const __grid_const
   long long tile = (long long)blockIdx.x * TILES + wg;
   if (tile < ntiles && is_tma_tile(tile)) issue_x(tile);
 
+  int n_lead = 0;                              // leading position entries take the unrolled paths
+  while (n_lead < p.n_entries && ent[ENTRY_INTS * n_lead] == FEAT_POSITION) ++n_lead;
+  const bool mixed = n_lead < p.n_entries;
   int vg_it = -1;
   for (; tile < ntiles; tile += tstride) {
     ++vg_it;
@@ -509,6 +620,9 @@ fused_tc_value_grad_kernel(const __grid_constant__ DevPlan p, const __grid_const
       wg_sync(wg);
     }
     VG_EVT(vg_it, 1);
+    float go[8];                               // this frame's output cotangent: issued now, consumed after two MMAs
+#pragma unroll
+    for (int o = 0; o < 8; ++o) go[o] = (o < kout && wt < nf) ? __ldg(gy + (f_base + wt) * kout + o) : 0.f;
     // ---- geometry ----
     const int f = wt < nf ? wt : nf - 1;
     const float* xf = xs + f * n3;
@@ -517,10 +631,23 @@ fused_tc_value_grad_kernel(const __grid_constant__ DevPlan p, const __grid_const
     if (aligned) kabsch<1>(xf, aidx, ref, p.n_align, 0, rg);
     __syncwarp();
     VG_EVT(vg_it, 2);
-    zero_a_operand(lane_addr, COL_AHI, COL_ALO, lay.kp[0]);
-    {
+    if (!aligned) {
+#pragma unroll
+      for (int q = 0; q < 9; ++q) rg.R[q] = (q == 0 || q == 4 || q == 8) ? 1.f : 0.f;
+      rg.c[0] = rg.c[1] = rg.c[2] = 0.f;
+    }
+    if (mixed) {
+      zero_a_operand(lane_addr, COL_AHI, COL_ALO, lay.kp[0]);
+    } else {                                   // only the padding columns [d_feat, kp) need zeros
+      for (int c = p.d_feat; c < lay.kp[0]; ++c) {
+        tmem_st1(lane_addr + COL_AHI + c, 0u);
+        tmem_st1(lane_addr + COL_ALO + c, 0u);
+      }
+    }
+    if (n_lead > 0) tc_position_features(xf, ent, n_lead, rg, lane_addr + COL_AHI, lane_addr + COL_ALO);
+    if (mixed) {
       TmemFeatOut out{lane_addr + COL_AHI, lane_addr + COL_ALO};
-      for (int e = 0; e < p.n_entries; ++e) {
+      for (int e = n_lead; e < p.n_entries; ++e) {
         const Entry en = load_entry(ent + ENTRY_INTS * e);
         feature_forward(en, xf, aligned, rg, p.use_angle, out);
       }
@@ -562,12 +689,9 @@ fused_tc_value_grad_kernel(const __grid_constant__ DevPlan p, const __grid_const
       const float* bl = reinterpret_cast<const float*>(smem + lay.blast_off);
       const float* bias = reinterpret_cast<const float*>(smem + lay.bias_off[nh - 1]);
       const int np = lay.np[nh - 1];
-      float go[8], yacc[8];
+      float yacc[8];
 #pragma unroll
-      for (int o = 0; o < 8; ++o) {
-        go[o] = (o < kout && wt < nf) ? __ldg(gy + (f_base + wt) * kout + o) : 0.f;
-        yacc[o] = (o < kout) ? bl[o] : 0.f;
-      }
+      for (int o = 0; o < 8; ++o) yacc[o] = (o < kout) ? bl[o] : 0.f;
 #pragma unroll
       for (int j = 0; j < TC_MAXW; ++j) h[j] = 0.f;
 #pragma unroll
@@ -663,7 +787,10 @@ fused_tc_value_grad_kernel(const __grid_constant__ DevPlan p, const __grid_const
       wg_sync(wg);
     }
     VG_EVT(vg_it, 10);
-    for (int i = wt; i < TC_F * n3; i += TC_F) gxs[i] = 0.f;
+    {
+      float4* g4 = reinterpret_cast<float4*>(gxs);       // tile bytes are a multiple of 16
+      for (int i = wt; i < (TC_F * n3) / 4; i += TC_F) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     wg_sync(wg);
     VG_EVT(vg_it, 11);
     {
@@ -673,7 +800,20 @@ fused_tc_value_grad_kernel(const __grid_constant__ DevPlan p, const __grid_const
 #pragma unroll
       for (int i = 0; i < 9; ++i) M[i] = 0.f;
       sg[0] = sg[1] = sg[2] = 0.f;
-      for (int e = 0; e < p.n_entries; ++e) {
+      int e_first = 0;
+      if (aligned && n_lead > 0) {             // unrolled position entries
+        const uint32_t lane_d = lane_addr + COL_D;
+        int e0 = 0;
+#pragma unroll 1
+        for (; e0 + 4 <= n_lead; e0 += 4) tc_position_group_bwd<4>(xf, ent, e0, rg, lane_d, acc, M, sg);
+        if (e0 + 2 <= n_lead) {
+          tc_position_group_bwd<2>(xf, ent, e0, rg, lane_d, acc, M, sg);
+          e0 += 2;
+        }
+        if (e0 < n_lead) tc_position_group_bwd<1>(xf, ent, e0, rg, lane_d, acc, M, sg);
+        e_first = n_lead;
+      }
+      for (int e = e_first; e < p.n_entries; ++e) {
         const Entry en = load_entry(ent + ENTRY_INTS * e);
         feature_backward(en, xf, aligned, rg, p.use_angle, gin, acc, M, sg);
       }

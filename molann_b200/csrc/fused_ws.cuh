@@ -134,72 +134,28 @@ __device__ __forceinline__ float ws_act(float zs) {
 __device__ __forceinline__ void ws_stage_weights(const float* __restrict__ Wg, const float* __restrict__ bg, int K, int N,
                                                  int kp, int np, float scale, unsigned char* bhi, unsigned char* blo,
                                                  float* bias, int tid, int nthreads) {
-  for (int idx = tid; idx < np * kp; idx += nthreads) {
-    const int n = idx / kp, k = idx - n * kp;
-    const float w = (n < N && k < K) ? scale * Wg[(long long)n * K + k] : 0.f;
-    uint32_t hi, lo;
-    split_tf32_rn(w, hi, lo);
-    lo = (lo + 0x1000u) & 0xffffe000u;
+  // 4 elements per thread and step with the (L2-latency) loads issued together: this prologue is part of the
+  // fixed cost of a launch (tests/cuda/ws_trace.cu: ~17 us before, of a 138 us bench step)
+  for (int base = tid * 4; base < np * kp; base += nthreads * 4) {
+    float w[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int idx = base + q;                 // kp is a multiple of 16: the 4 elements share a row and a K-chunk
+      const int n = idx / kp, k = idx - n * kp;
+      w[q] = (n < N && k < K) ? __ldg(Wg + (long long)n * K + k) : 0.f;
+    }
+    const int n = base / kp, k = base - n * kp;
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      split_tf32_rn(scale * w[q], hi[q], lo[q]);
+      lo[q] = (lo[q] + 0x1000u) & 0xffffe000u;
+    }
     const uint32_t off = chunk_major_offset(n, k, np);
-    *reinterpret_cast<uint32_t*>(bhi + off) = hi;
-    *reinterpret_cast<uint32_t*>(blo + off) = lo;
+    *reinterpret_cast<uint4*>(bhi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(blo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
   }
   for (int n = tid; n < np; n += nthreads) bias[n] = (n < N) ? scale * bg[n] : 0.f;
-}
-
-__device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d)
-               : "memory");
-}
-__device__ __forceinline__ void tmem_st2(uint32_t taddr, uint32_t a, uint32_t b) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(taddr), "r"(a), "r"(b) : "memory");
-}
-// N consecutive columns (N = 3 * atoms of a group: 24, 12, 6 or 3) as the widest stores that tile it
-template <int N>
-__device__ __forceinline__ void tmem_st_cols(uint32_t taddr, const uint32_t (&v)[N]) {
-  int c = 0;
-  if (N - c >= 16) {
-    tmem_st16(taddr + c, *reinterpret_cast<const uint32_t(*)[16]>(&v[c]));
-    c += 16;
-  }
-  if (N - c >= 8) {
-    tmem_st8(taddr + c, *reinterpret_cast<const uint32_t(*)[8]>(&v[c]));
-    c += 8;
-  }
-  if (N - c >= 4) {
-    tmem_st4(taddr + c, v[c], v[c + 1], v[c + 2], v[c + 3]);
-    c += 4;
-  }
-  if (N - c >= 2) {
-    tmem_st2(taddr + c, v[c], v[c + 1]);
-    c += 2;
-  }
-  if (N - c >= 1) tmem_st1(taddr + c, v[c]);
-}
-
-// D[:, n0 : n0+nn] = A[128 x kp] * B[n0 : n0+nn, :]^T with the 3xTF32 expansion (no commit).
-// B is chunk-major [(k/4)][np][4]: rows n0.. of every K-chunk start n0 * 16 bytes in.
-// Called by the WHOLE (converged) issuer warp; only `leader` issues.  Keeping the descriptor arithmetic
-// warp-uniform lets ptxas hold it in uniform registers and emit back-to-back UTCHMMA; issuing from inside a
-// divergent `if (lane == 0)` cost ~14 instructions (~85 cycles) per MMA and made the issuer the pipeline's
-// bottleneck (tests/cuda/ws_trace.cu).
-__device__ __forceinline__ void ws_issue_mma_cols(uint32_t leader, uint32_t tbase, uint32_t colA_hi, uint32_t colA_lo,
-                                                  uint32_t colD, const unsigned char* bhi, const unsigned char* blo,
-                                                  int kp, int np, int n0, int nn) {
-  const uint32_t idesc = idesc_tf32(WS_F, nn);
-  const uint32_t bhi_a = smem_u32(bhi) + (uint32_t)n0 * 16u, blo_a = smem_u32(blo) + (uint32_t)n0 * 16u;
-  const uint32_t step = 2u * (uint32_t)np * 16u;        // two 16-byte K-chunks per MMA (K = 8)
-  const uint32_t lbo = (uint32_t)np * 16u;
-#pragma unroll 4
-  for (int j = 0; j < kp / 8; ++j) {
-    const uint64_t bh = smem_desc_kmajor(bhi_a + j * step, lbo, 128);
-    const uint64_t bl = smem_desc_kmajor(blo_a + j * step, lbo, 128);
-    if (leader) {
-      mma_tf32_ts(tbase + colD + n0, tbase + colA_lo + 8 * j, bh, idesc, j > 0);      // small terms first
-      mma_tf32_ts(tbase + colD + n0, tbase + colA_hi + 8 * j, bl, idesc, 1);
-      mma_tf32_ts(tbase + colD + n0, tbase + colA_hi + 8 * j, bh, idesc, 1);
-    }
-  }
 }
 
 // Whole-layer issue, descriptors formed on the fly (the control warps run on a 40-register budget).
@@ -455,22 +411,13 @@ fused_ws_forward_kernel(const __grid_constant__ DevPlan p, const __grid_constant
   unsigned long long* d1_free = d1_full + 2;           // [2]
   unsigned long long* d2_full = d1_free + 2;           // [2]
   unsigned long long* d2_free = d2_full + 2;           // [2]
+  unsigned long long* w_ready = d2_free + 2;           // weights / biases staged
   uint32_t* tptr = reinterpret_cast<uint32_t*>(smem + wl.tptr_off);
 
-  // ---- one-time staging (all threads) ----
+  // ---- one-time staging.  What the geometry needs (a few hundred bytes) is staged by everyone before the first
+  // barrier; the weights are staged by the 16 epilogue warps AFTER it, while the producer and the geometry warps
+  // already work on the first tiles, and are published through the `w_ready` mbarrier. ----
   {
-    const float scale = ws_scale_for_act(ACT);
-    for (int k = 0; k < nh; ++k)
-      ws_stage_weights(p.W[k], p.b[k], p.dims[k], p.dims[k + 1], lay.kp[k], lay.np[k], scale, smem + lay.bhi_off[k],
-                       smem + lay.blo_off[k], reinterpret_cast<float*>(smem + lay.bias_off[k]), tid, WS_THREADS);
-    const int K = p.dims[nl - 1], N = p.dims[nl];
-    float* wlast = reinterpret_cast<float*>(smem + lay.wlast_off);
-    float* blast = reinterpret_cast<float*>(smem + lay.blast_off);
-    for (int i = tid; i < N * TC_MAXW; i += WS_THREADS) {
-      const int o = i / TC_MAXW, j = i - o * TC_MAXW;
-      wlast[i] = (j < K) ? p.W[nl - 1][(long long)o * K + j] : 0.f;
-    }
-    for (int o = tid; o < N; o += WS_THREADS) blast[o] = p.b[nl - 1][o];
     int* aoff = reinterpret_cast<int*>(smem + wl.aoff_off);
     float4* ref4 = reinterpret_cast<float4*>(smem + wl.ref4_off);
     int* ent = reinterpret_cast<int*>(smem + lay.ent_off);
@@ -491,6 +438,7 @@ fused_ws_forward_kernel(const __grid_constant__ DevPlan p, const __grid_constant
       mbar_init(&a2_full[b], WS_F);
       mbar_init(&a2_empty[b], 1);
     }
+    mbar_init(w_ready, 8 * WS_NE * 32);
     for (int h = 0; h < 2; ++h) {
       mbar_init(&d1_full[h], 1);
       mbar_init(&d1_free[h], WS_F);
@@ -522,6 +470,25 @@ fused_ws_forward_kernel(const __grid_constant__ DevPlan p, const __grid_constant
   if (warp >= WS_W_PROD) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WS_REGS_CTRL));
   else if (warp >= WS_W_E1) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WS_REGS_E));
   else asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(WS_REGS_G));
+
+  if (warp >= WS_W_E1 && warp < WS_W_PROD) {            // epilogue warps: stage weights, biases, last layer
+    const int st = tid - WS_W_E1 * 32, snt = 8 * WS_NE * 32;
+    const float scale = ws_scale_for_act(ACT);
+    for (int k = 0; k < nh; ++k)
+      ws_stage_weights(p.W[k], p.b[k], p.dims[k], p.dims[k + 1], lay.kp[k], lay.np[k], scale, smem + lay.bhi_off[k],
+                       smem + lay.blo_off[k], reinterpret_cast<float*>(smem + lay.bias_off[k]), st, snt);
+    const int K = p.dims[nl - 1], N = p.dims[nl];
+    float* wlast = reinterpret_cast<float*>(smem + lay.wlast_off);
+    float* blast = reinterpret_cast<float*>(smem + lay.blast_off);
+    for (int i = st; i < N * TC_MAXW; i += snt) {
+      const int o = i / TC_MAXW, j = i - o * TC_MAXW;
+      wlast[i] = (j < K) ? p.W[nl - 1][(long long)o * K + j] : 0.f;
+    }
+    for (int o = st; o < N; o += snt) blast[o] = p.b[nl - 1][o];
+    fence_proxy_async_smem();                  // weight operands are read by the tensor core (async proxy)
+    mbar_arrive(w_ready);
+    mbar_wait_hint(w_ready, 0u);
+  }
 
   if (warp == WS_W_PROD) {
     // ================= producer =================
@@ -558,6 +525,7 @@ fused_ws_forward_kernel(const __grid_constant__ DevPlan p, const __grid_constant
     // ================= MMA issuer, layer 1 (whole warp runs the loop, one elected lane issues) =================
     {
       const uint32_t leader = elect_one();
+      mbar_wait_hint(w_ready, 0u);
       int i = 0;
       for (long long tile = first; tile < ntiles; tile += stride, ++i) {
         const int ab = i & 1;
@@ -583,6 +551,7 @@ fused_ws_forward_kernel(const __grid_constant__ DevPlan p, const __grid_constant
     // ================= MMA issuer, layer 2 =================
     if (nh == 2) {
       const uint32_t leader = elect_one();
+      mbar_wait_hint(w_ready, 0u);
       int i = 0;
       for (long long tile = first; tile < ntiles; tile += stride, ++i) {
         const int ab = i % wl.n_a2buf;

@@ -67,6 +67,27 @@ int main() {
     }
     printf("\n");
   }
+  // ---- fixed cost per launch: time vs tiles per SM ----
+  {
+    float *dgy2, *dgx2;
+    cudaMalloc(&dgy2, (size_t)L * 2 * 4); cudaMalloc(&dgx2, x.size() * 4);
+    cudaMemset(dgy2, 0, (size_t)L * 2 * 4);
+    for (int k : {1, 2, 4, 8, 16, 40}) {
+      const long long Lk = 148LL * 128 * k;
+      float best_f = 1e9f, best_v = 1e9f;
+      for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0);
+        molann_b200_forward(&p, dx, Lk, dy, nullptr, 0, nullptr);
+        cudaEventRecord(e1); cudaDeviceSynchronize();
+        cudaEventElapsedTime(&ms, e0, e1); if (ms < best_f) best_f = ms;
+        cudaEventRecord(e0);
+        molann_b200_value_and_grad(&p, dx, dgy2, Lk, dy, dgx2, nullptr, 0, nullptr);
+        cudaEventRecord(e1); cudaDeviceSynchronize();
+        cudaEventElapsedTime(&ms, e0, e1); if (ms < best_v) best_v = ms;
+      }
+      printf("# tiles/SM %2d: forward %.1f us   value_and_grad %.1f us\n", k, best_f * 1e3, best_v * 1e3);
+    }
+  }
   // ---- value-and-gradient kernel (single-role, 2 tiles per CTA): phase stamps of warpgroup 0 of CTA 0 ----
   {
     float *dgy, *dgx;
