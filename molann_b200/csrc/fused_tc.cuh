@@ -506,6 +506,12 @@ __device__ __forceinline__ void wg_sync(int wg) {
 
 #ifdef MOLANN_WS_TRACE
 __device__ long long g_vg_trace[64 * 16];
+__device__ long long g_vg_life[256 * 4];       // per CTA: start, end of warpgroup 0, end of warpgroup 1 (globaltimer ns)
+__device__ __forceinline__ long long vg_gtime() {
+  unsigned long long gt;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+  return (long long)gt;
+}
 #define VG_EVT(it, ev)                                                                       \
   do {                                                                                       \
     if (blockIdx.x == 0 && threadIdx.x == 0 && (it) < 64) g_vg_trace[(it) * 16 + (ev)] = clock64(); \
@@ -605,6 +611,9 @@ fused_tc_value_grad_kernel(const __grid_constant__ DevPlan p, const __grid_const
   int n_lead = 0;                              // leading position entries take the unrolled paths
   while (n_lead < p.n_entries && ent[ENTRY_INTS * n_lead] == FEAT_POSITION) ++n_lead;
   const bool mixed = n_lead < p.n_entries;
+#ifdef MOLANN_WS_TRACE
+  if (tid == 0 && blockIdx.x < 256) g_vg_life[blockIdx.x * 4 + 0] = vg_gtime();
+#endif
   int vg_it = -1;
   for (; tile < ntiles; tile += tstride) {
     ++vg_it;
@@ -852,6 +861,9 @@ fused_tc_value_grad_kernel(const __grid_constant__ DevPlan p, const __grid_const
     }
   }
   if (wt == 0) bulk_wait0();
+#ifdef MOLANN_WS_TRACE
+  if (wt == 0 && blockIdx.x < 256) g_vg_life[blockIdx.x * 4 + 1 + wg] = vg_gtime();
+#endif
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(*tptr, TILES * 256);

@@ -54,6 +54,7 @@ constexpr int WS_REGS_G = 96, WS_REGS_E = 64, WS_REGS_CTRL = 56;
 // Development aid (tests/cuda/ws_trace.cu): per-role, per-tile clock64() stamps of CTA 0.  Compiled out of the product.
 #ifdef MOLANN_WS_TRACE
 __device__ long long g_ws_trace[8 * 64 * 8];
+__device__ long long g_ws_life[256 * 2];       // per CTA: start / end (globaltimer ns)
 #define WS_EVT(role, i, ev)                                                                    \
   do {                                                                                         \
     if (blockIdx.x == 0 && (i) < 64 && (threadIdx.x & 31) == 0 && ((threadIdx.x >> 5) & 3) == 0) \
@@ -397,6 +398,19 @@ fused_ws_forward_kernel(const __grid_constant__ DevPlan p, const __grid_constant
   extern __shared__ __align__(1024) unsigned char smem[];
   const TcLayout& lay = wl.base;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#ifdef MOLANN_WS_TRACE
+  if (blockIdx.x == 0 && tid == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    g_ws_trace[7 * 64 * 8 + 0] = clock64();
+    g_ws_trace[7 * 64 * 8 + 1] = (long long)gt;
+  }
+  if (tid == 0 && blockIdx.x < 256) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    g_ws_life[blockIdx.x * 2] = (long long)gt;
+  }
+#endif
   const int n3 = 3 * p.n_inp;
   const int nl = p.n_layers;
   const int nh = nl - 1;                      // 1 or 2 tensor-core layers
@@ -685,6 +699,19 @@ fused_ws_forward_kernel(const __grid_constant__ DevPlan p, const __grid_constant
   }
   tc_fence_before_sync();
   __syncthreads();
+#ifdef MOLANN_WS_TRACE
+  if (blockIdx.x == 0 && tid == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    g_ws_trace[7 * 64 * 8 + 2] = clock64();
+    g_ws_trace[7 * 64 * 8 + 3] = (long long)gt;
+  }
+  if (tid == 0 && blockIdx.x < 256) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    g_ws_life[blockIdx.x * 2 + 1] = (long long)gt;
+  }
+#endif
   if (warp == 0) tmem_dealloc(tbase, 512u);
 }
 

@@ -14,6 +14,7 @@
 #include "fused_small.cuh"
 #include "fused_tc.cuh"
 #include "fused_ws.cuh"
+#include "gemm_tc.cuh"
 #include "general.cuh"
 
 using namespace molann;
@@ -549,9 +550,20 @@ int max_dim(const MolannPlan* p) {
 
 size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 
+// scratch for the packed (TF32 hi/lo, chunk-major) weights of ONE tensor-core GEMM; packed right before each use
+size_t gemm_pack_bytes(const MolannPlan* p) {
+  long long m = 0;
+  for (int k = 0; k < p->n_layers; ++k) {
+    const long long f = gt_pack_floats(p->dims[k + 1], p->dims[k]), b = gt_pack_floats(p->dims[k], p->dims[k + 1]);
+    m = f > m ? f : m;
+    m = b > m ? b : m;
+  }
+  return align256((size_t)m * 4);
+}
+
 size_t general_ws_bytes(const MolannPlan* p, long long L, bool backward) {
   const long long ch = chunk_frames(p, L);
-  size_t total = align256((size_t)ch * p->d_feat * 4);
+  size_t total = align256((size_t)ch * p->d_feat * 4) + gemm_pack_bytes(p);
   if (!backward) {
     total += 2 * align256((size_t)ch * max_dim(p) * 4);
   } else {
@@ -569,8 +581,40 @@ unsigned warp_grid(long long L, const DeviceInfo& dev) {
   return (unsigned)blocks;
 }
 
+// Tensor-core GEMM (gemm_tc.cuh) for layers wide enough to fill its 128 x N x 32 tiles; MOLANN_B200_GEMM_TC = 0
+// keeps the FFMA kernel (A/B testing).
+bool use_gemm_tc(long long M, int K, int N, const void* pack) {
+  if (pack == nullptr || env_int("MOLANN_B200_GEMM_TC", 1) == 0 || env_int("MOLANN_B200_TC", 1) == 0) return false;
+  return M >= 64 && K >= 32 && N >= 32;
+}
+
+template <int EPI>
+int launch_gemm_tc(const float* A, long long M, int K, const float* W, long long rs, long long cs, int N, float* C,
+                   const float* bias, const float* H, int act, int apply_act, float* pack, const DeviceInfo& dev,
+                   cudaStream_t st) {
+  const long long total = (long long)((N + GT_NMAX - 1) / GT_NMAX) * GT_NMAX * round_up(K, GT_KC);
+  unsigned pb = (unsigned)((total + 255) / 256);
+  if (pb > 4096u) pb = 4096u;
+  gemm_tc_pack_kernel<<<pb, 256, 0, st>>>(W, rs, cs, N, K, pack);
+  int s = post_launch();
+  if (s) return s;
+  auto kern = gemm_tc_kernel<EPI>;
+  s = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM_BYTES));
+  if (s) return s;
+  const long long items = ((M + GT_M - 1) / GT_M) * ((N + GT_NMAX - 1) / GT_NMAX);
+  long long grid = dev.sm_count;
+  if (grid > items) grid = items;
+  kern<<<(unsigned)grid, GT_THREADS, GT_SMEM_BYTES, st>>>(A, (long long)K, M, K, pack, N, C, (long long)N, bias, H, act,
+                                                          apply_act);
+  return post_launch();
+}
+
 int launch_linear_forward(const float* in, const float* W, const float* b, float* out, long long M, int K, int N,
-                          int act, int apply_act, cudaStream_t st) {
+                          int act, int apply_act, cudaStream_t st, float* pack = nullptr,
+                          const DeviceInfo* dev = nullptr) {
+  if (dev != nullptr && use_gemm_tc(M, K, N, pack))
+    return launch_gemm_tc<GT_EPI_BIAS_ACT>(in, M, K, W, (long long)K, 1, N, out, b, nullptr, act, apply_act, pack, *dev,
+                                           st);
   dim3 grid((N + 63) / 64, (unsigned)((M + 63) / 64), 1);
   gemm_kernel<EPI_BIAS_ACT><<<grid, 256, 0, st>>>(in, K, 1, W, 1, K, out, N, (int)M, N, K, K, b, nullptr, act,
                                                   apply_act);
@@ -579,7 +623,12 @@ int launch_linear_forward(const float* in, const float* W, const float* b, float
 
 // gprev[M, K] = (gz[M, N] W[N, K]) * act'(hprev[M, K])
 int launch_linear_backward_input(const float* gz, const float* W, const float* hprev, float* gprev, long long M,
-                                 int K, int N, int act, cudaStream_t st) {
+                                 int K, int N, int act, cudaStream_t st, float* pack = nullptr,
+                                 const DeviceInfo* dev = nullptr) {
+  // gprev[M x K] = gz[M x N] * W[N x K]: as C = A B^T with B[j][c] = W[c * K + j] (rows = inputs, contraction = outputs)
+  if (dev != nullptr && use_gemm_tc(M, N, K, pack))
+    return launch_gemm_tc<GT_EPI_DACT>(gz, M, N, W, 1, (long long)K, K, gprev, nullptr, hprev, act, hprev != nullptr, pack,
+                                       *dev, st);
   dim3 grid((K + 63) / 64, (unsigned)((M + 63) / 64), 1);
   gemm_kernel<EPI_DACT><<<grid, 256, 0, st>>>(gz, N, 1, W, K, 1, gprev, K, (int)M, K, N, N, nullptr, hprev, act,
                                               hprev != nullptr);
@@ -611,6 +660,8 @@ int general_forward(const MolannPlan* p, const float* x, long long L, float* y, 
   char* base = static_cast<char*>(ws);
   float* feat = reinterpret_cast<float*>(base);
   base += align256((size_t)ch * p->d_feat * 4);
+  float* pack = reinterpret_cast<float*>(base);
+  base += gemm_pack_bytes(p);
   float* pp[2];
   pp[0] = reinterpret_cast<float*>(base);
   base += align256((size_t)ch * max_dim(p) * 4);
@@ -626,7 +677,8 @@ int general_forward(const MolannPlan* p, const float* x, long long L, float* y, 
     for (int k = 0; k < p->n_layers; ++k) {
       const bool last = (k == p->n_layers - 1);
       float* out = last ? (y + c0 * kout) : pp[k & 1];
-      s = launch_linear_forward(in, p->W[k], p->b[k], out, Lc, p->dims[k], p->dims[k + 1], p->act_id, !last, st);
+      s = launch_linear_forward(in, p->W[k], p->b[k], out, Lc, p->dims[k], p->dims[k + 1], p->act_id, !last, st, pack,
+                                &dev);
       if (s) return s;
       in = out;
     }
@@ -644,6 +696,8 @@ int general_backward(const MolannPlan* p, const float* x, const float* gy, long 
   float* h[MOLANN_MAX_LAYERS];       // h[0] = features, h[k] = activation after layer k
   h[0] = reinterpret_cast<float*>(base);
   base += align256((size_t)ch * p->d_feat * 4);
+  float* pack = reinterpret_cast<float*>(base);
+  base += gemm_pack_bytes(p);
   for (int k = 1; k < nl; ++k) {
     h[k] = reinterpret_cast<float*>(base);
     base += align256((size_t)ch * p->dims[k] * 4);
@@ -660,7 +714,8 @@ int general_backward(const MolannPlan* p, const float* x, const float* gy, long 
     int s = post_launch();
     if (s) return s;
     for (int k = 0; k < nl - 1; ++k) {
-      s = launch_linear_forward(h[k], p->W[k], p->b[k], h[k + 1], Lc, p->dims[k], p->dims[k + 1], p->act_id, 1, st);
+      s = launch_linear_forward(h[k], p->W[k], p->b[k], h[k + 1], Lc, p->dims[k], p->dims[k + 1], p->act_id, 1, st,
+                                pack, &dev);
       if (s) return s;
     }
     const float* gz = gy + c0 * kout;
@@ -671,7 +726,7 @@ int general_backward(const MolannPlan* p, const float* x, const float* gy, long 
       }
       float* gprev = pp[k & 1];
       s = launch_linear_backward_input(gz, p->W[k], k > 0 ? h[k] : nullptr, gprev, Lc, p->dims[k], p->dims[k + 1],
-                                       p->act_id, st);
+                                       p->act_id, st, pack, &dev);
       if (s) return s;
       gz = gprev;
     }

@@ -54,6 +54,27 @@ int main() {
          ms * 1e-3 * 1.965e9 / (L / 128 / 148));
   static long long tr[8 * 64 * 8];
   cudaMemcpyFromSymbol(tr, molann::g_ws_trace, sizeof(tr));
+  {
+    const long long* k = &tr[7 * 64 * 8];
+    printf("# CTA 0 lifetime: %lld SM cycles in %lld ns  ->  SM clock %.0f MHz while the kernel runs\n", k[2] - k[0], k[3] - k[1],
+           1e3 * (double)(k[2] - k[0]) / (double)(k[3] - k[1]));
+  }
+  {
+    static long long life[256 * 2];
+    cudaMemcpyFromSymbol(life, molann::g_ws_life, sizeof(life));
+    long long smin = life[0];
+    for (int b = 0; b < 148; ++b) if (life[2 * b] < smin) smin = life[2 * b];
+    long long smax = 0, emax = 0, emin = 1LL << 60; double esum = 0;
+    for (int b = 0; b < 148; ++b) {
+      const long long s0 = life[2 * b] - smin, e = life[2 * b + 1] - smin;
+      if (s0 > smax) smax = s0; if (e > emax) emax = e; if (e < emin) emin = e; esum += e;
+    }
+    printf("# forward CTA lifetimes (ns from first CTA start): latest start %lld; end min %lld mean %.0f max %lld\n", smax, emin,
+           esum / 148, emax);
+    printf("# slowest / fastest CTAs:");
+    for (int b = 0; b < 148; ++b) { const long long e = life[2 * b + 1] - smin; if (e > emax - (emax - emin) / 8 || e < emin + (emax - emin) / 8) printf(" %d:%lld", b, e); }
+    printf("\n");
+  }
   long long t0 = tr[(0 * 64 + 0) * 8 + 0];
   const char* names[7] = {"G0", "G1", "E1", "E2", "MMA1", "MMA2", "PROD"};
   for (int i = 0; i < 40; ++i) {
@@ -99,6 +120,22 @@ int main() {
     cudaEventRecord(e1); cudaDeviceSynchronize();
     cudaEventElapsedTime(&ms, e0, e1);
     printf("# value_and_grad status %d  %.3f ms  %.3f G frames/s\n", st, ms, L / ms * 1e-6);
+    {
+      static long long life[256 * 4];
+      cudaMemcpyFromSymbol(life, molann::g_vg_life, sizeof(life));
+      long long t0 = life[0], tmax = 0, smin = life[0];
+      for (int b = 0; b < 148; ++b) { if (life[b * 4] < smin) smin = life[b * 4]; }
+      double sum0 = 0, sum1 = 0; long long mx0 = 0, mx1 = 0, mn0 = 1LL << 60, smax = 0;
+      for (int b = 0; b < 148; ++b) {
+        const long long s0 = life[b * 4] - smin, e0 = life[b * 4 + 1] - smin, e1 = life[b * 4 + 2] - smin;
+        if (s0 > smax) smax = s0;
+        sum0 += e0; sum1 += e1;
+        if (e0 > mx0) mx0 = e0; if (e1 > mx1) mx1 = e1; if (e0 < mn0) mn0 = e0;
+      }
+      printf("# vg CTA lifetimes (ns from first CTA start): latest start %lld; WG0 end mean %.0f max %lld min %lld; WG1 end mean %.0f max %lld\n",
+             smax, sum0 / 148, mx0, mn0, sum1 / 148, mx1);
+      (void)t0; (void)tmax;
+    }
     static long long vt[64 * 16];
     cudaMemcpyFromSymbol(vt, molann::g_vg_trace, sizeof(vt));
     const char* ev[13] = {"start", "x", "kabsch", "feat", "mma1", "E1", "gyW", "mma2", "E2", "bwdMMA+E3", "lock", "zero", "featbwd"};
