@@ -481,11 +481,13 @@ fused_ws_forward_kernel(const __grid_constant__ DevPlan p, const __grid_constant
   // with one hidden layer the only accumulator is "D2" and E1 / MMA-2 have nothing to do
   const int ndb = wl.n_dbuf;
 
+  // (each setmaxnreg sits at the top of the code it governs: ptxas only applies the budget to a region the
+  // instruction clearly dominates -- placed in one if-chain ahead of the role dispatch it was ignored and the
+  // roles were allocated for the 72-register launch bound)
   if (warp >= WS_W_PROD) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WS_REGS_CTRL));
-  else if (warp >= WS_W_E1) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WS_REGS_E));
-  else asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(WS_REGS_G));
 
   if (warp >= WS_W_E1 && warp < WS_W_PROD) {            // epilogue warps: stage weights, biases, last layer
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WS_REGS_E));
     const int st = tid - WS_W_E1 * 32, snt = 8 * WS_NE * 32;
     const float scale = ws_scale_for_act(ACT);
     for (int k = 0; k < nh; ++k)
@@ -586,6 +588,7 @@ fused_ws_forward_kernel(const __grid_constant__ DevPlan p, const __grid_constant
     }
   } else if (warp < WS_W_E1) {
     // ================= G: geometry + features; warpgroup g takes local tiles g, g + NG, ... =================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(WS_REGS_G));
     const int g = warp >> 2;
     const int ft = tid & (WS_F - 1);            // frame within the tile
     const int* aoff = reinterpret_cast<const int*>(smem + wl.aoff_off);
