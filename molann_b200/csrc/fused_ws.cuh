@@ -76,12 +76,15 @@ __device__ long long g_ws_life[256 * 2];       // per CTA: start / end (globalti
 struct WsLayout {
   TcLayout base;                             // weights / biases / plan constants (xs_off, mbar_off unused)
   int xs_off[WS_XBUF];
+  int n_xbuf;                                // coordinate-tile ring depth actually used (2 when smem is short)
   int mbar_off, tptr_off;
   int ref4_off;                              // reference rows padded to float4
   int aoff_off;                              // 3 * align_idx (element offsets into a frame)
   int n_a2buf;                               // 1 or 2 A2 buffers
   int n_dbuf;                                // 1 or 2 buffers per accumulator
   int a1s_off[2];                            // layer-1 A operand buffers in SHARED memory (hi block, lo block)
+  int ones_off;                              // constant A tile [128 x 8]: column 0 = 1 (bias through the MMA)
+  int bbh_off[2], bbl_off[2];                // per MMA layer: bias as a [np x 8] B operand (column 0), hi / lo
   int col_a2[2], col_d1[2], col_d2[2];       // TMEM column bases
   int tmem_cols;
   int total_bytes;
@@ -156,12 +159,27 @@ __device__ __forceinline__ void ws_stage_weights(const float* __restrict__ Wg, c
     *reinterpret_cast<uint4*>(bhi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     *reinterpret_cast<uint4*>(blo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
   }
-  for (int n = tid; n < np; n += nthreads) bias[n] = (n < N) ? scale * bg[n] : 0.f;
+  if (bias != nullptr)
+    for (int n = tid; n < np; n += nthreads) bias[n] = (n < N) ? scale * bg[n] : 0.f;
 }
 
 // Whole-layer issue, descriptors formed on the fly (the control warps run on a 40-register budget).
 // TS form: A (hi / lo column blocks) in TMEM.  SS form: A in shared memory, canonical K-major tile
 // (hi block at `a_smem`, lo block kp * 512 bytes further; K-step = two 2048-byte K-chunks).
+// The bias enters through the tensor core as well: D = ONES[128 x 8] * BIAS[np x 8]^T (hi, then lo) starts the
+// accumulation, which takes a shared-memory load and an add per activation out of both epilogues for two extra
+// MMAs per layer.
+__device__ __forceinline__ void ws_issue_bias(uint32_t leader, uint32_t d, const unsigned char* ones,
+                                              const unsigned char* bbh, const unsigned char* bbl, int np, uint32_t idesc) {
+  const uint64_t a1 = smem_desc_kmajor(smem_u32(ones), WS_F * 16u, 128);
+  const uint64_t bh = smem_desc_kmajor(smem_u32(bbh), (uint32_t)np * 16u, 128);
+  const uint64_t bl = smem_desc_kmajor(smem_u32(bbl), (uint32_t)np * 16u, 128);
+  if (leader) {
+    mma_tf32_ss(d, a1, bl, idesc, 0);
+    mma_tf32_ss(d, a1, bh, idesc, 1);
+  }
+}
+
 __device__ __forceinline__ void ws_issue_layer_ts(uint32_t leader, uint32_t a_hi, uint32_t a_lo, uint32_t d,
                                                   const unsigned char* bhi, const unsigned char* blo, int kp, int np) {
   const uint32_t idesc = idesc_tf32(WS_F, np);
@@ -172,7 +190,7 @@ __device__ __forceinline__ void ws_issue_layer_ts(uint32_t leader, uint32_t a_hi
     const uint64_t bh = smem_desc_kmajor(bhi_a + j * step, lbo, 128);
     const uint64_t bl = smem_desc_kmajor(blo_a + j * step, lbo, 128);
     if (leader) {
-      mma_tf32_ts(d, a_lo + 8 * j, bh, idesc, j > 0);      // small terms first
+      mma_tf32_ts(d, a_lo + 8 * j, bh, idesc, 1);          // small terms first (the bias MMAs opened the sum)
       mma_tf32_ts(d, a_hi + 8 * j, bl, idesc, 1);
       mma_tf32_ts(d, a_hi + 8 * j, bh, idesc, 1);
     }
@@ -191,7 +209,7 @@ __device__ __forceinline__ void ws_issue_layer_ss(uint32_t leader, const unsigne
     const uint64_t ah = smem_desc_kmajor(ahi_a + j * (2u * WS_F * 16u), WS_F * 16u, 128);
     const uint64_t al = smem_desc_kmajor(alo_a + j * (2u * WS_F * 16u), WS_F * 16u, 128);
     if (leader) {
-      mma_tf32_ss(d, al, bh, idesc, j > 0);                // small terms first
+      mma_tf32_ss(d, al, bh, idesc, 1);                    // small terms first (the bias MMAs opened the sum)
       mma_tf32_ss(d, ah, bl, idesc, 1);
       mma_tf32_ss(d, ah, bh, idesc, 1);
     }
@@ -221,16 +239,9 @@ __device__ __forceinline__ void ws_hidden_epilogue(uint32_t lane_d, uint32_t lan
       tc_fence_before_sync();
       mbar_arrive(bar_d_free);
     }
-    const float4* b4 = reinterpret_cast<const float4*>(bias + c0);
     uint32_t hi[16], lo[16];
 #pragma unroll
-    for (int c = 0; c < 16; c += 4) {
-      const float4 b = b4[c >> 2];
-      split_tf32_rn(ws_act<ACT>(z[c] + b.x), hi[c], lo[c]);
-      split_tf32_rn(ws_act<ACT>(z[c + 1] + b.y), hi[c + 1], lo[c + 1]);
-      split_tf32_rn(ws_act<ACT>(z[c + 2] + b.z), hi[c + 2], lo[c + 2]);
-      split_tf32_rn(ws_act<ACT>(z[c + 3] + b.w), hi[c + 3], lo[c + 3]);
-    }
+    for (int c = 0; c < 16; ++c) split_tf32_rn(ws_act<ACT>(z[c]), hi[c], lo[c]);     // bias is already in z
     if (c0 == 0) {                             // the MMA that last read this A2 buffer is complete
       mbar_wait_hint(bar_a_empty, par_a_empty);
       tc_fence_after_sync();
@@ -269,15 +280,8 @@ __device__ __forceinline__ void ws_final_epilogue(uint32_t lane_d, const float* 
       tc_fence_before_sync();
       mbar_arrive(bar_d_free);
     }
-    const float4* b4 = reinterpret_cast<const float4*>(bias + c0);
 #pragma unroll
-    for (int c = 0; c < 16; c += 4) {
-      const float4 b = b4[c >> 2];
-      z[c] = ws_act<ACT>(z[c] + b.x);
-      z[c + 1] = ws_act<ACT>(z[c + 1] + b.y);
-      z[c + 2] = ws_act<ACT>(z[c + 2] + b.z);
-      z[c + 3] = ws_act<ACT>(z[c + 3] + b.w);
-    }
+    for (int c = 0; c < 16; ++c) z[c] = ws_act<ACT>(z[c]);                            // bias is already in z
     if (kout == 2) {                            // the common case: two collective variables
       const float4* w0 = reinterpret_cast<const float4*>(wl + c0);
       const float4* w1 = reinterpret_cast<const float4*>(wl + TC_MAXW + c0);
@@ -492,7 +496,21 @@ fused_ws_forward_kernel(const __grid_constant__ DevPlan p, const __grid_constant
     const float scale = ws_scale_for_act(ACT);
     for (int k = 0; k < nh; ++k)
       ws_stage_weights(p.W[k], p.b[k], p.dims[k], p.dims[k + 1], lay.kp[k], lay.np[k], scale, smem + lay.bhi_off[k],
-                       smem + lay.blo_off[k], reinterpret_cast<float*>(smem + lay.bias_off[k]), st, snt);
+                       smem + lay.blo_off[k], nullptr, st, snt);
+    for (int i = st; i < 2 * WS_F; i += snt)         // ONES: chunk 0 of row r = (1, 0, 0, 0), chunk 1 = 0
+      reinterpret_cast<float4*>(smem + wl.ones_off)[i] = make_float4(i < WS_F ? 1.f : 0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < nh; ++k) {                   // bias of layer k as a [np x 8] K-major operand, column 0
+      const int np = lay.np[k], N = p.dims[k + 1];
+      for (int i = st; i < 2 * np; i += snt) {
+        uint32_t hi = 0u, lo = 0u;
+        if (i < N) {
+          split_tf32_rn(scale * p.b[k][i], hi, lo);
+          lo = (lo + 0x1000u) & 0xffffe000u;
+        }
+        reinterpret_cast<uint4*>(smem + wl.bbh_off[k])[i] = make_uint4(i < np ? hi : 0u, 0u, 0u, 0u);
+        reinterpret_cast<uint4*>(smem + wl.bbl_off[k])[i] = make_uint4(i < np ? lo : 0u, 0u, 0u, 0u);
+      }
+    }
     const int K = p.dims[nl - 1], N = p.dims[nl];
     float* wlast = reinterpret_cast<float*>(smem + lay.wlast_off);
     float* blast = reinterpret_cast<float*>(smem + lay.blast_off);
@@ -510,8 +528,8 @@ fused_ws_forward_kernel(const __grid_constant__ DevPlan p, const __grid_constant
     // ================= producer =================
     int i = 0;
     for (long long tile = first; tile < ntiles; tile += stride, ++i) {
-      const int b = i % WS_XBUF;
-      const uint32_t par = (uint32_t)((i / WS_XBUF) & 1);
+      const int b = i % wl.n_xbuf;
+      const uint32_t par = (uint32_t)((i / wl.n_xbuf) & 1);
       float* dst = reinterpret_cast<float*>(smem + wl.xs_off[b]);
       const long long f_base = tile * (long long)WS_F;
       // a misaligned copy reads up to 16 bytes past the tile: fine inside the batch, not on its last tile
@@ -555,6 +573,8 @@ fused_ws_forward_kernel(const __grid_constant__ DevPlan p, const __grid_constant
         mbar_wait_hint(dfree, dpar ^ 1u);
         tc_fence_after_sync();
         if (leader) WS_EVT_L0(4, i, 1);
+        ws_issue_bias(leader, tbase + colD, smem + wl.ones_off, smem + wl.bbh_off[0], smem + wl.bbl_off[0], lay.np[0],
+                      idesc_tf32(WS_F, lay.np[0]));
         ws_issue_layer_ss(leader, smem + wl.a1s_off[ab], tbase + colD, smem + lay.bhi_off[0], smem + lay.blo_off[0],
                           lay.kp[0], lay.np[0]);
         if (leader) mma_commit(dfull);
@@ -578,6 +598,8 @@ fused_ws_forward_kernel(const __grid_constant__ DevPlan p, const __grid_constant
         mbar_wait_hint(&d2_free[db], (uint32_t)(((i / ndb) & 1) ^ 1));
         tc_fence_after_sync();
         if (leader) WS_EVT_L0(5, i, 1);
+        ws_issue_bias(leader, tbase + (uint32_t)wl.col_d2[db], smem + wl.ones_off, smem + wl.bbh_off[1],
+                      smem + wl.bbl_off[1], lay.np[1], idesc_tf32(WS_F, lay.np[1]));
         ws_issue_layer_ts(leader, tbase + colA, tbase + colA + lay.kp[1], tbase + (uint32_t)wl.col_d2[db],
                           smem + lay.bhi_off[1], smem + lay.blo_off[1], lay.kp[1], lay.np[1]);
         if (leader) mma_commit(&d2_full[db]);
@@ -601,12 +623,12 @@ fused_ws_forward_kernel(const __grid_constant__ DevPlan p, const __grid_constant
     const bool mixed = n_lead < p.n_entries;
     int i = g;
     for (long long tile = first + (long long)g * stride; tile < ntiles; tile += WS_NG * stride, i += WS_NG) {
-      const int b = i % WS_XBUF;
+      const int b = i % wl.n_xbuf;
       const long long f_base = tile * (long long)WS_F;
       const int nf = (int)((L - f_base) < (long long)WS_F ? (L - f_base) : (long long)WS_F);
       const int f = ft < nf ? ft : nf - 1;
       const float* xf = reinterpret_cast<const float*>(smem + wl.xs_off[b] + xoff) + f * n3;
-      mbar_wait_hint(&x_full[b], (uint32_t)((i / WS_XBUF) & 1));
+      mbar_wait_hint(&x_full[b], (uint32_t)((i / wl.n_xbuf) & 1));
       WS_EVT(g, i, 0);
       Rigid rg;
       if (aligned) {

@@ -354,20 +354,28 @@ WsChoice choose_ws(const MolannPlan* p, const float* x, const DeviceInfo& dev) {
   for (int k = 0; k < nl - 1; ++k) {
     lay.kp[k] = round_up(p->dims[k], 16);
     lay.np[k] = round_up(p->dims[k + 1], 16);
-    lay.bhi_off[k] = c.take(lay.kp[k] * lay.np[k] * 4, 1024);
-    lay.blo_off[k] = c.take(lay.kp[k] * lay.np[k] * 4, 1024);
-    lay.bias_off[k] = c.take(lay.np[k] * 4, 16);
+    lay.bhi_off[k] = c.take(lay.kp[k] * lay.np[k] * 4, 128);
+    lay.blo_off[k] = c.take(lay.kp[k] * lay.np[k] * 4, 128);
+    lay.bias_off[k] = 0;                                  // the bias goes through the MMA (bbh / bbl below)
+    wl.bbh_off[k] = c.take(2 * lay.np[k] * 16, 128);
+    wl.bbl_off[k] = c.take(2 * lay.np[k] * 16, 128);
   }
   lay.wlast_off = c.take(p->dims[nl] * TC_MAXW * 4, 16);
   lay.blast_off = c.take(p->dims[nl] * 4, 16);
   wl.aoff_off = c.take((p->n_align > 0 ? p->n_align : 1) * 4, 16);
   wl.ref4_off = c.take((p->n_align > 0 ? p->n_align : 1) * 16, 16);
   lay.ent_off = c.take(p->n_entries * ENTRY_INTS * 4, 16);
-  for (int b = 0; b < 2; ++b) wl.a1s_off[b] = c.take(2 * round_up(p->dims[0], 16) * WS_F * 4, 1024);
+  wl.ones_off = c.take(2 * WS_F * 16, 128);
+  for (int b = 0; b < 2; ++b) wl.a1s_off[b] = c.take(2 * round_up(p->dims[0], 16) * WS_F * 4, 128);
+  // coordinate-tile ring: 3 deep when it fits, else 2 (the kernel then exposes a little more load latency, which is
+  // still far better than falling back to the single-role kernel)
+  wl.n_xbuf = 0;
   for (int b = 0; b < WS_XBUF; ++b) {
-    if (c.off + tile_bytes + 16 > dev.max_smem_optin) return ch;
+    if (c.off + tile_bytes + 16 + 128 > dev.max_smem_optin) break;
     wl.xs_off[b] = c.take((int)tile_bytes + 16, 128);
+    wl.n_xbuf = b + 1;
   }
+  if (wl.n_xbuf < 2) return ch;
   wl.total_bytes = round_up(c.off, 128);
   if (wl.total_bytes > dev.max_smem_optin) return ch;
   // TMEM columns (A1 lives in shared memory): in order of value, double-buffered accumulators, second A2 buffer
