@@ -96,6 +96,151 @@ preprocess_backward_warp_kernel(const __grid_constant__ DevPlan p, const float* 
 }
 
 // out[L, n, 3] = (x - c) R   (stand-alone AlignmentLayer.forward)
+// ---------------------------------------------------------------------------------------------------------
+// Staged variants for big systems (C3 / C5).  The gather kernels above read ~300 scattered atoms of a 24 KB frame
+// twice (moments, then features); DRAM fetches 64 bytes per touched 12-byte atom, so they move 2x the frame
+// (ncu: 1.57 GB for a 786 MB batch, 88 % of the HBM peak -- memory bound on bytes nobody needs).  Here every warp
+// owns a frame-sized shared-memory buffer, pulls the frame in ONCE with one contiguous bulk copy
+// (cp.async.bulk from the 16-byte boundary below the frame) and gathers from shared memory.  The backward also
+// builds the dense gradient row in shared memory (shared-memory atomics) and writes it out with one bulk store,
+// instead of zero-filling the row in HBM and merging scattered REDs in L2.
+// ---------------------------------------------------------------------------------------------------------
+struct SmemRedAcc {
+  float* row;
+  __device__ __forceinline__ void operator()(int atom, V3 v) {
+    float* q = row + 3 * atom;
+    atomicAdd(q, v.x); atomicAdd(q + 1, v.y); atomicAdd(q + 2, v.z);
+  }
+};
+
+struct SmemGIn {
+  const float* row;
+  __device__ __forceinline__ float operator()(int col) const { return row[col]; }
+  __device__ __forceinline__ void load2(int col, float& a, float& b) const { a = row[col]; b = row[col + 1]; }
+  __device__ __forceinline__ void load3(int col, float& a, float& b, float& c) const {
+    a = row[col]; b = row[col + 1]; c = row[col + 2];
+  }
+};
+
+// one warp: row f (n3 floats) of x -> its buffer; returns the row's address inside the buffer
+__device__ __forceinline__ const float* stage_frame(const float* __restrict__ x, long long f, long long L, int n3,
+                                                    unsigned char* buf, unsigned long long* bar, uint32_t& phase,
+                                                    int lane) {
+  const float* src = x + f * n3;
+  const uint32_t off = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15u);
+  float* dst = reinterpret_cast<float*>(buf + off);
+  if (off == 0u || f + 1 < L) {               // the copy may run up to 15 bytes past the frame: not on the last one
+    if (lane == 0) {
+      const uint32_t bytes = ((uint32_t)n3 * 4u + off + 15u) & ~15u;
+      mbar_expect_tx(bar, bytes);
+      bulk_g2s(buf, reinterpret_cast<const unsigned char*>(src) - off, bytes, bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1u;
+  } else {
+    for (int i = lane; i < n3; i += 32) dst[i] = src[i];
+    __syncwarp();
+  }
+  return dst;
+}
+
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+preprocess_forward_staged_kernel(const __grid_constant__ DevPlan p, const float* __restrict__ x,
+                                 float* __restrict__ feat, long long L, int buf_bytes) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem);
+  unsigned char* buf = smem + 128 + (size_t)w * buf_bytes;
+  if (lane == 0) {
+    mbar_init(&bars[w], 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  const int n3 = 3 * p.n_inp;
+  const bool aligned = p.n_align > 0;
+  uint32_t phase = 0;
+  for (long long f = (long long)blockIdx.x * nw + w; f < L; f += (long long)gridDim.x * nw) {
+    const float* xf = stage_frame(x, f, L, n3, buf, &bars[w], phase, lane);
+    Rigid rg;
+    if (aligned) kabsch<32>(xf, p.align_idx, p.ref_x, p.n_align, lane, rg);
+    GlobalOut out{feat + f * p.d_feat};
+    for (int e = lane; e < p.n_entries; e += 32) {
+      const Entry en = load_entry(p.entries + ENTRY_INTS * e);
+      feature_forward(en, xf, aligned, rg, p.use_angle, out);
+    }
+    __syncwarp();                              // every lane is done with the buffer before the next copy lands
+  }
+}
+
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+preprocess_backward_staged_kernel(const __grid_constant__ DevPlan p, const float* __restrict__ x,
+                                  const float* __restrict__ gfeat, float* __restrict__ gx, long long L, int buf_bytes,
+                                  int fbuf_bytes) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem);
+  unsigned char* buf = smem + 128 + (size_t)w * (2 * buf_bytes + fbuf_bytes);   // [x frame | gradient row | cotangent]
+  unsigned char* gbuf = buf + buf_bytes;
+  unsigned char* fbuf = gbuf + buf_bytes;
+  if (lane == 0) {
+    mbar_init(&bars[2 * w], 1);
+    mbar_init(&bars[2 * w + 1], 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  const int n3 = 3 * p.n_inp;
+  const bool aligned = p.n_align > 0;
+  uint32_t phase = 0, phase_f = 0;
+  for (long long f = (long long)blockIdx.x * nw + w; f < L; f += (long long)gridDim.x * nw) {
+    const float* xf = stage_frame(x, f, L, n3, buf, &bars[2 * w], phase, lane);
+    const float* gf = stage_frame(gfeat, f, L, p.d_feat, fbuf, &bars[2 * w + 1], phase_f, lane);
+    float* dstg = gx + f * n3;
+    const uint32_t goff = (uint32_t)(reinterpret_cast<uintptr_t>(dstg) & 15u);
+    float* grow = reinterpret_cast<float*>(gbuf + goff);            // same 16-byte phase as the destination
+    if (lane == 0) bulk_wait_read0();          // the previous row's bulk store has finished reading the buffer
+    __syncwarp();
+    for (int i = lane; i < buf_bytes / 16; i += 32) reinterpret_cast<uint4*>(gbuf)[i] = make_uint4(0u, 0u, 0u, 0u);
+    __syncwarp();
+    Rigid rg;
+    if (aligned) kabsch<32>(xf, p.align_idx, p.ref_x, p.n_align, lane, rg);
+    SmemGIn gin{gf};
+    SmemRedAcc acc{grow};
+    float M[9], sg[3];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) M[i] = 0.f;
+    sg[0] = sg[1] = sg[2] = 0.f;
+    for (int e = lane; e < p.n_entries; e += 32) {
+      const Entry en = load_entry(p.entries + ENTRY_INTS * e);
+      feature_backward(en, xf, aligned, rg, p.use_angle, gin, acc, M, sg);
+    }
+    if (aligned) {
+#pragma unroll
+      for (int i = 0; i < 9; ++i) M[i] = gsum<32>(M[i]);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) sg[i] = gsum<32>(sg[i]);
+      float dH[9];
+      align_backward_dH(rg, M, dH);
+      const float inv_na = 1.0f / (float)p.n_align;
+      for (int k = lane; k < p.n_align; k += 32)
+        acc(p.align_idx[k],
+            align_atom_grad(dH, sg, inv_na, p.ref_x[3 * k], p.ref_x[3 * k + 1], p.ref_x[3 * k + 2]));
+    }
+    __syncwarp();
+    // write the row: head / tail up to the 16-byte grid with plain stores, the aligned middle as one bulk store
+    const int head = goff ? (int)((16u - goff) >> 2) : 0;            // floats before the first 16-byte boundary
+    const int mid = ((n3 - head) >> 2) << 2;
+    for (int i = lane; i < head && i < n3; i += 32) dstg[i] = grow[i];
+    for (int i = head + mid + lane; i < n3; i += 32) dstg[i] = grow[i];
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0 && mid > 0) {
+      bulk_s2g(dstg + head, grow + head, (uint32_t)mid * 4u);
+      bulk_commit();
+    }
+  }
+  if (lane == 0) bulk_wait0();
+}
+
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 align_forward_warp_kernel(const __grid_constant__ DevPlan p, const float* __restrict__ x, float* __restrict__ out,
                           long long L) {

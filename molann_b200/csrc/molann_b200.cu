@@ -581,6 +581,65 @@ size_t general_ws_bytes(const MolannPlan* p, long long L, bool backward) {
   return total;
 }
 
+// Staged preprocess kernels (general.cuh): every warp owns a frame buffer (two for the backward) in shared memory.
+// MOLANN_B200_STAGED = 0 keeps the gather kernels.
+struct StagedChoice {
+  bool ok = false;
+  int warps = 0, buf_bytes = 0, fbuf_bytes = 0, smem = 0;
+};
+StagedChoice choose_staged(const MolannPlan* p, bool backward, const DeviceInfo& dev) {
+  StagedChoice ch;
+  if (env_int("MOLANN_B200_STAGED", 1) == 0 || p->n_inp < 256) return ch;     // small frames: gathers are fine
+  ch.buf_bytes = round_up(3 * p->n_inp * 4 + 32, 128);
+  ch.fbuf_bytes = round_up(p->d_feat * 4 + 32, 128);
+  const int per_warp = backward ? 2 * ch.buf_bytes + ch.fbuf_bytes : ch.buf_bytes;
+  int w = (dev.max_smem_optin - 128) / per_warp;
+  if (w > WARPS_PER_CTA) w = WARPS_PER_CTA;
+  if (w < 2) return ch;
+  ch.warps = w;
+  ch.smem = 128 + w * per_warp;
+  ch.ok = true;
+  return ch;
+}
+int launch_preprocess_forward(const MolannPlan* p, const DevPlan& dp, const float* x, float* feat, long long L,
+                              const DeviceInfo& dev, cudaStream_t st) {
+  const StagedChoice sc = choose_staged(p, false, dev);
+  if (sc.ok) {
+    int s = check_cuda(cudaFuncSetAttribute(preprocess_forward_staged_kernel,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, sc.smem));
+    if (s) return s;
+    long long grid = (L + sc.warps - 1) / sc.warps;
+    if (grid > dev.sm_count) grid = dev.sm_count;
+    preprocess_forward_staged_kernel<<<(unsigned)grid, sc.warps * 32, sc.smem, st>>>(dp, x, feat, L, sc.buf_bytes);
+    return post_launch();
+  }
+  long long blocks = (L + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+  const long long cap = (long long)dev.sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  preprocess_forward_warp_kernel<<<(unsigned)(blocks < 1 ? 1 : blocks), WARPS_PER_CTA * 32, 0, st>>>(dp, x, feat, L);
+  return post_launch();
+}
+int launch_preprocess_backward(const MolannPlan* p, const DevPlan& dp, const float* x, const float* gfeat, float* gx,
+                               long long L, const DeviceInfo& dev, cudaStream_t st) {
+  const StagedChoice sc = choose_staged(p, true, dev);
+  if (sc.ok) {
+    int s = check_cuda(cudaFuncSetAttribute(preprocess_backward_staged_kernel,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, sc.smem));
+    if (s) return s;
+    long long grid = (L + sc.warps - 1) / sc.warps;
+    if (grid > dev.sm_count) grid = dev.sm_count;
+    preprocess_backward_staged_kernel<<<(unsigned)grid, sc.warps * 32, sc.smem, st>>>(dp, x, gfeat, gx, L,
+                                                                                      sc.buf_bytes, sc.fbuf_bytes);
+    return post_launch();
+  }
+  long long blocks = (L + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+  const long long cap = (long long)dev.sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  preprocess_backward_warp_kernel<<<(unsigned)(blocks < 1 ? 1 : blocks), WARPS_PER_CTA * 32, 0, st>>>(dp, x, gfeat, gx,
+                                                                                                   L);
+  return post_launch();
+}
+
 unsigned warp_grid(long long L, const DeviceInfo& dev) {
   long long blocks = (L + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
   const long long cap = (long long)dev.sm_count * 8;
@@ -677,9 +736,7 @@ int general_forward(const MolannPlan* p, const float* x, long long L, float* y, 
   const int kout = p->dims[p->n_layers];
   for (long long c0 = 0; c0 < L; c0 += ch) {
     const long long Lc = (L - c0 < ch) ? (L - c0) : ch;
-    preprocess_forward_warp_kernel<<<warp_grid(Lc, dev), WARPS_PER_CTA * 32, 0, st>>>(
-        dp, x + c0 * 3 * p->n_inp, feat, Lc);
-    int s = post_launch();
+    int s = launch_preprocess_forward(p, dp, x + c0 * 3 * p->n_inp, feat, Lc, dev, st);
     if (s) return s;
     const float* in = feat;
     for (int k = 0; k < p->n_layers; ++k) {
@@ -718,8 +775,7 @@ int general_backward(const MolannPlan* p, const float* x, const float* gy, long 
   for (long long c0 = 0; c0 < L; c0 += ch) {
     const long long Lc = (L - c0 < ch) ? (L - c0) : ch;
     const float* xc = x + c0 * 3 * p->n_inp;
-    preprocess_forward_warp_kernel<<<warp_grid(Lc, dev), WARPS_PER_CTA * 32, 0, st>>>(dp, xc, h[0], Lc);
-    int s = post_launch();
+    int s = launch_preprocess_forward(p, dp, xc, h[0], Lc, dev, st);
     if (s) return s;
     for (int k = 0; k < nl - 1; ++k) {
       s = launch_linear_forward(h[k], p->W[k], p->b[k], h[k + 1], Lc, p->dims[k], p->dims[k + 1], p->act_id, 1, st,
@@ -738,9 +794,7 @@ int general_backward(const MolannPlan* p, const float* x, const float* gy, long 
       if (s) return s;
       gz = gprev;
     }
-    preprocess_backward_warp_kernel<<<warp_grid(Lc, dev), WARPS_PER_CTA * 32, 0, st>>>(dp, xc, gz,
-                                                                                       gx + c0 * 3 * p->n_inp, Lc);
-    s = post_launch();
+    s = launch_preprocess_backward(p, dp, xc, gz, gx + c0 * 3 * p->n_inp, Lc, dev, st);
     if (s) return s;
   }
   return MOLANN_OK;
@@ -878,10 +932,7 @@ int molann_b200_preprocess_forward(const MolannPlan* plan, const float* x, int64
   if (misaligned4(x) || misaligned4(feat)) return MOLANN_ERR_ALIGNMENT;
   const DeviceInfo dev = device_info();
   if (!dev.ok) return MOLANN_ERR_CUDA;
-  const DevPlan dp = to_dev(plan);
-  preprocess_forward_warp_kernel<<<warp_grid(L, dev), WARPS_PER_CTA * 32, 0, static_cast<cudaStream_t>(stream)>>>(
-      dp, x, feat, L);
-  return post_launch();
+  return launch_preprocess_forward(plan, to_dev(plan), x, feat, (long long)L, dev, static_cast<cudaStream_t>(stream));
 }
 
 int molann_b200_preprocess_backward(const MolannPlan* plan, const float* x, const float* gfeat, int64_t L, float* gx,
@@ -894,10 +945,8 @@ int molann_b200_preprocess_backward(const MolannPlan* plan, const float* x, cons
   if (misaligned4(x) || misaligned4(gfeat) || misaligned4(gx)) return MOLANN_ERR_ALIGNMENT;
   const DeviceInfo dev = device_info();
   if (!dev.ok) return MOLANN_ERR_CUDA;
-  const DevPlan dp = to_dev(plan);
-  preprocess_backward_warp_kernel<<<warp_grid(L, dev), WARPS_PER_CTA * 32, 0, static_cast<cudaStream_t>(stream)>>>(
-      dp, x, gfeat, gx, L);
-  return post_launch();
+  return launch_preprocess_backward(plan, to_dev(plan), x, gfeat, gx, (long long)L, dev,
+                                    static_cast<cudaStream_t>(stream));
 }
 
 int molann_b200_align_forward(const MolannPlan* plan, const float* x, int64_t L, float* out, void* stream) {

@@ -400,14 +400,20 @@ def test_full_size_properties_c2():
     assert_parity(g1[idx.cuda()].cpu(), gx64, None, 2e-5, "full-size gx sample")
 
 
-def test_c3_full_width_general_path():
-    """n = 2000 atoms, d = 800 -> [800,256,128,2]: warp-per-frame geometry + layered GEMMs."""
+@pytest.mark.parametrize("kernels", ["tensor_core_staged", "ffma_gather"])
+def test_c3_full_width_general_path(kernels, monkeypatch):
+    """n = 2000 atoms, d = 800 -> [800,256,128,2]: warp-per-frame geometry + layered GEMMs.
+    tensor_core_staged = smem-staged preprocess kernels + tcgen05 3xTF32 GEMMs with segmented accumulation
+    (K = 800 is where the tensor core's accumulator rounding shows); ffma_gather = the CUDA-core kernels."""
+    if kernels == "ffma_gather":
+        monkeypatch.setenv("MOLANN_B200_GEMM_TC", "0")
+        monkeypatch.setenv("MOLANN_B200_STAGED", "0")
     spec = S.get_spec("C3")
     model, _ = S.build_model(spec)
     sd = model.state_dict()
     ws = [sd["ann_layers.%dth_layer.weight" % k] for k in (1, 2, 3)]
     bs = [sd["ann_layers.%dth_layer.bias" % k] for k in (1, 2, 3)]
-    L = 96
+    L = 203                                      # two row tiles, the second ragged; odd frame count
     x = S.make_frames(spec, L, seed=17)
     cot = torch.randn(L, 2, generator=torch.Generator().manual_seed(5))
     y64, gx64 = oracle_value_and_grad(oracle_model(spec, ws, bs), x, cot)
