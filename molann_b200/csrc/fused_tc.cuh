@@ -663,36 +663,41 @@ fused_tc_value_grad_kernel(const __grid_constant__ DevPlan p, const __grid_const
     }
     VG_EVT(vg_it, 3);
     publish_a_and_issue(smem + lay.bhi_off[0], smem + lay.blo_off[0], lay.kp[0], lay.np[0]);
+    // The epilogues are ROLLED 16-column loops: this kernel's executed path was ~70 KB of straight-line code per
+    // tile against a 32 KB L1.5 instruction cache ("no instruction" = 20 % of its stalls, profiles/r1_g).
     // ---- first hidden layer (only when there are two): h_1 -> A operand, act'(z_1) parked in TMEM ----
     if (nh == 2) {
       wait_mma();
       VG_EVT(vg_it, 4);
       const float* bias = reinterpret_cast<const float*>(smem + lay.bias_off[0]);
       const int np = lay.np[0];
+#pragma unroll 1
+      for (int c = 0; c < np; c += 16) {
+        float z[16];
+        tmem_ld16(lane_addr + COL_D + c, z);
+        tmem_wait_ld();
+        const float4* b4 = reinterpret_cast<const float4*>(bias + c);
+        uint32_t dv[16], hi[16], lo[16];
 #pragma unroll
-      for (int c = 0; c < TC_MAXW; c += 16) {
-        if (c < np) {
-          float z[16];
-          tmem_ld16(lane_addr + COL_D + c, z);
-          tmem_wait_ld();
-          uint32_t dv[16], hi[16], lo[16];
+        for (int q = 0; q < 4; ++q) {
+          const float4 b = b4[q];
+          const float bb[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
+          for (int i = 0; i < 4; ++i) {
             float hh, dd;
-            act_value_and_grad_t<ACT>(z[i] + bias[c + i], hh, dd);
-            dv[i] = __float_as_uint(dd);
-            split_tf32_rn(hh, hi[i], lo[i]);
+            act_value_and_grad_t<ACT>(z[4 * q + i] + bb[i], hh, dd);
+            dv[4 * q + i] = __float_as_uint(dd);
+            split_tf32_rn(hh, hi[4 * q + i], lo[4 * q + i]);
           }
-          tmem_st16(lane_addr + COL_H1 + c, dv);
-          tmem_st16(lane_addr + COL_AHI + c, hi);
-          tmem_st16(lane_addr + COL_ALO + c, lo);
         }
+        tmem_st16(lane_addr + COL_H1 + c, dv);
+        tmem_st16(lane_addr + COL_AHI + c, hi);
+        tmem_st16(lane_addr + COL_ALO + c, lo);
       }
       VG_EVT(vg_it, 5);
       publish_a_and_issue(smem + lay.bhi_off[1], smem + lay.blo_off[1], lay.kp[1], lay.np[1]);
     }
-    // ---- last hidden layer, streamed 16 columns at a time: y += h W_last^T, gz = (gy W_last) * act'(z) ----
-    float h[TC_MAXW];                    // h := gy W_last (cotangent of the last hidden activation)
+    // ---- last hidden layer, 16 columns at a time: y += h W_last^T, gz = (gy W_last) * act'(z) ----
     {
       const float* wl = reinterpret_cast<const float*>(smem + lay.wlast_off);
       const float* bl = reinterpret_cast<const float*>(smem + lay.blast_off);
@@ -701,61 +706,65 @@ fused_tc_value_grad_kernel(const __grid_constant__ DevPlan p, const __grid_const
       float yacc[8];
 #pragma unroll
       for (int o = 0; o < 8; ++o) yacc[o] = (o < kout) ? bl[o] : 0.f;
-#pragma unroll
-      for (int j = 0; j < TC_MAXW; ++j) h[j] = 0.f;
-#pragma unroll
-      for (int o = 0; o < 8; ++o) {
-        if (o < kout) {
-          const float4* w4 = reinterpret_cast<const float4*>(wl + o * TC_MAXW);
-          const float g_o = go[o];
-#pragma unroll
-          for (int j = 0; j < TC_MAXW / 4; ++j) {
-            const float4 w = w4[j];
-            h[4 * j] = fmaf(g_o, w.x, h[4 * j]);
-            h[4 * j + 1] = fmaf(g_o, w.y, h[4 * j + 1]);
-            h[4 * j + 2] = fmaf(g_o, w.z, h[4 * j + 2]);
-            h[4 * j + 3] = fmaf(g_o, w.w, h[4 * j + 3]);
-          }
-        }
-      }
       VG_EVT(vg_it, 6);
       wait_mma();
       VG_EVT(vg_it, 7);
+#pragma unroll 1
+      for (int c = 0; c < np; c += 16) {
+        float z[16];
+        tmem_ld16(lane_addr + COL_D + c, z);
+        float gh[16];                              // (gy W_last)[c .. c+15], formed while the load is in flight
 #pragma unroll
-      for (int c = 0; c < TC_MAXW; c += 16) {
-        if (c < np) {
-          float z[16];
-          tmem_ld16(lane_addr + COL_D + c, z);
-          tmem_wait_ld();
-          uint32_t hi[16], lo[16];
+        for (int i = 0; i < 16; ++i) gh[i] = 0.f;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float hh, dd;
-            act_value_and_grad_t<ACT>(z[i] + bias[c + i], hh, dd);
-            z[i] = hh;
-            split_tf32_rn(h[c + i] * dd, hi[i], lo[i]);          // gz of the last hidden layer
-          }
-          tmem_st16(lane_addr + COL_AHI + c, hi);
-          tmem_st16(lane_addr + COL_ALO + c, lo);
-          if (y != nullptr) {
+        for (int o = 0; o < 8; ++o) {
+          if (o < kout) {
+            const float4* w4 = reinterpret_cast<const float4*>(wl + o * TC_MAXW + c);
+            const float g_o = go[o];
 #pragma unroll
-            for (int o = 0; o < 8; ++o) {
-              if (o < kout) {
-                const float4* w4 = reinterpret_cast<const float4*>(wl + o * TC_MAXW + c);
-                float a = 0.f, b = 0.f;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  const float4 w = w4[q];
-                  a = fmaf(z[4 * q], w.x, a);
-                  b = fmaf(z[4 * q + 1], w.y, b);
-                  a = fmaf(z[4 * q + 2], w.z, a);
-                  b = fmaf(z[4 * q + 3], w.w, b);
-                }
-                yacc[o] += a + b;
-              }
+            for (int q = 0; q < 4; ++q) {
+              const float4 w = w4[q];
+              gh[4 * q] = fmaf(g_o, w.x, gh[4 * q]);
+              gh[4 * q + 1] = fmaf(g_o, w.y, gh[4 * q + 1]);
+              gh[4 * q + 2] = fmaf(g_o, w.z, gh[4 * q + 2]);
+              gh[4 * q + 3] = fmaf(g_o, w.w, gh[4 * q + 3]);
             }
           }
-        } else if (c < lay.np[nh - 1]) {
+        }
+        tmem_wait_ld();
+        const float4* b4 = reinterpret_cast<const float4*>(bias + c);
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 b = b4[q];
+          const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float hh, dd;
+            act_value_and_grad_t<ACT>(z[4 * q + i] + bb[i], hh, dd);
+            z[4 * q + i] = hh;
+            split_tf32_rn(gh[4 * q + i] * dd, hi[4 * q + i], lo[4 * q + i]);      // gz of the last hidden layer
+          }
+        }
+        tmem_st16(lane_addr + COL_AHI + c, hi);
+        tmem_st16(lane_addr + COL_ALO + c, lo);
+        if (y != nullptr) {
+#pragma unroll
+          for (int o = 0; o < 8; ++o) {
+            if (o < kout) {
+              const float4* w4 = reinterpret_cast<const float4*>(wl + o * TC_MAXW + c);
+              float a = 0.f, b = 0.f;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float4 w = w4[q];
+                a = fmaf(z[4 * q], w.x, a);
+                b = fmaf(z[4 * q + 1], w.y, b);
+                a = fmaf(z[4 * q + 2], w.z, a);
+                b = fmaf(z[4 * q + 3], w.w, b);
+              }
+              yacc[o] += a + b;
+            }
+          }
         }
       }
       if (y != nullptr && wt < nf) {
@@ -772,19 +781,17 @@ fused_tc_value_grad_kernel(const __grid_constant__ DevPlan p, const __grid_const
       publish_a_and_issue(smem + lay.thi_off[k], smem + lay.tlo_off[k], kb, nb);
       wait_mma();
       if (k > 0) {               // gz_k = gh_k * act'(z_k) (parked in TMEM) -> A operand of the next contraction
+#pragma unroll 1
+        for (int c = 0; c < nb; c += 16) {
+          float gh[16], dk[16];
+          tmem_ld16(lane_addr + COL_D + c, gh);
+          tmem_ld16(lane_addr + COL_H1 + c, dk);
+          tmem_wait_ld();
+          uint32_t hi[16], lo[16];
 #pragma unroll
-        for (int c = 0; c < TC_MAXW; c += 16) {
-          if (c < nb) {
-            float gh[16], dk[16];
-            tmem_ld16(lane_addr + COL_D + c, gh);
-            tmem_ld16(lane_addr + COL_H1 + c, dk);
-            tmem_wait_ld();
-            uint32_t hi[16], lo[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) split_tf32_rn(gh[i] * dk[i], hi[i], lo[i]);
-            tmem_st16(lane_addr + COL_AHI + c, hi);
-            tmem_st16(lane_addr + COL_ALO + c, lo);
-          }
+          for (int i = 0; i < 16; ++i) split_tf32_rn(gh[i] * dk[i], hi[i], lo[i]);
+          tmem_st16(lane_addr + COL_AHI + c, hi);
+          tmem_st16(lane_addr + COL_ALO + c, lo);
         }
       }
     }

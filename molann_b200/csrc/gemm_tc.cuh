@@ -32,7 +32,7 @@ namespace molann {
 constexpr int GT_M = 128;                      // rows per tile
 constexpr int GT_KC = 32;                      // K per chunk (8 K-major 16-byte chunks)
 constexpr int GT_NMAX = 256;                   // columns per tile
-constexpr int GT_SEG = 4;                      // K-chunks per TMEM accumulation segment (128 K = 48 MMAs)
+constexpr int GT_SEG = 1;                      // default K-chunks per TMEM accumulation segment (32 K = 12 MMAs)
 constexpr int GT_THREADS = 28 * 32;            // 4 converter + 16 epilogue + (producer, MMA, 2 idle) + 4 idle warps
 // setmaxnreg budgets.  The pool is what the CTA was LAUNCHED with (896 threads x 72 registers = 64512), not the SM's
 // register file: increases beyond it wait forever.  4*96 + 16*88 + 4*32 + 4*24 warps x 32 = 64512.  The idle
@@ -133,7 +133,7 @@ template <int EPI>
 __global__ void __launch_bounds__(GT_THREADS, 1)
 gemm_tc_kernel(const float* __restrict__ A, long long lda, long long M, int K, const float* __restrict__ Bp, int N,
                float* __restrict__ C, long long ldc, const float* __restrict__ bias, const float* __restrict__ H,
-               int act, int apply_act) {
+               int act, int apply_act, int seg) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + 2 * GT_STAGE_BYTES);
@@ -201,8 +201,8 @@ gemm_tc_kernel(const float* __restrict__ A, long long lda, long long M, int K, c
       for (int kc = 0; kc < nkc; ++kc, ++g) {
         const int db = sg & 1;
         const uint32_t d = (uint32_t)db * GT_NMAX;
-        const bool seg_first = (kc % GT_SEG) == 0;
-        const bool seg_last = (kc % GT_SEG) == GT_SEG - 1 || kc == nkc - 1;
+        const bool seg_first = (kc % seg) == 0;
+        const bool seg_last = (kc % seg) == seg - 1 || kc == nkc - 1;
         if (seg_first) {
           mbar_wait_hint(&d_free[db], (uint32_t)(((sg >> 1) & 1) ^ 1));
           tc_fence_after_sync();
@@ -214,6 +214,9 @@ gemm_tc_kernel(const float* __restrict__ A, long long lda, long long M, int K, c
         tc_fence_after_sync();
         const uint32_t a_hi = smem_u32(smem + s * GT_STAGE_BYTES), a_lo = a_hi + GT_A_BYTES;
         const uint32_t b_hi = a_hi + 2 * GT_A_BYTES, b_lo = b_hi + (uint32_t)np * GT_KC * 4u;
+        // the chunk's eight cross-term MMAs first, its four leading-term MMAs last: every accumulation step
+        // truncates at the magnitude the accumulator has reached, and in a fresh accumulator (seg = 1: every
+        // chunk) the cross terms are 2^-11 of the result, so only the four leading steps round at full scale
 #pragma unroll 1
         for (int j = 0; j < GT_KC / 8; ++j) {
           const uint64_t ah = smem_desc_kmajor(a_hi + j * (2u * GT_M * 16u), GT_M * 16u, 128);
@@ -221,10 +224,15 @@ gemm_tc_kernel(const float* __restrict__ A, long long lda, long long M, int K, c
           const uint64_t bh = smem_desc_kmajor(b_hi + j * (2u * lbo_b), lbo_b, 128);
           const uint64_t bl = smem_desc_kmajor(b_lo + j * (2u * lbo_b), lbo_b, 128);
           if (leader) {
-            mma_tf32_ss(d, al, bh, idesc, (!seg_first || j > 0) ? 1u : 0u);     // small terms first
+            mma_tf32_ss(d, al, bh, idesc, (!seg_first || j > 0) ? 1u : 0u);
             mma_tf32_ss(d, ah, bl, idesc, 1);
-            mma_tf32_ss(d, ah, bh, idesc, 1);
           }
+        }
+#pragma unroll 1
+        for (int j = 0; j < GT_KC / 8; ++j) {
+          const uint64_t ah = smem_desc_kmajor(a_hi + j * (2u * GT_M * 16u), GT_M * 16u, 128);
+          const uint64_t bh = smem_desc_kmajor(b_hi + j * (2u * lbo_b), lbo_b, 128);
+          if (leader) mma_tf32_ss(d, ah, bh, idesc, 1);
         }
         if (leader) mma_commit(&empty[s]);
         if (seg_last) {
@@ -295,7 +303,7 @@ gemm_tc_kernel(const float* __restrict__ A, long long lda, long long M, int K, c
     const uint32_t lane_base = ((uint32_t)((warp & 3) * 32) << 16);
     const bool vec = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15u) == 0) &&
                      (EPI != GT_EPI_DACT || H == nullptr || (reinterpret_cast<uintptr_t>(H) & 15u) == 0);
-    const int nseg = (nkc + GT_SEG - 1) / GT_SEG;
+    const int nseg = (nkc + seg - 1) / seg;
     int sg = 0;
     for (long long item = first; item < nitems; item += stride) {
       const int n_tile = (int)(item % nt);
@@ -310,16 +318,13 @@ gemm_tc_kernel(const float* __restrict__ A, long long lda, long long M, int K, c
         mbar_wait_hint(&d_full[db], (uint32_t)((sg >> 1) & 1));
         tc_fence_after_sync();
 #pragma unroll
-        for (int c = 0; c < 64; c += 8) {       // 8 columns at a time: 64 running sums already fill the registers
+        for (int c = 0; c < 64; c += 16) {      // 16 columns at a time: 64 running sums already fill the registers
           if (64 * e + c < np) {
-            uint32_t u[8];
-            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                         : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
-                         : "r"(lane_base + (uint32_t)db * GT_NMAX + 64 * e + c)
-                         : "memory");
+            float u[16];
+            tmem_ld16(lane_base + (uint32_t)db * GT_NMAX + 64 * e + c, u);
             tmem_wait_ld();
 #pragma unroll
-            for (int i = 0; i < 8; ++i) acc[c + i] += __uint_as_float(u[i]);
+            for (int i = 0; i < 16; ++i) acc[c + i] += u[i];
           }
         }
         tc_fence_before_sync();

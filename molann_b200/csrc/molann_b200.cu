@@ -671,8 +671,10 @@ int launch_gemm_tc(const float* A, long long M, int K, const float* W, long long
   const long long items = ((M + GT_M - 1) / GT_M) * ((N + GT_NMAX - 1) / GT_NMAX);
   long long grid = dev.sm_count;
   if (grid > items) grid = items;
+  int seg = env_int("MOLANN_B200_GEMM_SEG", GT_SEG);
+  if (seg < 1) seg = 1;
   kern<<<(unsigned)grid, GT_THREADS, GT_SMEM_BYTES, st>>>(A, (long long)K, M, K, pack, N, C, (long long)N, bias, H, act,
-                                                          apply_act);
+                                                          apply_act, seg);
   return post_launch();
 }
 
