@@ -29,7 +29,11 @@ struct RedAcc {
   float* row;
   __device__ __forceinline__ void operator()(int atom, V3 v) {
     float* q = row + 3 * atom;
+#ifdef MOLANN_PROBE_NO_RED                      // tests/cuda/sb_trace.cu: what the REDs cost (results are wrong)
+    if (v.x == 123456.f) q[0] = v.y + v.z;
+#else
     atomicAdd(q, v.x); atomicAdd(q + 1, v.y); atomicAdd(q + 2, v.z);
+#endif
   }
 };
 

@@ -15,6 +15,7 @@
 #include "fused_tc.cuh"
 #include "fused_ws.cuh"
 #include "gemm_tc.cuh"
+#include "staged_block.cuh"
 #include "general.cuh"
 
 using namespace molann;
@@ -601,8 +602,64 @@ StagedChoice choose_staged(const MolannPlan* p, bool backward, const DeviceInfo&
   ch.ok = true;
   return ch;
 }
+// Block-per-frame pipelined kernels (staged_block.cuh): MOLANN_B200_STAGED = 2 (default) for big frames; = 1 keeps
+// the warp-per-frame staged kernels, = 0 the gather kernels.  Ring depth: MOLANN_B200_SB_STAGES (default 2, the
+// minimum), reduced towards 2 while it costs the second CTA per SM.
+struct BlockChoice {
+  bool ok = false;
+  SbLayout lay;
+};
+BlockChoice choose_block(const MolannPlan* p, bool backward, const DeviceInfo& dev) {
+  BlockChoice ch;
+  const int mode = env_int("MOLANN_B200_STAGED", 2);
+  if (mode < 2 || p->n_inp < 256) return ch;
+  // forward: the warp-per-frame staged kernel still wins while 5+ frames fit on an SM (C3: 0.20 vs 0.23 ms per 32768
+  // frames); the role pipeline takes over for frames beyond 40 KB (C5: 0.36 vs 0.38 ms).  MOLANN_B200_STAGED = 3
+  // forces the block kernel in both directions.
+  if (!backward && mode < 3 && 3 * p->n_inp * 4 <= 40 * 1024) return ch;
+  SbLayout& lay = ch.lay;
+  lay.buf_bytes = round_up(3 * p->n_inp * 4 + 32, 128);
+  lay.fbuf_bytes = backward ? round_up(p->d_feat * 4 + 32, 128) : 0;
+  int off = SB_HEAD;
+  lay.aidx_off = off; off += round_up(4 * p->n_align, 16);
+  lay.ref_off = off; off += round_up(12 * p->n_align, 16);
+  lay.ent_off = off; off += round_up(4 * MOLANN_ENTRY_INTS * p->n_entries, 128);
+  lay.ring_off = off;
+  const int slot = lay.buf_bytes + lay.fbuf_bytes;
+  int stages = env_int("MOLANN_B200_SB_STAGES", 2);
+  if (stages > 4) stages = 4;
+  if (stages < 2) stages = 2;                                 // the roles run one frame apart: two slots at least
+  const int two_ctas = (dev.smem_per_sm / 2) - 1024;          // budget per CTA that keeps two resident
+  while (stages > 2 && off + stages * slot > two_ctas) --stages;
+  if (off + stages * slot > dev.max_smem_optin) return ch;
+  lay.stages = stages;
+  lay.total = off + stages * slot;
+  ch.ok = true;
+  return ch;
+}
+template <class Kern>
+int block_grid(Kern kern, int smem, long long L, const DeviceInfo& dev, long long* grid) {
+  int s = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  if (s) return s;
+  int per_sm = 0;
+  s = check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SB_THREADS, (size_t)smem));
+  if (s) return s;
+  const int want = env_int("MOLANN_B200_SB_CTAS", 0);
+  if (want > 0 && want < per_sm) per_sm = want;
+  *grid = (long long)dev.sm_count * (per_sm < 1 ? 1 : per_sm);
+  if (*grid > L) *grid = L;
+  return MOLANN_OK;
+}
 int launch_preprocess_forward(const MolannPlan* p, const DevPlan& dp, const float* x, float* feat, long long L,
                               const DeviceInfo& dev, cudaStream_t st) {
+  const BlockChoice bc = choose_block(p, false, dev);
+  if (bc.ok) {
+    long long grid = 1;
+    int s = block_grid(preprocess_forward_block_kernel, bc.lay.total, L, dev, &grid);
+    if (s) return s;
+    preprocess_forward_block_kernel<<<(unsigned)grid, SB_THREADS, bc.lay.total, st>>>(dp, bc.lay, x, feat, L);
+    return post_launch();
+  }
   const StagedChoice sc = choose_staged(p, false, dev);
   if (sc.ok) {
     int s = check_cuda(cudaFuncSetAttribute(preprocess_forward_staged_kernel,
@@ -621,6 +678,14 @@ int launch_preprocess_forward(const MolannPlan* p, const DevPlan& dp, const floa
 }
 int launch_preprocess_backward(const MolannPlan* p, const DevPlan& dp, const float* x, const float* gfeat, float* gx,
                                long long L, const DeviceInfo& dev, cudaStream_t st) {
+  const BlockChoice bc = choose_block(p, true, dev);
+  if (bc.ok) {
+    long long grid = 1;
+    int s = block_grid(preprocess_backward_block_kernel, bc.lay.total, L, dev, &grid);
+    if (s) return s;
+    preprocess_backward_block_kernel<<<(unsigned)grid, SB_THREADS, bc.lay.total, st>>>(dp, bc.lay, x, gfeat, gx, L);
+    return post_launch();
+  }
   const StagedChoice sc = choose_staged(p, true, dev);
   if (sc.ok) {
     int s = check_cuda(cudaFuncSetAttribute(preprocess_backward_staged_kernel,

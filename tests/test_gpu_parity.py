@@ -400,7 +400,7 @@ def test_full_size_properties_c2():
     assert_parity(g1[idx.cuda()].cpu(), gx64, None, 2e-5, "full-size gx sample")
 
 
-@pytest.mark.parametrize("kernels", ["tensor_core_staged", "ffma_gather"])
+@pytest.mark.parametrize("kernels", ["tensor_core_staged", "tensor_core_warp_staged", "ffma_gather"])
 def test_c3_full_width_general_path(kernels, monkeypatch):
     """n = 2000 atoms, d = 800 -> [800,256,128,2]: warp-per-frame geometry + layered GEMMs.
     tensor_core_staged = smem-staged preprocess kernels + tcgen05 3xTF32 GEMMs with segmented accumulation
@@ -408,6 +408,8 @@ def test_c3_full_width_general_path(kernels, monkeypatch):
     if kernels == "ffma_gather":
         monkeypatch.setenv("MOLANN_B200_GEMM_TC", "0")
         monkeypatch.setenv("MOLANN_B200_STAGED", "0")
+    elif kernels == "tensor_core_warp_staged":
+        monkeypatch.setenv("MOLANN_B200_STAGED", "1")
     spec = S.get_spec("C3")
     model, _ = S.build_model(spec)
     sd = model.state_dict()
@@ -425,6 +427,70 @@ def test_c3_full_width_general_path(kernels, monkeypatch):
     assert_parity(y.detach().cpu(), y64, y32, TOL, "C3 y")
     assert_parity(gx.cpu(), gx64, gx32, 2e-5, "C3 gx")
     assert int((gx.cpu() != 0).any(dim=2).sum(dim=1).max()) <= 200 + 400       # dense row, sparse support
+
+
+@pytest.mark.parametrize("staged", ["3", "2", "1", "0"])
+@pytest.mark.parametrize("with_align", [True, False])
+def test_big_frame_preprocess_kernel_sets(staged, with_align, monkeypatch):
+    """Preprocessing of a 303-atom system (rows of 3636 bytes: every other row starts off the 16-byte grid, the last
+    one takes the non-bulk path) with all four feature types, several contributions per atom, 77 frames: the
+    block-per-frame role pipeline in both directions (3) or for the backward only (2, the default), the
+    warp-per-frame staged kernels (1) and the gather kernels (0)."""
+    from molann_b200.ann import AlignmentLayer, FeatureLayer, PreprocessingANN
+    from molann_b200.atomgroup import Universe
+    from molann_b200.feature import Feature
+    monkeypatch.setenv("MOLANN_B200_STAGED", staged)
+    n, L = 303, 77
+    rng = np.random.RandomState(5)
+    u = Universe(S.chain_positions(n, 11))
+    inp = u.select_ix(np.arange(n))
+    sel = np.arange(0, n, 7)
+    feats = [Feature("p", "position", u.select_ix(sel))]
+    for k in range(40):
+        a = 7 * k
+        feats.append(Feature("d%d" % k, "dihedral", u.select_ix([a, a + 1, a + 2, a + 3])))
+        feats.append(Feature("b%d" % k, "bond", u.select_ix([a + 3, a + 4])))
+        feats.append(Feature("a%d" % k, "angle", u.select_ix([a + 2, a + 4, a + 5])))
+    feats.append(Feature("p2", "position", u.select_ix(rng.permutation(n)[:30])))
+    al = AlignmentLayer(u.select_ix(sel), inp) if with_align else None
+    pp = PreprocessingANN(al, FeatureLayer(feats, inp, use_angle_value=False)).cuda()
+    base = torch.from_numpy(u.atoms.positions)
+    g = torch.Generator().manual_seed(8)
+    x = base.unsqueeze(0) + 0.2 * torch.randn(L, n, 3, generator=g)
+    x = torch.bmm(x, S.random_rotations(L, g, "cpu")) + 11.0
+    fl = [(f.get_type_id(), list(f.atom_group.ix)) for f in feats]
+    ref = torch.from_numpy(u.atoms.positions[sel])
+    ref = (ref - ref.mean(0)).double()
+    fn = lambda xx: R.preprocess_forward(xx, list(sel) if with_align else None, ref if with_align else None, fl, False)
+    cot = torch.randn(L, pp.output_dimension(), generator=g)
+    f64, gx64 = oracle_value_and_grad(fn, x, cot)
+    flat = torch.empty(L * n * 3 + 1, device="cuda")
+    for shift in (0, 1):                                   # 16-byte aligned base, then a base 4 bytes off
+        xd = flat[shift:shift + L * n * 3].view(L, n, 3)
+        xd.copy_(x)
+        xd = xd.detach().requires_grad_(True)
+        f = pp(xd)
+        (gx,) = torch.autograd.grad(f, xd, cot.cuda())
+        assert_parity(f.detach().cpu(), f64, None, TOL, "big-frame features staged=%s shift=%d" % (staged, shift))
+        assert_parity(gx.cpu(), gx64, None, 2e-5, "big-frame gx staged=%s shift=%d" % (staged, shift))
+
+
+def test_c5_shape_parity():
+    """BASELINE configs[4] shape (5000 atoms, 500-atom selection, d = 2000 -> [2000,256,128,2]) on a few frames."""
+    spec = S.get_spec("C5")
+    model, _ = S.build_model(spec)
+    sd = model.state_dict()
+    ws = [sd["ann_layers.%dth_layer.weight" % k] for k in (1, 2, 3)]
+    bs = [sd["ann_layers.%dth_layer.bias" % k] for k in (1, 2, 3)]
+    L = 131
+    x = S.make_frames(spec, L, seed=23)
+    cot = torch.randn(L, 2, generator=torch.Generator().manual_seed(6))
+    y64, gx64 = oracle_value_and_grad(oracle_model(spec, ws, bs), x, cot)
+    y32, gx32 = oracle_value_and_grad(oracle_model(spec, ws, bs, torch.float32), x, cot, torch.float32)
+    model = model.cuda()
+    y, gx = model.value_and_grad(dev(x), cot.cuda())
+    assert_parity(y.cpu(), y64, y32, TOL, "C5 y")
+    assert_parity(gx.cpu(), gx64, gx32, 2e-5, "C5 gx")
 
 
 def test_torchscript_roundtrip_in_fresh_process(tmp_path):
