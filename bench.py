@@ -42,7 +42,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C3", "C5"])
+    ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C3", "C4", "C5"])
     ap.add_argument("--frames", type=int, default=0, help="frames per GPU per step (default: workload's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -253,6 +253,153 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------------------
+# C4: data-parallel autoencoder training (BASELINE.json configs[3]): encoder = the C2 MolANN, decoder =
+# create_sequential_nn([2,64,64,30]), loss = mean((dec(enc(x)) - preprocessing(x))^2), plain SGD, FIXED global batch of
+# 2^20 frames split over the ranks (strong scaling), one flat allreduce of the MLP gradients per step.
+# ------------------------------------------------------------------------------------------------------------
+C4_GLOBAL = 1 << 20
+C4_NOTE = ("C4: autoencoder training, encoder = C2 MolANN [30,64,64,2], decoder [2,64,64,30], MSE against the "
+           "preprocessing output, SGD lr 1e-3, global batch 2^20 frames")
+
+
+def c4_models(api=None):
+    from molann_b200 import synthetic as S
+    spec = S.get_spec("C2")
+    enc, _ = S.build_model(spec, api)
+    torch.manual_seed(404)
+    create = (api or S.default_api()).create_sequential_nn
+    dec = create([spec.out_dim(), 64, 64, spec.feature_dim()])
+    return spec, enc, dec
+
+
+def c4_cpu_step_rate(frames, steps, warmup=1):
+    """The reference's modules (baseline/_ref, else the drop-in classes are NOT used: oracle port) training on CPU."""
+    import warnings
+    from molann_b200 import synthetic as S
+    from molann_b200.train import AutoencoderStep
+    api, kind, where = reference_api()
+    if api is None:
+        return None, kind, where
+    spec, enc, dec = c4_models(api)
+    step = AutoencoderStep(enc, dec, lr=1e-3)
+    x = S.make_frames(spec, frames, seed=404)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for _ in range(warmup):
+            step.step(x)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step.step(x)
+        dt = time.perf_counter() - t0
+    return steps * frames / dt, kind, where
+
+
+def run_training(args, rank, local_rank, world):
+    import torch.distributed as dist
+    from molann_b200 import _lib
+    from molann_b200 import synthetic as S
+    from molann_b200.shard import frame_range
+    from molann_b200.train import AutoencoderStep
+    spec, enc, dec = c4_models()
+    enc, dec = enc.cuda(), dec.cuda()
+    n_global = args.frames * world if args.frames else C4_GLOBAL
+    lo, hi = frame_range(n_global, rank, world)
+    x = S.make_frames(spec, hi - lo, device="cuda", seed=404 + rank)
+    trainer = AutoencoderStep(enc, dec, lr=1e-3, global_frames=n_global)
+    K, W = args.steps, max(args.warmup, 3)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    sampler = ClockSampler(local_rank)
+    for _ in range(W):
+        trainer.step(x)
+    barrier()
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.start()
+    e0.record()
+    for _ in range(K):
+        loss = trainer.step(x)
+    e1.record()
+    barrier()
+    sampler.pause()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = _lib.launch_count() - l0
+    # the collective alone (flat gradient buffer of this model), same stream, device-timed
+    nparam = sum(p.numel() for p in trainer.params)
+    flat = torch.zeros(nparam + 1, device="cuda")
+    ar_ms = 0.0
+    if world > 1:
+        for _ in range(3):
+            dist.all_reduce(flat)
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(20):
+            dist.all_reduce(flat)
+        a1.record()
+        barrier()
+        ar_ms = max_over_ranks(a0.elapsed_time(a1)) / 20
+    # end to end: this rank's shard arrives from pinned host memory every step, the loss is read back
+    xh = x.cpu().pin_memory()
+    ke = max(3, min(K, 10))
+    for _ in range(2):
+        x.copy_(xh, non_blocking=True)
+        float(trainer.step(x))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(ke):
+        x.copy_(xh, non_blocking=True)
+        last = float(trainer.step(x))
+    torch.cuda.synchronize()
+    ms_e = max_over_ranks(1e3 * (time.perf_counter() - t0))
+    clocks = sampler.summary()
+    sampler.close()
+    if rank != 0:
+        return
+    peak, peak_src = peaks()
+    value = n_global * K / (ms * 1e-3)
+    bytes_per_frame = 12 * spec.n_inp                      # SURVEY 8(d): B_train = 12 n_inp per frame
+    achieved = value * bytes_per_frame / world / 1e9
+    line = {
+        "metric": "frames_per_sec_train", "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": C4_NOTE, "n_inp": spec.n_inp, "global_batch_frames": n_global,
+                   "frames_per_gpu_per_step": hi - lo, "trainable_parameters": nparam,
+                   "l2_policy": "inputs larger than L2 (%.0f MB per step per GPU)" % ((hi - lo) * 12 * spec.n_inp / 1e6),
+                   "parallelism": "data-parallel x%d, one flat sum-allreduce of %d floats per step (NCCL)"
+                                  % (world, nparam + 1)},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src,
+                     "note": "per GPU, algorithmic 12*n_inp bytes per frame; the step is compute/launch bound "
+                             "(74 kFLOP per frame incl. weight gradients), see DESIGN.md"},
+        "gpu_launches": int(launches), "allreduce_ms": ar_ms, "final_loss": float(loss), "clocks": clocks,
+        "e2e": {"value": n_global * ke / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(xh.numel() * 4),
+                "d2h_bytes_per_step": 4, "steps": ke, "ms_per_step": ms_e / ke, "last_loss": last,
+                "api": "x.copy_(pinned shard); molann_b200.train.AutoencoderStep.step(x); float(loss)"},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        rate, kind, where = c4_cpu_step_rate(1 << 16, 3)
+        if rate is not None:
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": kind,
+                                    "sample": "3 SGD steps on 65536 frames; %s; torch.set_num_threads(%d)"
+                                              % (where, os.cpu_count() or 1)}
+    print(json.dumps(line), flush=True)
+
+
 def workload_config(spec, frames, n_gpus):
     return {"workload": "%s: %s" % (spec.name, spec.note), "n_inp": spec.n_inp, "d_feat": spec.feature_dim(),
             "mlp": spec.layer_dims, "frames_per_gpu_per_step": frames,
@@ -268,6 +415,19 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
+        if args.workload == "C4":
+            if rank == 0:
+                torch.set_num_threads(os.cpu_count() or 1)
+                rate, kind, where = c4_cpu_step_rate(1 << 16, max(1, args.steps), 1)
+                print(json.dumps({"impl": "reference", "metric": "frames_per_sec_train", "value": rate, "unit": UNIT,
+                                  "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                                  "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                                  "data": "synthetic", "config": {"workload": C4_NOTE},
+                                  "cpu_baseline": {"value": rate, "unit": UNIT, "cores": os.cpu_count() or 1,
+                                                   "kind": kind, "sample": "SGD steps on 65536 frames; " + where},
+                                  "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0,
+                                          "d2h_bytes_per_step": 0}}), flush=True)
+            return
         run_reference(args, rank)
         return
     if not torch.cuda.is_available():
@@ -277,6 +437,13 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+
+    if args.workload == "C4":
+        torch.set_num_threads(os.cpu_count() or 1)
+        run_training(args, rank, local_rank, world)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     from molann_b200 import _lib
     from molann_b200 import synthetic as S

@@ -72,3 +72,66 @@ def test_two_rank_gradient_allreduce_equals_single_process():
         assert torch.allclose(gp, ref, rtol=1e-10, atol=1e-12), name
     assert abs(loss - float((torch.from_numpy(g["y64"]) * torch.from_numpy(g["cot"]).double()).sum())) < 1e-9
     assert torch.allclose(y, torch.from_numpy(g["y64"]), atol=1e-12)
+
+
+class _OracleEncoder(torch.nn.Module):
+    """CPU stand-in with the MolANN surface AutoencoderStep uses (the product has no CPU path): the oracle restatement
+    as compute, the C2 MLP as parameters."""
+
+    def __init__(self, spec, ws, bs):
+        super().__init__()
+        self.spec = spec
+        self.ws = torch.nn.ParameterList([torch.nn.Parameter(w.double().clone()) for w in ws])
+        self.bs = torch.nn.ParameterList([torch.nn.Parameter(b.double().clone()) for b in bs])
+
+    def get_preprocessing_layer(self):
+        from helpers import oracle_preprocess
+        return oracle_preprocess(self.spec)
+
+    def forward(self, x):
+        return oracle_model(self.spec, list(self.ws), list(self.bs))(x)
+
+
+def _make_c4(spec, g):
+    ws, bs = golden_weights(g, 3)
+    enc = _OracleEncoder(spec, ws, bs)
+    torch.manual_seed(404)
+    dec = torch.nn.Sequential(torch.nn.Linear(2, 16), torch.nn.Tanh(), torch.nn.Linear(16, 30)).double()
+    return enc, dec
+
+
+def _train_worker(rank, world, port, ret):
+    from molann_b200.train import AutoencoderStep
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    spec = S.get_spec("C2")
+    g = golden("config_C2")
+    enc, dec = _make_c4(spec, g)
+    x = torch.from_numpy(g["x"]).double()
+    s, e = frame_range(x.shape[0], rank, world)
+    trainer = AutoencoderStep(enc, dec, lr=1e-2, global_frames=x.shape[0])
+    losses = [float(trainer.step(x[s:e])) for _ in range(2)]
+    if rank == 0:
+        ret["losses"] = losses
+        ret["params"] = [p.detach().clone() for p in trainer.params]
+    dist.destroy_process_group()
+
+
+def test_two_rank_autoencoder_step_equals_single_process():
+    """C4 host logic: sharded batch + ONE flat allreduce (gradients + loss) + SGD == the single-process step."""
+    from molann_b200.train import AutoencoderStep
+    spec = S.get_spec("C2")
+    g = golden("config_C2")
+    enc, dec = _make_c4(spec, g)
+    x = torch.from_numpy(g["x"]).double()
+    single = AutoencoderStep(enc, dec, lr=1e-2, global_frames=x.shape[0])
+    want = [float(single.step(x)) for _ in range(2)]
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_train_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
+        losses, params = ret["losses"], ret["params"]
+    assert all(abs(a - b) < 1e-12 * max(1.0, abs(b)) for a, b in zip(losses, want))
+    assert want[1] < want[0]
+    for p, q in zip(params, single.params):
+        assert torch.allclose(p, q.detach(), rtol=1e-10, atol=1e-13)

@@ -493,6 +493,50 @@ def test_c5_shape_parity():
     assert_parity(gx.cpu(), gx64, gx32, 2e-5, "C5 gx")
 
 
+def test_c4_training_step_gradients_and_sgd():
+    """BASELINE configs[3]: autoencoder step -- encoder = C2 MolANN through the fused kernels, decoder
+    = create_sequential_nn([2,64,64,30]), MSE against the preprocessing output.  Step-1 parameter gradients and the
+    loss against the fp64 oracle on a 4096-frame batch, then two SGD steps must lower the loss."""
+    import copy
+    sys.path.insert(0, ROOT)
+    from bench import c4_models
+    from molann_b200.train import AutoencoderStep
+    spec, enc, dec = c4_models()
+    L = 4096
+    x = S.make_frames(spec, L, seed=404)
+    sd = enc.state_dict()
+    ws = [sd["ann_layers.%dth_layer.weight" % k].double().clone().requires_grad_(True) for k in (1, 2, 3)]
+    bs = [sd["ann_layers.%dth_layer.bias" % k].double().clone().requires_grad_(True) for k in (1, 2, 3)]
+    dec64 = copy.deepcopy(dec).double()
+    target = oracle_preprocess(spec)(x)
+    recon = dec64(oracle_model(spec, ws, bs)(x))
+    loss64 = ((recon - target) ** 2).sum() / (L * target.shape[1])
+    loss64.backward()
+    ref = {}
+    for k in (1, 2, 3):
+        ref["enc.%d.w" % k], ref["enc.%d.b" % k] = ws[k - 1].grad, bs[k - 1].grad
+    for name, p in dec64.named_parameters():
+        ref["dec." + name] = p.grad
+    enc, dec = enc.cuda(), dec.cuda()
+    trainer = AutoencoderStep(enc, dec, lr=1e-3, global_frames=L)
+    loss = trainer.loss_and_grads(dev(x))
+    assert abs(float(loss) - float(loss64)) < 1e-5 * abs(float(loss64))
+    got = {}
+    for k in (1, 2, 3):
+        layer = getattr(enc.ann_layers, "%dth_layer" % k)
+        got["enc.%d.w" % k], got["enc.%d.b" % k] = layer.weight.grad, layer.bias.grad
+    for name, p in dec.named_parameters():
+        got["dec." + name] = p.grad
+    for name, r in ref.items():
+        err = float((got[name].cpu().double() - r).abs().max() / r.abs().max())
+        assert err < 2e-5, (name, err)
+    l0 = float(trainer.step(dev(x)))
+    trainer.lr = 0.05
+    for _ in range(3):
+        l1 = float(trainer.step(dev(x)))
+    assert l1 < l0
+
+
 def test_torchscript_roundtrip_in_fresh_process(tmp_path):
     spec = S.get_spec("C2")
     model, _ = S.build_model(spec)
