@@ -526,7 +526,7 @@ __device__ __forceinline__ long long vg_gtime() {
 // 16 elements of a chunk could not overlap, and the two epilogues took 8k + 11k of a tile's 42k cycles
 // (tests/cuda/ws_trace.cu).
 template <int TILES, int ACT>
-__global__ void __launch_bounds__(TILES * TC_F)
+__global__ void __launch_bounds__(TILES * TC_F, 1)
 fused_tc_value_grad_kernel(const __grid_constant__ DevPlan p, const __grid_constant__ TcVgLayout vl,
                            const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ y,
                            float* __restrict__ gx, long long L, int use_tma) {
