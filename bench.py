@@ -85,7 +85,8 @@ class ClockSampler(object):
             import pynvml
             pynvml.nvmlInit()
             self.nv = pynvml
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            from molann_b200.stream import nvml_handle
+            self.h = nvml_handle(pynvml, index)
             self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
             self._thread = threading.Thread(target=self._run, daemon=True)
             self._thread.start()
@@ -250,7 +251,7 @@ def run_reference(args, rank):
         "fwd_dx": {"value": vdx, "unit": UNIT},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -397,7 +398,7 @@ def run_training(args, rank, local_rank, world):
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": kind,
                                     "sample": "3 SGD steps on 65536 frames; %s; torch.set_num_threads(%d)"
                                               % (where, os.cpu_count() or 1)}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(spec, frames, n_gpus):
@@ -409,8 +410,31 @@ def workload_config(spec, frames, n_gpus):
             "parallelism": "frame-sharded x%d, no data-path collective" % n_gpus}
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """stdout carries exactly ONE JSON line: anything libraries print there (NCCL's version banner under
+    NCCL_DEBUG=VERSION, torchrun notices) is sent to stderr; emit() writes to the original descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
     args = parse_args()
+    quiet_stdout()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -419,14 +443,14 @@ def main():
             if rank == 0:
                 torch.set_num_threads(os.cpu_count() or 1)
                 rate, kind, where = c4_cpu_step_rate(1 << 16, max(1, args.steps), 1)
-                print(json.dumps({"impl": "reference", "metric": "frames_per_sec_train", "value": rate, "unit": UNIT,
+                emit({"impl": "reference", "metric": "frames_per_sec_train", "value": rate, "unit": UNIT,
                                   "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                                   "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                                   "data": "synthetic", "config": {"workload": C4_NOTE},
                                   "cpu_baseline": {"value": rate, "unit": UNIT, "cores": os.cpu_count() or 1,
                                                    "kind": kind, "sample": "SGD steps on 65536 frames; " + where},
                                   "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0,
-                                          "d2h_bytes_per_step": 0}}), flush=True)
+                                          "d2h_bytes_per_step": 0}})
             return
         run_reference(args, rank)
         return
@@ -435,6 +459,9 @@ def main():
     import torch.distributed as dist
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # host buffers of the end-to-end leg live on the NUMA node next to this rank's GPU
+        from molann_b200.stream import bind_to_gpu_numa_node
+        bind_to_gpu_numa_node(local_rank)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
 
@@ -590,7 +617,7 @@ def main():
                                 "sample": "best of 3: %d frames fwd (no_grad), %d frames fwd+dx (autograd); %s; "
                                           "torch.set_num_threads(%d)" % (ff, fd, where, cores),
                                 "fwd_dx_value": cd}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -10,6 +10,43 @@ from typing import Optional
 import torch
 
 
+def nvml_handle(pynvml, device_index: int):
+    """NVML handle of CUDA device ``device_index`` (by UUID: CUDA_VISIBLE_DEVICES may renumber the devices)."""
+    try:
+        uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+        if not uuid.startswith("GPU-"):
+            uuid = "GPU-" + uuid
+        return pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+    except Exception:
+        return pynvml.nvmlDeviceGetHandleByIndex(device_index)
+
+
+def bind_to_gpu_numa_node(device_index: int) -> int:
+    """Restrict the calling process to the CPUs NVML reports as closest to GPU ``device_index`` (same NUMA node /
+    PCIe root).  Pinned buffers allocated afterwards are first-touched on that node, so H2D / D2H copies of an
+    8-GPU box do not cross the inter-socket link.  Returns the number of CPUs kept (0: left unchanged)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = nvml_handle(pynvml, device_index)
+        words = (max(os.sched_getaffinity(0)) // 64) + 1
+        try:
+            ncpu = os.cpu_count() or 64
+            words = max(words, (ncpu + 63) // 64)
+        except Exception:
+            pass
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        ideal = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        keep = ideal & os.sched_getaffinity(0)
+        if keep:
+            os.sched_setaffinity(0, keep)
+            return len(keep)
+    except Exception:
+        pass
+    return 0
+
+
 class HostPipeline(object):
     """Double-buffered host->device->host pipeline around a ``molann_b200`` model.
 
