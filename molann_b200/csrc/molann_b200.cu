@@ -544,10 +544,22 @@ int run_tc_vg(const TcVgChoice& ch, const DevPlan& dp, const float* x, const flo
 // ---------------------------------------------------------------------------------------------
 constexpr long long kChunkFrames = 32768;
 
+// Frames per pass of the layered path: scratch stays O(chunk).  32768 frames for wide systems (C3: 11 KB of
+// activations per frame); narrow ones (C2 / C4: 1.2 KB) take up to 8x that within the same 256 MB, which cuts the
+// launches of a 2^20-frame training step from 482 to ~90.  MOLANN_B200_CHUNK overrides.
 long long chunk_frames(const MolannPlan* p, long long L) {
-  long long ch = env_int("MOLANN_B200_CHUNK", (int)kChunkFrames);
+  long long per_frame = p->d_feat;
+  int widest = p->d_feat;
+  for (int k = 1; k <= p->n_layers; ++k) {
+    per_frame += p->dims[k];
+    widest = p->dims[k] > widest ? p->dims[k] : widest;
+  }
+  per_frame = 4 * (per_frame + 2LL * widest);
+  long long ch = (256LL << 20) / (per_frame > 0 ? per_frame : 1) / kChunkFrames * kChunkFrames;
+  if (ch < kChunkFrames) ch = kChunkFrames;
+  if (ch > 8 * kChunkFrames) ch = 8 * kChunkFrames;
+  ch = env_int("MOLANN_B200_CHUNK", (int)ch);
   if (ch < 256) ch = 256;
-  (void)p;
   return L < ch ? L : ch;
 }
 
@@ -770,17 +782,31 @@ int launch_linear_backward_input(const float* gz, const float* W, const float* h
 }
 
 // gW[N, K] += gz[M, N]^T hin[M, K];  gb[N] += colsum(gz)
+// The contraction runs over the FRAMES, the output is tiny (64 x 64 for C2/C4), so the frame axis is what fills the
+// GPU: it is cut so that about two CTAs per SM exist (a fixed 2048-row cut left 16 CTAs for a 32768-frame chunk and
+// made this kernel 60 % of a C4 training step); partial results meet in L2 through fp32 atomics.
 int launch_linear_backward_params(const float* gz, const float* hin, float* gW, float* gb, long long M, int K, int N,
-                                  cudaStream_t st) {
-  const long long kchunk = 2048;
+                                  cudaStream_t st, int sm_count = 148) {
+  const long long tiles = (long long)((K + 63) / 64) * ((N + 63) / 64);
+  long long slabs = (2LL * sm_count + tiles - 1) / tiles;
+  if (slabs < 1) slabs = 1;
+  long long kchunk = (M + slabs - 1) / slabs;
+  kchunk = (kchunk + 15) / 16 * 16;
+  if (kchunk < 64) kchunk = 64;
+  if (kchunk > 2048) kchunk = 2048;
   dim3 grid((K + 63) / 64, (N + 63) / 64, (unsigned)((M + kchunk - 1) / kchunk));
   gemm_kernel<EPI_ATOMIC><<<grid, 256, 0, st>>>(gz, 1, N, hin, K, 1, gW, K, N, K, M, kchunk, nullptr, nullptr, 0, 0);
   int s = post_launch();
   if (s) return s;
   if (gb) {
-    const int rows_per_block = 4096;
-    dim3 g2((N + 31) / 32, (unsigned)((M + rows_per_block - 1) / rows_per_block), 1);
-    colsum_atomic_kernel<<<g2, 256, 0, st>>>(gz, (int)M, N, gb, rows_per_block);
+    const long long cols = (N + 31) / 32;
+    long long rslabs = (2LL * sm_count + cols - 1) / cols;
+    long long rows = (M + rslabs - 1) / rslabs;
+    rows = (rows + 7) / 8 * 8;
+    if (rows < 64) rows = 64;
+    if (rows > 4096) rows = 4096;
+    dim3 g2((unsigned)cols, (unsigned)((M + rows - 1) / rows), 1);
+    colsum_atomic_kernel<<<g2, 256, 0, st>>>(gz, (int)M, N, gb, (int)rows);
     s = post_launch();
   }
   return s;
@@ -852,7 +878,8 @@ int general_backward(const MolannPlan* p, const float* x, const float* gy, long 
     const float* gz = gy + c0 * kout;
     for (int k = nl - 1; k >= 0; --k) {
       if (gW && gW[k]) {
-        s = launch_linear_backward_params(gz, h[k], gW[k], gb ? gb[k] : nullptr, Lc, p->dims[k], p->dims[k + 1], st);
+        s = launch_linear_backward_params(gz, h[k], gW[k], gb ? gb[k] : nullptr, Lc, p->dims[k], p->dims[k + 1], st,
+                                          dev.sm_count);
         if (s) return s;
       }
       float* gprev = pp[k & 1];
