@@ -96,7 +96,9 @@ int molann_b200_forward(const MolannPlan* plan, const float* x, int64_t L, float
                         void* workspace, size_t workspace_bytes, void* stream);
 
 /* gx[L, n_inp, 3] = d<gy, y>/dx (overwritten, dense).  gW / gb: NULL, or arrays of n_layers device
- * pointers into which d<gy,y>/dW_k, /db_k are ACCUMULATED (+=; caller zeroes them). */
+ * pointers into which d<gy,y>/dW_k, /db_k are ACCUMULATED (+=; caller zeroes them).  gx may be NULL when
+ * parameter gradients are requested (training: the coordinates do not require a gradient) -- the first layer's
+ * input contraction and the whole preprocessing backward are then skipped. */
 int molann_b200_backward(const MolannPlan* plan, const float* x, const float* gy, int64_t L, float* gx,
                          float* const* gW, float* const* gb,
                          void* workspace, size_t workspace_bytes, void* stream);

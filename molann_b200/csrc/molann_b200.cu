@@ -882,12 +882,14 @@ int general_backward(const MolannPlan* p, const float* x, const float* gy, long 
                                           dev.sm_count);
         if (s) return s;
       }
+      if (k == 0 && gx == nullptr) break;       // training: nobody asked for the coordinate gradient
       float* gprev = pp[k & 1];
       s = launch_linear_backward_input(gz, p->W[k], k > 0 ? h[k] : nullptr, gprev, Lc, p->dims[k], p->dims[k + 1],
                                        p->act_id, st, pack, &dev);
       if (s) return s;
       gz = gprev;
     }
+    if (gx == nullptr) continue;
     s = launch_preprocess_backward(p, dp, xc, gz, gx + c0 * 3 * p->n_inp, Lc, dev, st);
     if (s) return s;
   }
@@ -978,14 +980,14 @@ int molann_b200_backward(const MolannPlan* plan, const float* x, const float* gy
   if (plan->n_layers < 1) return MOLANN_ERR_UNSUPPORTED;
   if (L < 0) return MOLANN_ERR_PLAN;
   if (L == 0) return MOLANN_OK;
-  if (!x || !gy || !gx) return MOLANN_ERR_NULL;
+  bool want_params = false;
+  if (gW)
+    for (int k = 0; k < plan->n_layers; ++k) want_params = want_params || (gW[k] != nullptr);
+  if (!x || !gy || (!gx && !want_params)) return MOLANN_ERR_NULL;
   if (misaligned4(x) || misaligned4(gy) || misaligned4(gx)) return MOLANN_ERR_ALIGNMENT;
   const DeviceInfo dev = device_info();
   if (!dev.ok) return MOLANN_ERR_CUDA;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  bool want_params = false;
-  if (gW)
-    for (int k = 0; k < plan->n_layers; ++k) want_params = want_params || (gW[k] != nullptr);
   if (!want_params) {
     const TcVgChoice vg = choose_tc_vg(plan, dev);
     if (vg.ok) return run_tc_vg(vg, to_dev(plan), x, gy, nullptr, gx, (long long)L, dev, st);

@@ -187,7 +187,8 @@ Tensor molann_fwd_impl(const Tensor& x, const Tensor& align_idx, const Tensor& r
 // returns {gx, gW1, gb1, gW2, gb2, ...}; parameter gradients are undefined tensors unless requested
 std::vector<Tensor> molann_bwd_impl(const Tensor& x, const Tensor& align_idx, const Tensor& ref_x,
                                     const Tensor& entries, int64_t d_feat, bool use_angle_value,
-                                    at::TensorList params, int64_t act, const Tensor& gy_in, bool want_params) {
+                                    at::TensorList params, int64_t act, const Tensor& gy_in, bool want_params,
+                                    bool want_x = true) {
   c10::cuda::CUDAGuard guard(x.device());
   PlanHolder h;
   fill_geometry(h, x, align_idx, ref_x);
@@ -196,7 +197,8 @@ std::vector<Tensor> molann_bwd_impl(const Tensor& x, const Tensor& align_idx, co
   const int64_t L = x.size(0);
   const int nl = h.plan.n_layers;
   Tensor gy = gy_in.contiguous();
-  Tensor gx = at::empty_like(x);
+  want_x = want_x || !want_params;
+  Tensor gx = want_x ? at::empty_like(x) : Tensor();
   std::vector<Tensor> out;
   out.push_back(gx);
   float* gW[MOLANN_MAX_LAYERS] = {nullptr};
@@ -217,7 +219,8 @@ std::vector<Tensor> molann_bwd_impl(const Tensor& x, const Tensor& align_idx, co
     ws = at::empty({static_cast<int64_t>(ws_bytes)}, x.options().dtype(at::kByte));
     wsp = ws.data_ptr();
   }
-  check_status(molann_b200_backward(&h.plan, x.data_ptr<float>(), gy.data_ptr<float>(), L, gx.data_ptr<float>(),
+  check_status(molann_b200_backward(&h.plan, x.data_ptr<float>(), gy.data_ptr<float>(), L,
+                                    want_x ? gx.data_ptr<float>() : nullptr,
                                     want_params ? gW : nullptr, want_params ? gb : nullptr, wsp, ws_bytes,
                                     cur_stream()),
                "backward");
@@ -319,9 +322,9 @@ struct MolannFn : public torch::autograd::Function<MolannFn> {
       for (int64_t i = 0; i < np; ++i) want_params = want_params || ctx->needs_input_grad(4 + i);
     auto g = molann_bwd_impl(saved[0], saved[1], saved[2], saved[3], ctx->saved_data["d_feat"].toInt(),
                              ctx->saved_data["use_angle_value"].toBool(), params, ctx->saved_data["act"].toInt(),
-                             grads[0], want_params);
+                             grads[0], want_params, ctx->needs_input_grad(0));
     variable_list out;
-    out.push_back(g[0]);                                         // x
+    out.push_back(g[0]);                                         // x (undefined when x needs no gradient)
     for (int i = 0; i < 5; ++i) out.push_back(Tensor());         // align_idx, ref_x, entries, d_feat, use_angle
     for (int64_t i = 0; i < np; ++i) out.push_back(want_params ? g[1 + i] : Tensor());
     out.push_back(Tensor());                                     // act
