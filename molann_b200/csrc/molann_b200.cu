@@ -16,6 +16,7 @@
 #include "fused_ws.cuh"
 #include "gemm_tc.cuh"
 #include "staged_block.cuh"
+#include "small_tile.cuh"
 #include "general.cuh"
 
 using namespace molann;
@@ -662,8 +663,42 @@ int block_grid(Kern kern, int smem, long long L, const DeviceInfo& dev, long lon
   if (*grid > L) *grid = L;
   return MOLANN_OK;
 }
+// Thread-per-frame tile kernels (small_tile.cuh) for frames small enough that 128 of them (+ the result tile) fit in
+// shared memory twice over (two CTAs per SM).  MOLANN_B200_TILE = 0 keeps the warp-per-frame kernels.
+struct TileChoice {
+  bool ok = false;
+  StLayout lay;
+};
+TileChoice choose_tile(const MolannPlan* p, bool backward, const DeviceInfo& dev) {
+  TileChoice ch;
+  if (env_int("MOLANN_B200_TILE", 1) == 0 || p->n_entries < 1) return ch;
+  StLayout& lay = ch.lay;
+  int off = 0;
+  lay.aidx_off = off; off += round_up(4 * p->n_align, 16);
+  lay.ref_off = off; off += round_up(12 * p->n_align, 16);
+  lay.ent_off = off; off += round_up(4 * MOLANN_ENTRY_INTS * p->n_entries, 128);
+  lay.xs_off = off; off += round_up(ST_F * 3 * p->n_inp * 4, 128);
+  lay.out_off = off; off += round_up(ST_F * (backward ? 3 * p->n_inp : p->d_feat) * 4, 128);
+  lay.gf_off = off;
+  if (backward) off += round_up(ST_F * p->d_feat * 4, 128);
+  lay.total = off;
+  if (lay.total > (dev.smem_per_sm / 2) - 1024) return ch;
+  ch.ok = true;
+  return ch;
+}
 int launch_preprocess_forward(const MolannPlan* p, const DevPlan& dp, const float* x, float* feat, long long L,
                               const DeviceInfo& dev, cudaStream_t st) {
+  const TileChoice tc = choose_tile(p, false, dev);
+  if (tc.ok) {
+    int s = check_cuda(cudaFuncSetAttribute(preprocess_forward_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            tc.lay.total));
+    if (s) return s;
+    long long grid = (L + ST_F - 1) / ST_F;
+    const long long cap = (long long)dev.sm_count * (dev.smem_per_sm / (tc.lay.total + 1024));
+    if (grid > cap) grid = cap;
+    preprocess_forward_tile_kernel<<<(unsigned)grid, ST_F, tc.lay.total, st>>>(dp, tc.lay, x, feat, L);
+    return post_launch();
+  }
   const BlockChoice bc = choose_block(p, false, dev);
   if (bc.ok) {
     long long grid = 1;
@@ -690,6 +725,17 @@ int launch_preprocess_forward(const MolannPlan* p, const DevPlan& dp, const floa
 }
 int launch_preprocess_backward(const MolannPlan* p, const DevPlan& dp, const float* x, const float* gfeat, float* gx,
                                long long L, const DeviceInfo& dev, cudaStream_t st) {
+  const TileChoice tc = choose_tile(p, true, dev);
+  if (tc.ok) {
+    int s = check_cuda(cudaFuncSetAttribute(preprocess_backward_tile_kernel,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, tc.lay.total));
+    if (s) return s;
+    long long grid = (L + ST_F - 1) / ST_F;
+    const long long cap = (long long)dev.sm_count * (dev.smem_per_sm / (tc.lay.total + 1024));
+    if (grid > cap) grid = cap;
+    preprocess_backward_tile_kernel<<<(unsigned)grid, ST_F, tc.lay.total, st>>>(dp, tc.lay, x, gfeat, gx, L);
+    return post_launch();
+  }
   const BlockChoice bc = choose_block(p, true, dev);
   if (bc.ok) {
     long long grid = 1;
