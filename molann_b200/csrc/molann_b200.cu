@@ -686,6 +686,29 @@ TileChoice choose_tile(const MolannPlan* p, bool backward, const DeviceInfo& dev
   ch.ok = true;
   return ch;
 }
+TileChoice choose_align_tile(const MolannPlan* p, bool backward, const DeviceInfo& dev) {
+  TileChoice ch;
+  if (env_int("MOLANN_B200_TILE", 1) == 0) return ch;
+  StLayout& lay = ch.lay;
+  int off = 0;
+  lay.aidx_off = off; off += round_up(4 * p->n_align, 16);
+  lay.ref_off = off; off += round_up(12 * p->n_align, 16);
+  lay.ent_off = off;
+  lay.xs_off = off; off += round_up(ST_F * 3 * p->n_inp * 4, 128);
+  lay.out_off = off;
+  if (backward) off += round_up(ST_F * 3 * p->n_inp * 4, 128);
+  lay.gf_off = off;
+  lay.total = off;
+  if (lay.total > (dev.smem_per_sm / 2) - 1024) return ch;
+  ch.ok = true;
+  return ch;
+}
+unsigned tile_grid(long long L, int smem, const DeviceInfo& dev) {
+  long long grid = (L + ST_F - 1) / ST_F;
+  const long long cap = (long long)dev.sm_count * (dev.smem_per_sm / (smem + 1024));
+  if (grid > cap) grid = cap;
+  return (unsigned)(grid < 1 ? 1 : grid);
+}
 int launch_preprocess_forward(const MolannPlan* p, const DevPlan& dp, const float* x, float* feat, long long L,
                               const DeviceInfo& dev, cudaStream_t st) {
   const TileChoice tc = choose_tile(p, false, dev);
@@ -1101,7 +1124,17 @@ int molann_b200_align_forward(const MolannPlan* plan, const float* x, int64_t L,
   if (misaligned4(x) || misaligned4(out)) return MOLANN_ERR_ALIGNMENT;
   const DeviceInfo dev = device_info();
   if (!dev.ok) return MOLANN_ERR_CUDA;
-  const DevPlan dp = to_dev(plan);
+  DevPlan dp = to_dev(plan);
+  dp.n_entries = 0;                              // only the geometry fields of the plan are meaningful here
+  const TileChoice tc = choose_align_tile(plan, false, dev);
+  if (tc.ok) {
+    s = check_cuda(cudaFuncSetAttribute(align_forward_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        tc.lay.total));
+    if (s) return s;
+    align_forward_tile_kernel<<<tile_grid(L, tc.lay.total, dev), ST_F, tc.lay.total,
+                                static_cast<cudaStream_t>(stream)>>>(dp, tc.lay, x, out, L);
+    return post_launch();
+  }
   align_forward_warp_kernel<<<warp_grid(L, dev), WARPS_PER_CTA * 32, 0, static_cast<cudaStream_t>(stream)>>>(dp, x,
                                                                                                              out, L);
   return post_launch();
@@ -1118,7 +1151,17 @@ int molann_b200_align_backward(const MolannPlan* plan, const float* x, const flo
   if (misaligned4(x) || misaligned4(gout) || misaligned4(gx)) return MOLANN_ERR_ALIGNMENT;
   const DeviceInfo dev = device_info();
   if (!dev.ok) return MOLANN_ERR_CUDA;
-  const DevPlan dp = to_dev(plan);
+  DevPlan dp = to_dev(plan);
+  dp.n_entries = 0;
+  const TileChoice tc = choose_align_tile(plan, true, dev);
+  if (tc.ok) {
+    s = check_cuda(cudaFuncSetAttribute(align_backward_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        tc.lay.total));
+    if (s) return s;
+    align_backward_tile_kernel<<<tile_grid(L, tc.lay.total, dev), ST_F, tc.lay.total,
+                                 static_cast<cudaStream_t>(stream)>>>(dp, tc.lay, x, gout, gx, L);
+    return post_launch();
+  }
   align_backward_warp_kernel<<<warp_grid(L, dev), WARPS_PER_CTA * 32, 0, static_cast<cudaStream_t>(stream)>>>(
       dp, x, gout, gx, L);
   return post_launch();

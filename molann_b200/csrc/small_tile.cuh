@@ -163,4 +163,94 @@ preprocess_backward_tile_kernel(const __grid_constant__ DevPlan p, const __grid_
   }
 }
 
+// out[L, n, 3] = (x - c) R   (stand-alone AlignmentLayer.forward, molann/ann.py:157-199), thread = frame
+__global__ void __launch_bounds__(ST_F)
+align_forward_tile_kernel(const __grid_constant__ DevPlan p, const __grid_constant__ StLayout lay,
+                          const float* __restrict__ x, float* __restrict__ out, long long L) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x;
+  const int n3 = 3 * p.n_inp;
+  const int* aidx = reinterpret_cast<const int*>(smem + lay.aidx_off);
+  const float* ref = reinterpret_cast<const float*>(smem + lay.ref_off);
+  float* xs = reinterpret_cast<float*>(smem + lay.xs_off);
+  st_stage_consts(p, lay, smem, tid);
+  const long long ntiles = (L + ST_F - 1) / ST_F;
+  for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const long long f0 = t * ST_F;
+    const int nf = (int)((L - f0) < ST_F ? (L - f0) : ST_F);
+    __syncthreads();
+    st_load_rows(x, f0, nf, n3, xs, tid);
+    __syncthreads();
+    {
+      float* xf = xs + (tid < nf ? tid : nf - 1) * n3;
+      Rigid rg;
+      kabsch<1>(xf, aidx, ref, p.n_align, 0, rg);
+      if (tid < nf)                                // in place: the row belongs to this thread
+        for (int j = 0; j < p.n_inp; ++j) {
+          float zx, zy, zz;
+          rigid_apply(rg, xf[3 * j], xf[3 * j + 1], xf[3 * j + 2], zx, zy, zz);
+          xf[3 * j] = zx; xf[3 * j + 1] = zy; xf[3 * j + 2] = zz;
+        }
+    }
+    __syncthreads();
+    st_store_rows(out, f0, nf, n3, xs, tid);
+  }
+}
+
+// gx = d<gout, align(x)>/dx, thread = frame (closed form)
+__global__ void __launch_bounds__(ST_F)
+align_backward_tile_kernel(const __grid_constant__ DevPlan p, const __grid_constant__ StLayout lay,
+                           const float* __restrict__ x, const float* __restrict__ gout, float* __restrict__ gx,
+                           long long L) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x;
+  const int n3 = 3 * p.n_inp;
+  const int* aidx = reinterpret_cast<const int*>(smem + lay.aidx_off);
+  const float* ref = reinterpret_cast<const float*>(smem + lay.ref_off);
+  float* xs = reinterpret_cast<float*>(smem + lay.xs_off);
+  float* gs = reinterpret_cast<float*>(smem + lay.out_off);
+  st_stage_consts(p, lay, smem, tid);
+  const long long ntiles = (L + ST_F - 1) / ST_F;
+  for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const long long f0 = t * ST_F;
+    const int nf = (int)((L - f0) < ST_F ? (L - f0) : ST_F);
+    __syncthreads();
+    st_load_rows(x, f0, nf, n3, xs, tid);
+    st_load_rows(gout, f0, nf, n3, gs, tid);
+    __syncthreads();
+    {
+      const int fr = tid < nf ? tid : nf - 1;
+      const float* xf = xs + fr * n3;
+      float* gf = gs + fr * n3;
+      Rigid rg;
+      kabsch<1>(xf, aidx, ref, p.n_align, 0, rg);
+      if (tid < nf) {
+        float M[9], sg[3];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) M[i] = 0.f;
+        sg[0] = sg[1] = sg[2] = 0.f;
+        for (int j = 0; j < p.n_inp; ++j) {
+          const float g0 = gf[3 * j], g1 = gf[3 * j + 1], g2 = gf[3 * j + 2];
+          const float dx = xf[3 * j] - rg.c[0], dy = xf[3 * j + 1] - rg.c[1], dz = xf[3 * j + 2] - rg.c[2];
+          M[0] = fmaf(dx, g0, M[0]); M[1] = fmaf(dx, g1, M[1]); M[2] = fmaf(dx, g2, M[2]);
+          M[3] = fmaf(dy, g0, M[3]); M[4] = fmaf(dy, g1, M[4]); M[5] = fmaf(dy, g2, M[5]);
+          M[6] = fmaf(dz, g0, M[6]); M[7] = fmaf(dz, g1, M[7]); M[8] = fmaf(dz, g2, M[8]);
+          float tx, ty, tz;
+          rot_transpose_apply(rg, g0, g1, g2, tx, ty, tz);
+          sg[0] += tx; sg[1] += ty; sg[2] += tz;
+          gf[3 * j] = tx; gf[3 * j + 1] = ty; gf[3 * j + 2] = tz;      // in place: G_j -> G_j R^T
+        }
+        float dH[9];
+        align_backward_dH(rg, M, dH);
+        const float inv_na = 1.0f / (float)p.n_align;
+        StRowAcc acc{gf};
+        for (int k = 0; k < p.n_align; ++k)
+          acc(aidx[k], align_atom_grad(dH, sg, inv_na, ref[3 * k], ref[3 * k + 1], ref[3 * k + 2]));
+      }
+    }
+    __syncthreads();
+    st_store_rows(gx, f0, nf, n3, gs, tid);
+  }
+}
+
 }  // namespace molann

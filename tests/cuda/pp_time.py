@@ -16,5 +16,10 @@ for tile in ("1", "0"):
     os.environ["MOLANN_B200_TILE"] = tile
     with torch.no_grad(): tf = t(lambda: pp(x))
     f = pp(xg); tb = t(lambda: torch.autograd.grad(f, xg, g, retain_graph=True))
+    al = pp.align_layer
+    with torch.no_grad(): ta = t(lambda: al(x))
+    z = al(xg); go = torch.randn_like(z); tab = t(lambda: torch.autograd.grad(z, xg, go, retain_graph=True))
+    print("TILE=%s AlignmentLayer   C2 2^20 frames: forward %.3f ms (%.2f G frames/s), backward %.3f ms (%.2f G frames/s)"
+          % (tile, ta, L / ta / 1e6, tab, L / tab / 1e6))
     print("TILE=%s PreprocessingANN C2 2^20 frames: forward %.3f ms (%.2f G frames/s), backward %.3f ms (%.2f G frames/s)"
           % (tile, tf, L / tf / 1e6, tb, L / tb / 1e6))

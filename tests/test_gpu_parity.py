@@ -173,8 +173,11 @@ def test_value_and_grad_single_pass(name):
     assert torch.equal(ys, y) and torch.equal(gxs, gx)
 
 
-def test_alignment_layer_standalone_and_composition():
-    """AlignmentLayer alone (fwd + autograd) and the unfused composition feature(align(x))."""
+@pytest.mark.parametrize("tile", ["1", "0"])
+def test_alignment_layer_standalone_and_composition(tile, monkeypatch):
+    """AlignmentLayer alone (fwd + autograd) and the unfused composition feature(align(x)); thread-per-frame tile
+    kernels (1, the default for small frames) and warp-per-frame kernels (0)."""
+    monkeypatch.setenv("MOLANN_B200_TILE", tile)
     spec = S.get_spec("C2")
     g = golden("config_C2")
     model, _ = S.build_model(spec)
@@ -192,6 +195,19 @@ def test_alignment_layer_standalone_and_composition():
     assert_parity(gz.cpu(), gz64, None, TOL, "align gx")
     f2 = pp.feature_layer(pp.align_layer(dev(g["x"])))
     assert_parity(f2.cpu(), g["feat64"], g["feat32"], TOL, "composed feat")
+    # stand-alone preprocessing on ragged batches (partial last tile, 4-byte-offset base pointer)
+    x_all = torch.from_numpy(g["x"])
+    flat = torch.empty(x_all.numel() + 1, device="cuda")
+    for L, shift in ((1, 0), (129, 1), (x_all.shape[0], 0)):
+        xd = flat[shift:shift + L * x_all[0].numel()].view(L, *x_all.shape[1:])
+        xd.copy_(x_all[:L])
+        xd = xd.detach().requires_grad_(True)
+        f = pp(xd)
+        assert_parity(f.detach().cpu(), g["feat64"][:L], g["feat32"][:L], TOL, "feat L=%d" % L)
+        (gxf,) = torch.autograd.grad(f, xd, dev(g["cotf"][:L]))
+        assert_parity(gxf.cpu(), g["gxf64"][:L], g["gxf32"][:L], TOL, "gxf L=%d" % L)
+        zz = pp.align_layer(xd)
+        assert_parity(zz.detach().cpu(), z64.detach()[:L], None, TOL, "align z L=%d" % L)
 
 
 @pytest.mark.parametrize("L", [1, 2, 3, 4, 5, 63, 64, 65, 127, 128, 129, 255, 256, 257, 385, 1000])
