@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument("--frames", type=int, default=0, help="frames per GPU per step (default: workload's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-layers", action="store_true", help="skip the stand-alone AlignmentLayer / PreprocessingANN rates")
     return ap.parse_args()
 
 
@@ -537,6 +538,39 @@ def main():
     clocks = sampler.summary()
     sampler.close()
 
+    # ---- the stand-alone layers of the same model: AlignmentLayer, PreprocessingANN ----
+    layers = None
+    pp = model.get_preprocessing_layer()
+    if not args.no_layers and getattr(pp, "align_layer", None) is not None and hasattr(pp.align_layer, "ref_x"):
+        n3b, db = 12 * spec.n_inp, 4 * spec.feature_dim()
+        gfe = torch.zeros(frames, spec.feature_dim(), device="cuda")
+        gfe[:, 0] = 1.0
+
+        def rate(step, nbytes):
+            ms_l, _ = timed(step, K, W, False)
+            v = world * frames * K / (ms_l * 1e-3)
+            return {"value": v, "unit": UNIT, "ms_per_step": ms_l / K, "bytes_per_frame": nbytes,
+                    "frac_of_hbm_peak": v / world * nbytes / 1e9 / peaks()[0]}
+
+        def al_f():
+            with torch.no_grad():
+                return pp.align_layer(x)
+
+        def pp_f():
+            with torch.no_grad():
+                return pp(x)
+
+        za = pp.align_layer(xg)
+        fa = pp(xg)
+        layers = {
+            "AlignmentLayer.forward": rate(al_f, 2 * n3b),
+            "AlignmentLayer.backward": rate(lambda: torch.autograd.grad(za, xg, x, retain_graph=True), 3 * n3b),
+            "PreprocessingANN.forward": rate(pp_f, n3b + db),
+            "PreprocessingANN.backward": rate(lambda: torch.autograd.grad(fa, xg, gfe, retain_graph=True),
+                                              2 * n3b + db),
+        }
+        del za, fa, gfe
+
     # ---- end to end through the public API with host buffers ----
     e2e = e2e_dx = None
     if not args.no_e2e:
@@ -610,6 +644,8 @@ def main():
                                     "api": "y = model(x); torch.autograd.grad(y, x, cotangent)"}},
         "e2e": e2e,
     }
+    if layers is not None:
+        line["layers"] = layers
     if world == 1 and not args.no_cpu_baseline:
         ff, fd = cpu_sample_sizes(spec)
         cf, cd, cores, kind, where = time_cpu(spec, ff, fd)
