@@ -128,7 +128,7 @@ def spec_c1() -> SystemSpec:
         name="C1", positions=ala2_positions(), input_ix=list(range(22)), align_ix=None,
         features=[("b56", "bond", [4, 5]), ("d1234", "dihedral", [0, 1, 2, 3])],
         use_angle_value=True, layer_dims=[2, 5, 3], noise=0.1, trans_sigma=0.0, rotate=False,
-        seed=101, default_frames=4096,
+        seed=101, default_frames=1 << 20,
         note="alanine dipeptide, bond+dihedral FeatureLayer -> MLP [2,5,3], no alignment")
 
 
@@ -156,11 +156,11 @@ def _chain_spec(name, n, chain_seed, seed, default_frames, hidden):
 
 
 def spec_c3() -> SystemSpec:
-    return _chain_spec("C3", 2000, 2000, 303, 1 << 18, [256, 128, 2])
+    return _chain_spec("C3", 2000, 2000, 303, 1 << 15, [256, 128, 2])
 
 
 def spec_c5() -> SystemSpec:
-    return _chain_spec("C5", 5000, 5000, 505, 1 << 17, [256, 128, 2])
+    return _chain_spec("C5", 5000, 5000, 505, 1 << 14, [256, 128, 2])
 
 
 def spec_small_chain(n=200, seed=77) -> SystemSpec:
