@@ -392,6 +392,81 @@ gemm_kernel(const float* __restrict__ A, long long sam, long long sak, const flo
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Narrow layers (the model's last Linear: 128 -> 2 for every BASELINE config).  The 64 x 64 tile kernel spends a
+// whole tile on 2 output columns (33 us per 32768 x 128 -> 2, 22 us for the matching backward); these two stream the
+// wide operand once at full width instead.
+// ---------------------------------------------------------------------------------------------
+constexpr int NARROW_MAX = 8;
+
+// out[m, o] = act(b[o] + sum_k in[m, k] W[o, k]),  N <= NARROW_MAX: one warp per row, lanes stride k
+__global__ void __launch_bounds__(256)
+narrow_forward_kernel(const float* __restrict__ in, const float* __restrict__ W, const float* __restrict__ b,
+                      float* __restrict__ out, long long M, int K, int N, int act, int apply_act) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * 8;
+  const bool vec = ((K & 3) == 0) && ((reinterpret_cast<uintptr_t>(in) & 15u) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(W) & 15u) == 0);
+  for (long long m = warp0; m < M; m += nwarps) {
+    const float* row = in + m * K;
+    float acc[NARROW_MAX];
+#pragma unroll
+    for (int o = 0; o < NARROW_MAX; ++o) acc[o] = 0.f;
+    if (vec) {
+      for (int k = 4 * lane; k < K; k += 128) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(row + k));
+#pragma unroll
+        for (int o = 0; o < NARROW_MAX; ++o) {
+          if (o < N) {
+            const float4 w = __ldg(reinterpret_cast<const float4*>(W + (long long)o * K + k));
+            acc[o] = fmaf(v.x, w.x, fmaf(v.y, w.y, fmaf(v.z, w.z, fmaf(v.w, w.w, acc[o]))));
+          }
+        }
+      }
+    } else {
+      for (int k = lane; k < K; k += 32) {
+        const float v = __ldg(row + k);
+#pragma unroll
+        for (int o = 0; o < NARROW_MAX; ++o)
+          if (o < N) acc[o] = fmaf(v, __ldg(W + (long long)o * K + k), acc[o]);
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < NARROW_MAX; ++o)
+      if (o < N) acc[o] = gsum<32>(acc[o]);
+    if (lane == 0) {
+#pragma unroll
+      for (int o = 0; o < NARROW_MAX; ++o) {
+        if (o < N) {
+          float v = acc[o] + __ldg(b + o);
+          if (apply_act) v = act_forward(v, act);
+          out[m * N + o] = v;
+        }
+      }
+    }
+  }
+}
+
+// gprev[m, k] = (sum_o gz[m, o] W[o, k]) * act'(hprev[m, k]),  N <= NARROW_MAX: one thread per (m, k)
+__global__ void __launch_bounds__(256)
+narrow_backward_input_kernel(const float* __restrict__ gz, const float* __restrict__ W,
+                             const float* __restrict__ hprev, float* __restrict__ gprev, long long M, int K, int N,
+                             int act) {
+  const long long total = M * K;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long m = i / K;
+    const int k = (int)(i - m * K);
+    float a = 0.f;
+#pragma unroll
+    for (int o = 0; o < NARROW_MAX; ++o)
+      if (o < N) a = fmaf(__ldg(gz + m * N + o), __ldg(W + (long long)o * K + k), a);
+    if (hprev != nullptr) a *= act_grad_from_output(__ldg(hprev + i), act);
+    gprev[i] = a;
+  }
+}
+
 // gb[n] += sum_m gz[m, n]
 __global__ void __launch_bounds__(256)
 colsum_atomic_kernel(const float* __restrict__ gz, int M, int N, float* __restrict__ gb, int rows_per_block) {

@@ -830,6 +830,13 @@ int launch_linear_forward(const float* in, const float* W, const float* b, float
   if (dev != nullptr && use_gemm_tc(M, K, N, pack))
     return launch_gemm_tc<GT_EPI_BIAS_ACT>(in, M, K, W, (long long)K, 1, N, out, b, nullptr, act, apply_act, pack, *dev,
                                            st);
+  if (N <= NARROW_MAX && env_int("MOLANN_B200_NARROW", 1) != 0) {
+    long long blocks = (M + 7) / 8;
+    const long long cap = (long long)(dev ? dev->sm_count : 148) * 8;
+    if (blocks > cap) blocks = cap;
+    narrow_forward_kernel<<<(unsigned)(blocks < 1 ? 1 : blocks), 256, 0, st>>>(in, W, b, out, M, K, N, act, apply_act);
+    return post_launch();
+  }
   dim3 grid((N + 63) / 64, (unsigned)((M + 63) / 64), 1);
   gemm_kernel<EPI_BIAS_ACT><<<grid, 256, 0, st>>>(in, K, 1, W, 1, K, out, N, (int)M, N, K, K, b, nullptr, act,
                                                   apply_act);
@@ -844,6 +851,14 @@ int launch_linear_backward_input(const float* gz, const float* W, const float* h
   if (dev != nullptr && use_gemm_tc(M, N, K, pack))
     return launch_gemm_tc<GT_EPI_DACT>(gz, M, N, W, 1, (long long)K, K, gprev, nullptr, hprev, act, hprev != nullptr, pack,
                                        *dev, st);
+  if (N <= NARROW_MAX && env_int("MOLANN_B200_NARROW", 1) != 0) {
+    long long blocks = (M * K + 255) / 256;
+    const long long cap = (long long)(dev ? dev->sm_count : 148) * 16;
+    if (blocks > cap) blocks = cap;
+    narrow_backward_input_kernel<<<(unsigned)(blocks < 1 ? 1 : blocks), 256, 0, st>>>(gz, W, hprev, gprev, M, K, N,
+                                                                                     act);
+    return post_launch();
+  }
   dim3 grid((K + 63) / 64, (unsigned)((M + 63) / 64), 1);
   gemm_kernel<EPI_DACT><<<grid, 256, 0, st>>>(gz, N, 1, W, K, 1, gprev, K, (int)M, K, N, N, nullptr, hprev, act,
                                               hprev != nullptr);
