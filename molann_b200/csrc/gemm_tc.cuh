@@ -318,13 +318,16 @@ gemm_tc_kernel(const float* __restrict__ A, long long lda, long long M, int K, c
         mbar_wait_hint(&d_full[db], (uint32_t)((sg >> 1) & 1));
         tc_fence_after_sync();
 #pragma unroll
-        for (int c = 0; c < 64; c += 16) {      // 16 columns at a time: 64 running sums already fill the registers
-          if (64 * e + c < np) {
-            float u[16];
-            tmem_ld16(lane_base + (uint32_t)db * GT_NMAX + 64 * e + c, u);
+        for (int c = 0; c < 64; c += 8) {       // 8 columns at a time: 64 running sums already fill the registers
+          if (64 * e + c < np) {                // (16 at a time spilled the sums to local memory: profiles/r1_h)
+            uint32_t u[8];
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
+                         : "r"(lane_base + (uint32_t)db * GT_NMAX + 64 * e + c)
+                         : "memory");
             tmem_wait_ld();
 #pragma unroll
-            for (int i = 0; i < 16; ++i) acc[c + i] += u[i];
+            for (int i = 0; i < 8; ++i) acc[c + i] += __uint_as_float(u[i]);
           }
         }
         tc_fence_before_sync();
