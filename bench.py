@@ -328,6 +328,7 @@ def run_training(args, rank, local_rank, world):
     for _ in range(W):
         trainer.step(x)
     barrier()
+    # eager: every kernel launched from the host
     l0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.start()
@@ -337,8 +338,27 @@ def run_training(args, rank, local_rank, world):
     e1.record()
     barrier()
     sampler.pause()
-    ms = max_over_ranks(e0.elapsed_time(e1))
+    ms_eager = max_over_ranks(e0.elapsed_time(e1))
     launches = _lib.launch_count() - l0
+    # the same step captured once as a CUDA graph (forward, backward, allreduce, SGD) and replayed
+    graphed = bool(int(os.environ.get("MOLANN_BENCH_GRAPH", "1"))) and trainer.capture(x)
+    if world > 1:
+        flag = torch.tensor([1.0 if graphed else 0.0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        graphed = bool(flag.item() > 0.5)
+    ms = ms_eager
+    if graphed:
+        for _ in range(W):
+            trainer.replay()
+        barrier()
+        sampler.start()
+        e0.record()
+        for _ in range(K):
+            loss = trainer.replay()
+        e1.record()
+        barrier()
+        sampler.pause()
+        ms = max_over_ranks(e0.elapsed_time(e1))
     # the collective alone (flat gradient buffer of this model), same stream, device-timed
     nparam = sum(p.numel() for p in trainer.params)
     flat = torch.zeros(nparam + 1, device="cuda")
@@ -357,14 +377,15 @@ def run_training(args, rank, local_rank, world):
     # end to end: this rank's shard arrives from pinned host memory every step, the loss is read back
     xh = x.cpu().pin_memory()
     ke = max(3, min(K, 10))
+    run = trainer.replay if graphed else (lambda: trainer.step(x))
     for _ in range(2):
         x.copy_(xh, non_blocking=True)
-        float(trainer.step(x))
+        float(run())
     barrier()
     t0 = time.perf_counter()
     for _ in range(ke):
         x.copy_(xh, non_blocking=True)
-        last = float(trainer.step(x))
+        last = float(run())
     torch.cuda.synchronize()
     ms_e = max_over_ranks(1e3 * (time.perf_counter() - t0))
     clocks = sampler.summary()
@@ -389,6 +410,10 @@ def run_training(args, rank, local_rank, world):
                      "note": "per GPU, algorithmic 12*n_inp bytes per frame; the step is compute/launch bound "
                              "(74 kFLOP per frame incl. weight gradients), see DESIGN.md"},
         "gpu_launches": int(launches), "allreduce_ms": ar_ms, "final_loss": float(loss), "clocks": clocks,
+        "cuda_graph": {"used": graphed, "eager_ms_per_step": ms_eager / K,
+                       "note": "value is the graph replay when used (one launch per step replays gpu_launches / steps "
+                               "of our kernels + the decoder's); gpu_launches counts the eager leg",
+                       "capture_error": getattr(trainer, "_capture_error", None)},
         "e2e": {"value": n_global * ke / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(xh.numel() * 4),
                 "d2h_bytes_per_step": 4, "steps": ke, "ms_per_step": ms_e / ke, "last_loss": last,
                 "api": "x.copy_(pinned shard); molann_b200.train.AutoencoderStep.step(x); float(loss)"},
