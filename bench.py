@@ -601,7 +601,7 @@ def main():
     if not args.no_e2e:
         xh = x.cpu().pin_memory()
         yh = torch.empty(frames, spec.out_dim()).pin_memory()
-        pipe = HostPipeline(model, spec.n_inp, spec.out_dim(), chunk_frames=max(1 << 16, frames // 8))
+        pipe = HostPipeline(model, spec.n_inp, spec.out_dim(), chunk_frames=int(os.environ.get("MOLANN_BENCH_E2E_CHUNK", max(1 << 12, frames // 8))))
         ke = max(3, min(K, 10))
 
         def e2e_step():
