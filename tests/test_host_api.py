@@ -218,3 +218,44 @@ def test_atomgroup_protocol():
     assert ag.positions.dtype == np.float32 and ag.positions[0].tolist() == [9, 10, 11]
     with pytest.raises(IndexError):
         AtomGroup([7], np.zeros((5, 3)))
+
+
+def test_numa_binding_helper_is_harmless_without_a_gpu():
+    """bench.py binds each rank to the CPUs next to its GPU before it pins host buffers; on a box without NVML /
+    GPUs the helper must change nothing and report 0."""
+    import os
+    from molann_b200.stream import bind_to_gpu_numa_node
+    before = os.sched_getaffinity(0)
+    kept = bind_to_gpu_numa_node(0)
+    assert kept == 0 or kept == len(os.sched_getaffinity(0))
+    if kept == 0:
+        assert os.sched_getaffinity(0) == before
+
+
+def test_autoencoder_step_surface():
+    """Host logic of the C4 trainer on plain CPU modules: loss normalised by the GLOBAL batch, SGD update applied."""
+    import torch
+    from molann_b200.train import AutoencoderStep
+
+    class Enc(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.lin = torch.nn.Linear(6, 2)
+
+        def get_preprocessing_layer(self):
+            return lambda x: x.reshape(x.shape[0], -1)
+
+        def forward(self, x):
+            return self.lin(x.reshape(x.shape[0], -1))
+
+    torch.manual_seed(0)
+    enc, dec = Enc().double(), torch.nn.Linear(2, 6).double()
+    x = torch.randn(32, 2, 3, dtype=torch.float64)
+    tr = AutoencoderStep(enc, dec, lr=0.1, global_frames=64)
+    w0 = dec.weight.detach().clone()
+    loss = tr.loss_and_grads(x)
+    want = ((dec(enc(x)) - x.reshape(32, -1)) ** 2).sum() / (64 * 6)
+    assert abs(float(loss) - float(want)) < 1e-12
+    g = dec.weight.grad.clone()
+    tr.step(x)
+    assert torch.allclose(dec.weight.detach(), w0 - 0.1 * g, atol=1e-12)
