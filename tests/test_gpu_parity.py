@@ -416,6 +416,54 @@ def test_full_size_properties_c2():
     assert_parity(g1[idx.cuda()].cpu(), gx64, None, 2e-5, "full-size gx sample")
 
 
+@pytest.mark.parametrize("name", ["C3", "C5"])
+def test_bench_size_properties_big_systems(name):
+    """BASELINE configs[2] / [4] at the bench's batch size (32768 x 2000 atoms / 16384 x 5000 atoms), through
+    size-independent properties: frames independent (slices equal to rounding), invariance of the aligned model under a
+    rigid motion of the input, the coordinate gradient rotating WITH the frame, linear in the cotangent, summing to
+    zero over atoms (translation invariance), zero on unreferenced atoms; plus a 48-frame sample against the fp64
+    oracle."""
+    spec = S.get_spec(name)
+    L = spec.default_frames
+    model, _ = S.build_model(spec)
+    model = model.cuda()
+    x = S.make_frames(spec, L, device="cuda", seed=9)
+    cot = torch.randn(L, 2, device="cuda", generator=torch.Generator(device="cuda").manual_seed(4))
+    y, g1 = model.value_and_grad(x, cot)
+    assert torch.isfinite(y).all() and torch.isfinite(g1).all()
+    # frames are independent; on the layered path a row's K-summation order follows the CTA that owns its tile (the
+    # GEMM rotates the chunk order per CTA), so a slice agrees to rounding, not bitwise like the fused kernels
+    ys, gs = model.value_and_grad(x[1000:1000 + 333].contiguous(), cot[1000:1000 + 333].contiguous())
+    assert float((ys - y[1000:1333]).abs().max()) <= 2e-6 * max(1.0, float(y.abs().max()))
+    assert float((gs - g1[1000:1333]).abs().max()) <= 1e-5 * float(g1.abs().max())
+    Ls = 2048
+    Rm = S.random_rotations(Ls, torch.Generator(device="cuda").manual_seed(7), "cuda")
+    x2 = (torch.bmm(x[:Ls], Rm) + 5.0).contiguous()
+    y2, g2 = model.value_and_grad(x2, cot[:Ls].contiguous())
+    scale_y = float(y[:Ls].abs().max())
+    assert float((y2 - y[:Ls]).abs().max()) < 3e-4 * max(1.0, scale_y)
+    g1r = torch.bmm(g1[:Ls], Rm)                                   # d/dx of an invariant function rotates with x
+    cov = (g2 - g1r).abs().amax(dim=(1, 2)) / float(g1[:Ls].abs().max())
+    assert float(cov.median()) < 5e-5 and float(cov.max()) < 3e-3, (float(cov.median()), float(cov.max()))
+    _, g3 = model.value_and_grad(x[:Ls].contiguous(), (2.0 * cot[:Ls]).contiguous())
+    assert float((g3 - 2.0 * g1[:Ls]).abs().max()) <= 1e-6 * float(g1[:Ls].abs().max())
+    assert float(g1.sum(dim=1).abs().max()) < 2e-3 * float(g1.abs().max())
+    used = set(spec.align_ix)
+    for _, _, ix in spec.features:
+        used.update(ix)
+    unused = torch.tensor(sorted(set(range(spec.n_inp)) - used), device="cuda")
+    assert float(g1[:, unused].abs().max()) == 0.0
+    sd = model.state_dict()
+    ws = [sd["ann_layers.%dth_layer.weight" % k].cpu() for k in (1, 2, 3)]
+    bs = [sd["ann_layers.%dth_layer.bias" % k].cpu() for k in (1, 2, 3)]
+    idx = torch.randint(0, L, (48,), generator=torch.Generator().manual_seed(0))
+    xs, cs = x[idx.cuda()].cpu(), cot[idx.cuda()].cpu()
+    y64, gx64 = oracle_value_and_grad(oracle_model(spec, ws, bs), xs, cs)
+    y32, gx32 = oracle_value_and_grad(oracle_model(spec, ws, bs, torch.float32), xs, cs, torch.float32)
+    assert_parity(y[idx.cuda()].cpu(), y64, y32, TOL, name + " bench-size y sample")
+    assert_parity(g1[idx.cuda()].cpu(), gx64, gx32, 2e-5, name + " bench-size gx sample")
+
+
 @pytest.mark.parametrize("kernels", ["tensor_core_staged", "tensor_core_warp_staged", "ffma_gather"])
 def test_c3_full_width_general_path(kernels, monkeypatch):
     """n = 2000 atoms, d = 800 -> [800,256,128,2]: warp-per-frame geometry + layered GEMMs.
