@@ -434,6 +434,13 @@ __device__ __forceinline__ void feature_forward(const Entry& e, const float* __r
   }
 }
 
+// Four atoms of one entry at once; accumulators that can do better than four separate calls (vector reductions
+// for four consecutive atoms, staged_block.cuh) overload this.
+template <class Acc>
+__device__ __forceinline__ void acc_quad(Acc& acc, int a0, int a1, int a2, int a3, V3 g0, V3 g1, V3 g2, V3 g3) {
+  acc(a0, g0); acc(a1, g1); acc(a2, g2); acc(a3, g3);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Feature backward for one entry.  `gin(col)` reads the cotangent of a feature column,
 // `acc(atom, V3)` accumulates into the frame's coordinate gradient.  For aligned position entries the
@@ -492,10 +499,7 @@ __device__ __forceinline__ void feature_backward(const Entry& e, const float* __
     gr23 = add(gr23, cross(gn1, r12));
     gr23 = add(gr23, cross(r34, gn2));
     gr34 = add(gr34, cross(gn2, r23));
-    acc(e.a0, scale(gr12, -1.f));
-    acc(e.a1, sub(gr12, gr23));
-    acc(e.a2, sub(gr23, gr34));
-    acc(e.a3, gr34);
+    acc_quad(acc, e.a0, e.a1, e.a2, e.a3, scale(gr12, -1.f), sub(gr12, gr23), sub(gr23, gr34), gr34);
   } else if (e.type == FEAT_BOND) {
     const V3 r = sub(ld3(xf, e.a1), ld3(xf, e.a0));
     const float g = gin(e.off) / sqrtf(dot(r, r));
