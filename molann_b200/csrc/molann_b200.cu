@@ -637,6 +637,11 @@ BlockChoice choose_block(const MolannPlan* p, bool backward, const DeviceInfo& d
   lay.aidx_off = off; off += round_up(4 * p->n_align, 16);
   lay.ref_off = off; off += round_up(12 * p->n_align, 16);
   lay.ent_off = off; off += round_up(4 * MOLANN_ENTRY_INTS * p->n_entries, 128);
+  lay.zero_off = -1;
+  if (backward && env_int("MOLANN_B200_SB_BULKZERO", 1) != 0) {
+    lay.zero_off = off;
+    off += SB_ZERO_BYTES;
+  }
   lay.ring_off = off;
   const int slot = lay.buf_bytes + lay.fbuf_bytes;
   int stages = env_int("MOLANN_B200_SB_STAGES", 2);

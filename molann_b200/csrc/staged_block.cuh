@@ -54,8 +54,11 @@ struct SbSmem {
 };
 static_assert(sizeof(SbSmem) <= SB_HEAD, "header too small");
 
+constexpr int SB_ZERO_BYTES = 4096;                // block of zeros the backward's row fill is bulk-stored from
+
 struct SbLayout {                                  // byte offsets into dynamic shared memory (host-computed)
   int aidx_off, ref_off, ent_off;                  // plan constants
+  int zero_off;                                    // backward: SB_ZERO_BYTES of zeros (-1: fill with plain stores)
   int ring_off;                                    // stages x [x row | cotangent row (backward)]
   int buf_bytes, fbuf_bytes, stages, total;
 };
@@ -379,6 +382,11 @@ preprocess_backward_block_kernel(const __grid_constant__ DevPlan p, const __grid
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n3 = 3 * p.n_inp;
   const bool aligned = p.n_align > 0;
+  if (lay.zero_off >= 0) {
+    for (int i = tid; i < SB_ZERO_BYTES / 16; i += SB_THREADS)
+      reinterpret_cast<uint4*>(smem + lay.zero_off)[i] = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async_smem();
+  }
   sb_stage_consts(p, lay, smem, s, tid);
   const int n_lead = s.n_lead;
   const long long stride = gridDim.x;
@@ -441,9 +449,26 @@ preprocess_backward_block_kernel(const __grid_constant__ DevPlan p, const __grid
       const int head = head0 < n3 ? head0 : n3;
       const int nv = (n3 - head) >> 2;
       if (et < head) dstg[et] = 0.f;
-      float4* d4 = reinterpret_cast<float4*>(dstg + head);
-      for (int i = et; i < nv; i += SB_E_THREADS) d4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int i = head + 4 * nv + et; i < n3; i += SB_E_THREADS) dstg[i] = 0.f;
+      if (lay.zero_off >= 0) {
+        // the aligned middle of the row leaves as a few bulk stores of a block of zeros issued by ONE thread: 224
+        // threads x 6 STG.128 per frame were competing with the REDs for the LSU
+        if (tid == 32) {
+          const unsigned char* zsrc = smem + lay.zero_off;
+          unsigned char* d = reinterpret_cast<unsigned char*>(dstg + head);
+          long long left = 16LL * nv;
+          while (left > 0) {
+            const uint32_t nb = left < SB_ZERO_BYTES ? (uint32_t)left : (uint32_t)SB_ZERO_BYTES;
+            bulk_s2g(d, zsrc, nb);
+            d += nb;
+            left -= nb;
+          }
+          bulk_commit();
+        }
+      } else {
+        float4* d4 = reinterpret_cast<float4*>(dstg + head);
+        for (int i = et; i < nv; i += SB_E_THREADS) d4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
     SB_EVT((int)it, 1);
     const float* xn = nullptr;
@@ -451,6 +476,7 @@ preprocess_backward_block_kernel(const __grid_constant__ DevPlan p, const __grid
       xn = land(it + 1);
       if (aligned) sb_moments_partial(xn, aidx, ref, p.n_align, et, lane, ewarp, s.red[k ^ 1]);
     }
+    if (lay.zero_off >= 0 && tid == 32) bulk_wait0();             // the zeros have landed (not just been read)
     sb_e_sync();                                   // zeros before REDs; moment partials complete
     if (aligned && it + 1 < nframes && tid == 32) mbar_arrive(&s.mom_full[k ^ 1]);
     SB_EVT((int)it, 2);
