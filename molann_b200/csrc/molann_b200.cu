@@ -933,8 +933,11 @@ int general_forward(const MolannPlan* p, const float* x, long long L, float* y, 
   return MOLANN_OK;
 }
 
+// y_out != nullptr: also write the model outputs (value_and_grad: the forward the backward recomputes anyway is the
+// forward the caller wanted -- running molann_b200_forward first cost a second pass over x and both wide GEMMs).
 int general_backward(const MolannPlan* p, const float* x, const float* gy, long long L, float* gx, float* const* gW,
-                     float* const* gb, void* ws, size_t ws_bytes, const DeviceInfo& dev, cudaStream_t st) {
+                     float* const* gb, void* ws, size_t ws_bytes, const DeviceInfo& dev, cudaStream_t st,
+                     float* y_out = nullptr) {
   if (!ws || ws_bytes < general_ws_bytes(p, L, true)) return MOLANN_ERR_WORKSPACE;
   const DevPlan dp = to_dev(p);
   const long long ch = chunk_frames(p, L);
@@ -962,6 +965,11 @@ int general_backward(const MolannPlan* p, const float* x, const float* gy, long 
     for (int k = 0; k < nl - 1; ++k) {
       s = launch_linear_forward(h[k], p->W[k], p->b[k], h[k + 1], Lc, p->dims[k], p->dims[k + 1], p->act_id, 1, st,
                                 pack, &dev);
+      if (s) return s;
+    }
+    if (y_out != nullptr) {
+      s = launch_linear_forward(h[nl - 1], p->W[nl - 1], p->b[nl - 1], y_out + c0 * kout, Lc, p->dims[nl - 1], kout,
+                                p->act_id, 0, st, pack, &dev);
       if (s) return s;
     }
     const float* gz = gy + c0 * kout;
@@ -1103,9 +1111,14 @@ int molann_b200_value_and_grad(const MolannPlan* plan, const float* x, const flo
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const TcVgChoice vg = choose_tc_vg(plan, dev);
   if (vg.ok) return run_tc_vg(vg, to_dev(plan), x, gy, y, gx, (long long)L, dev, st);   // ONE kernel
-  s = molann_b200_forward(plan, x, L, y, workspace, workspace_bytes, stream);
-  if (s) return s;
-  return molann_b200_backward(plan, x, gy, L, gx, nullptr, nullptr, workspace, workspace_bytes, stream);
+  const SmallChoice ch = choose_small(plan, true, dev);
+  if (ch.ok) {                                   // fused FFMA family: two launches (forward, backward)
+    s = molann_b200_forward(plan, x, L, y, workspace, workspace_bytes, stream);
+    if (s) return s;
+    return molann_b200_backward(plan, x, gy, L, gx, nullptr, nullptr, workspace, workspace_bytes, stream);
+  }
+  // layered path: ONE pass -- the backward's forward recompute also writes y
+  return general_backward(plan, x, gy, L, gx, nullptr, nullptr, workspace, workspace_bytes, dev, st, y);
 }
 
 int molann_b200_preprocess_forward(const MolannPlan* plan, const float* x, int64_t L, float* feat, void* stream) {
