@@ -448,11 +448,39 @@ narrow_forward_kernel(const float* __restrict__ in, const float* __restrict__ W,
   }
 }
 
-// gprev[m, k] = (sum_o gz[m, o] W[o, k]) * act'(hprev[m, k]),  N <= NARROW_MAX: one thread per (m, k)
+// gprev[m, k] = (sum_o gz[m, o] W[o, k]) * act'(hprev[m, k]),  N <= NARROW_MAX: one thread per four consecutive k
 __global__ void __launch_bounds__(256)
 narrow_backward_input_kernel(const float* __restrict__ gz, const float* __restrict__ W,
                              const float* __restrict__ hprev, float* __restrict__ gprev, long long M, int K, int N,
                              int act) {
+  const bool vec = ((K & 3) == 0) && ((reinterpret_cast<uintptr_t>(W) & 15u) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(gprev) & 15u) == 0) &&
+                   (hprev == nullptr || (reinterpret_cast<uintptr_t>(hprev) & 15u) == 0);
+  if (vec) {
+    const int K4 = K >> 2;
+    const long long total = M * K4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+      const long long m = i / K4;
+      const int k = (int)(i - m * K4) << 2;
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int o = 0; o < NARROW_MAX; ++o) {
+        if (o < N) {
+          const float g = __ldg(gz + m * N + o);
+          const float4 w = __ldg(reinterpret_cast<const float4*>(W + (long long)o * K + k));
+          a.x = fmaf(g, w.x, a.x); a.y = fmaf(g, w.y, a.y); a.z = fmaf(g, w.z, a.z); a.w = fmaf(g, w.w, a.w);
+        }
+      }
+      if (hprev != nullptr) {
+        const float4 h = __ldg(reinterpret_cast<const float4*>(hprev + m * K + k));
+        a.x *= act_grad_from_output(h.x, act); a.y *= act_grad_from_output(h.y, act);
+        a.z *= act_grad_from_output(h.z, act); a.w *= act_grad_from_output(h.w, act);
+      }
+      *reinterpret_cast<float4*>(gprev + m * K + k) = a;
+    }
+    return;
+  }
   const long long total = M * K;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {

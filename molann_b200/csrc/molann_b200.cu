@@ -857,7 +857,7 @@ int launch_linear_backward_input(const float* gz, const float* W, const float* h
     return launch_gemm_tc<GT_EPI_DACT>(gz, M, N, W, 1, (long long)K, K, gprev, nullptr, hprev, act, hprev != nullptr, pack,
                                        *dev, st);
   if (N <= NARROW_MAX && env_int("MOLANN_B200_NARROW", 1) != 0) {
-    long long blocks = (M * K + 255) / 256;
+    long long blocks = (M * ((K + 3) / 4) + 255) / 256;
     const long long cap = (long long)(dev ? dev->sm_count : 148) * 16;
     if (blocks > cap) blocks = cap;
     narrow_backward_input_kernel<<<(unsigned)(blocks < 1 ? 1 : blocks), 256, 0, st>>>(gz, W, hprev, gprev, M, K, N,
