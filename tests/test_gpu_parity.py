@@ -537,6 +537,12 @@ def test_big_frame_preprocess_kernel_sets(staged, with_align, monkeypatch):
         (gx,) = torch.autograd.grad(f, xd, cot.cuda())
         assert_parity(f.detach().cpu(), f64, None, TOL, "big-frame features staged=%s shift=%d" % (staged, shift))
         assert_parity(gx.cpu(), gx64, None, 2e-5, "big-frame gx staged=%s shift=%d" % (staged, shift))
+        for Ls in (1, 2):                                  # fewer frames than ring stages / CTAs
+            xs = xd.detach()[:Ls].contiguous().requires_grad_(True)
+            fs = pp(xs)
+            (gs,) = torch.autograd.grad(fs, xs, cot[:Ls].cuda())
+            assert_parity(fs.detach().cpu(), f64[:Ls], None, TOL, "big-frame features L=%d" % Ls)
+            assert_parity(gs.cpu(), gx64[:Ls], None, 2e-5, "big-frame gx L=%d" % Ls)
 
 
 def test_c5_shape_parity():
