@@ -47,6 +47,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-layers", action="store_true", help="skip the stand-alone AlignmentLayer / PreprocessingANN rates")
+    ap.add_argument("--no-workloads", action="store_true",
+                    help="default (C2) run: skip the C1 / C3 / C5 / C4 / latency entries of `workloads`")
     return ap.parse_args()
 
 
@@ -247,7 +249,8 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": dict(workload_config(spec, spec.default_frames, args.gpus), reference_sample_frames_per_step=ff),
+        "config": workload_config(spec, args.frames or spec.default_frames, args.gpus),
+        "reference_sample_frames_per_step": ff,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "fwd_dx": {"value": vdx, "unit": UNIT},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -390,8 +393,9 @@ def run_training(args, rank, local_rank, world):
     ms_e = max_over_ranks(1e3 * (time.perf_counter() - t0))
     clocks = sampler.summary()
     sampler.close()
+    del xh
     if rank != 0:
-        return
+        return None
     peak, peak_src = peaks()
     value = n_global * K / (ms * 1e-3)
     bytes_per_frame = 12 * spec.n_inp                      # B_train = 12 n_inp per frame
@@ -424,7 +428,7 @@ def run_training(args, rank, local_rank, world):
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": kind,
                                     "sample": "3 SGD steps on 65536 frames; %s; torch.set_num_threads(%d)"
                                               % (where, os.cpu_count() or 1)}
-    emit(line)
+    return line
 
 
 def workload_config(spec, frames, n_gpus):
@@ -456,6 +460,313 @@ def emit(line):
         sys.stdout.flush()
     else:
         os.write(_REAL_STDOUT, data)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# inference workloads (C1, C2, C3, C5): forward and forward + d/dx, device-resident and end to end
+# ------------------------------------------------------------------------------------------------------------
+MIN_TIMED_MS = float(os.environ.get("MOLANN_BENCH_MIN_MS", "100"))   # every leg is warmed up for and timed over at
+                                                                      # least this long (clock ramp, noise); 0 for ncu runs
+MAX_REPS = 40
+
+
+class Dist(object):
+    """barrier / reductions over the ranks of this job (no-ops for one rank)."""
+
+    def __init__(self, world):
+        self.world = world
+        if world > 1:
+            import torch.distributed as dist
+            self.dist = dist
+
+    def barrier(self):
+        torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+            torch.cuda.synchronize()
+
+    def gather(self, value):
+        """-> list of `value` over the ranks (every rank gets it)."""
+        if self.world == 1:
+            return [float(value)]
+        t = torch.zeros(self.world, device="cuda", dtype=torch.float64)
+        t[self.dist.get_rank()] = float(value)
+        self.dist.all_reduce(t)
+        return [float(v) for v in t.tolist()]
+
+
+def timed_leg(step, K, W, dd, sampler=None):
+    """Warm up (>= W steps and >= MIN_TIMED_MS), then time repetitions of EXACTLY K steps -- each bracketed by a
+    barrier + synchronize on both sides, CUDA events on the launching stream -- until MIN_TIMED_MS of device time
+    has been measured.  The leg's figure is the MEDIAN repetition of the max-over-ranks time.  Returns
+    (ms for K steps, launches per K steps, stats)."""
+    from molann_b200 import _lib
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(W):
+        step()
+    dd.barrier()
+    e0.record()
+    for _ in range(K):
+        step()
+    e1.record()
+    dd.barrier()
+    guess = max(e0.elapsed_time(e1), 1e-3)
+    extra = int(min(50.0, MIN_TIMED_MS / guess))            # time-based part of the warm-up
+    if dd.world > 1:
+        extra = int(max(dd.gather(extra)))
+    for _ in range(extra * K):
+        step()
+    reps, total, launches, per_rank = [], 0.0, 0, []
+    while True:
+        dd.barrier()
+        l0 = _lib.launch_count()
+        if sampler is not None:
+            sampler.start()
+        e0.record()
+        for _ in range(K):
+            step()
+        e1.record()
+        dd.barrier()
+        if sampler is not None:
+            sampler.pause()
+        launches = _lib.launch_count() - l0
+        ranks = dd.gather(e0.elapsed_time(e1))
+        per_rank.append(ranks)
+        reps.append(max(ranks))
+        total += max(ranks)
+        if total >= MIN_TIMED_MS or len(reps) >= MAX_REPS:
+            break
+    order = sorted(range(len(reps)), key=lambda i: reps[i])
+    mid = order[len(order) // 2]
+    pr = per_rank[mid]
+    stats = {"repetitions": len(reps), "ms_min": min(reps), "ms_median": reps[mid], "ms_max": max(reps),
+             "per_rank_ms_of_median_rep": {"min": min(pr), "median": sorted(pr)[len(pr) // 2], "max": max(pr)},
+             "rule": "median over repetitions of max over ranks; each repetition = K steps between barriers"}
+    return reps[mid], launches, stats
+
+
+def measure_workload(name, args, rank, local_rank, world, dd, full):
+    """One inference workload on this job's ranks.  `full`: also the stand-alone layers, both end-to-end legs and
+    the CPU baseline (the headline workload); otherwise forward, forward + d/dx and the forward end-to-end leg."""
+    from molann_b200 import synthetic as S
+    from molann_b200.stream import HostPipeline
+    spec = S.get_spec(name)
+    frames = (args.frames if (args.frames and full) else 0) or spec.default_frames
+    model, _ = S.build_model(spec)
+    model = model.cuda()
+    x = S.make_frames(spec, frames, device="cuda", seed=spec.seed + rank)
+    cot = torch.zeros(frames, spec.out_dim(), device="cuda")
+    cot[:, 0] = 1.0                                        # d y_0 / dx: one collective-variable force
+    K, W = args.steps, max(args.warmup, 3)
+
+    def fwd_step():
+        with torch.no_grad():
+            return model(x)
+
+    def fwd_dx_step():
+        # outputs + coordinate gradient in ONE pass (MolANN.value_and_grad, the biasing-force entry)
+        return model.value_and_grad(x, cot)
+
+    sampler = ClockSampler(local_rank)
+    ms_f, launches_f, st_f = timed_leg(fwd_step, K, W, dd, sampler)
+    ms_d, launches_d, st_d = timed_leg(fwd_dx_step, K, W, dd, sampler)
+    clocks = sampler.summary()
+    sampler.close()
+    # cross-rank result check: every rank ALSO evaluates rank 0's first frames; all ranks must agree bit for bit
+    # (frames are independent, so a shard's output may not depend on the GPU it ran on)
+    n_chk = min(frames, 4096)
+    x0 = S.make_frames(spec, n_chk, device="cuda", seed=spec.seed)
+    with torch.no_grad():
+        y0 = model(x0)
+    chk = float(y0.double().sum())
+    chks = dd.gather(chk)
+    checksum = {"frames": n_chk, "value": chk, "identical_across_ranks": bool(all(c == chks[0] for c in chks))}
+    del x0, y0
+
+    via_autograd = None
+    layers = None
+    if full:
+        xg = x.clone().requires_grad_(True)
+
+        def fwd_dx_autograd_step():
+            y = model(xg)
+            (g,) = torch.autograd.grad(y, xg, cot)
+            return g
+
+        ms_da, launches_da, _ = timed_leg(fwd_dx_autograd_step, K, W, dd)
+        via_autograd = {"value": world * frames * K / (ms_da * 1e-3), "ms_per_step": ms_da / K,
+                        "gpu_launches": int(launches_da), "api": "y = model(x); torch.autograd.grad(y, x, cotangent)"}
+        # ---- the stand-alone layers of the same model (SURVEY 8(a) rows a2, a6) ----
+        pp = model.get_preprocessing_layer()
+        if not args.no_layers and getattr(pp, "align_layer", None) is not None and hasattr(pp.align_layer, "ref_x"):
+            n3b, db = 12 * spec.n_inp, 4 * spec.feature_dim()
+            gfe = torch.zeros(frames, spec.feature_dim(), device="cuda")
+            gfe[:, 0] = 1.0
+
+            def rate(step, nbytes):
+                ms_l, _, _ = timed_leg(step, K, W, dd)
+                v = world * frames * K / (ms_l * 1e-3)
+                return {"value": v, "unit": UNIT, "ms_per_step": ms_l / K, "bytes_per_frame": nbytes,
+                        "frac_of_hbm_peak": v / world * nbytes / 1e9 / peaks()[0]}
+
+            def al_f():
+                with torch.no_grad():
+                    return pp.align_layer(x)
+
+            def pp_f():
+                with torch.no_grad():
+                    return pp(x)
+
+            za = pp.align_layer(xg)
+            fa = pp(xg)
+            layers = {
+                "AlignmentLayer.forward": rate(al_f, 2 * n3b),
+                "AlignmentLayer.backward": rate(lambda: torch.autograd.grad(za, xg, x, retain_graph=True), 3 * n3b),
+                "PreprocessingANN.forward": rate(pp_f, n3b + db),
+                "PreprocessingANN.backward": rate(lambda: torch.autograd.grad(fa, xg, gfe, retain_graph=True),
+                                                  2 * n3b + db),
+            }
+            del za, fa, gfe
+        del xg
+
+    # ---- end to end through the public API with host buffers ----
+    e2e = e2e_dx = None
+    if not args.no_e2e:
+        xh = x.cpu().pin_memory()
+        yh = torch.empty(frames, spec.out_dim()).pin_memory()
+        chunk = int(os.environ.get("MOLANN_BENCH_E2E_CHUNK", max(1 << 10, frames // 8)))
+        pipe = HostPipeline(model, spec.n_inp, spec.out_dim(), chunk_frames=chunk)
+        ke = max(3, min(K, 10))
+        for _ in range(2):
+            pipe.run(xh, yh)
+        dd.barrier()
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            pipe.run(xh, yh)                              # returns once the results are in host memory
+        torch.cuda.synchronize()
+        ranks = dd.gather(1e3 * (time.perf_counter() - t0))
+        ms_e = max(ranks)
+        e2e = {"value": world * frames * ke / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes,
+               "d2h_bytes_per_step": pipe.d2h_bytes, "steps": ke, "ms_per_step": ms_e / ke,
+               "api": "molann_b200.stream.HostPipeline(MolANN).run(pinned x, pinned y)",
+               "result_checksum": float(yh[:: max(1, frames // 1024)].double().sum()),
+               "per_rank_h2d_GBps": [pipe.h2d_bytes * ke / (r * 1e-3) / 1e9 for r in ranks]}
+        if full:
+            coth = cot.cpu().pin_memory()
+            gxh = torch.empty(frames, spec.n_inp, 3).pin_memory()
+            pipe.run(xh, yh, coth, gxh)
+            dd.barrier()
+            t0 = time.perf_counter()
+            for _ in range(ke):
+                pipe.run(xh, yh, coth, gxh)
+            torch.cuda.synchronize()
+            ms_ed = max(dd.gather(1e3 * (time.perf_counter() - t0)))
+            e2e_dx = {"value": world * frames * ke / (ms_ed * 1e-3), "unit": UNIT,
+                      "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes, "steps": ke,
+                      "ms_per_step": ms_ed / ke}
+            del coth, gxh
+        del xh, yh, pipe
+
+    out = None
+    if rank == 0:
+        peak, peak_src = peaks()
+
+        def roofline(bytes_per_frame, ms_total, launches, which):
+            # SURVEY 8(d) honesty guard: credit min(algorithmic bytes, DRAM bytes ncu measured for this launch
+            # shape), so a kernel is never credited for bytes it did not move.  The ncu figure only applies to the
+            # launch shape it was captured on.
+            per_launch_s = ms_total * 1e-3 / K
+            alg = bytes_per_frame * frames
+            traffic = ncu_traffic(spec.name, which) if frames == spec.default_frames else None
+            credited = min(alg, traffic) if traffic else alg
+            achieved = credited / per_launch_s / 1e9
+            return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
+                    "credited_bytes_per_launch": credited, "kernel_launches_per_step": launches / K,
+                    "frac_of_nominal_8TBs": achieved / 8000.0}
+
+        out = {
+            "metric": METRIC, "value": world * frames * K / (ms_f * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": ms_f / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(spec, frames, world),
+            "roofline": roofline(spec.bytes_fwd(), ms_f, launches_f, "fwd"),
+            "gpu_launches": int(launches_f), "clocks": clocks, "timing": st_f,
+            "fwd_dx": {"value": world * frames * K / (ms_d * 1e-3), "unit": UNIT, "ms_per_step": ms_d / K,
+                       "gpu_launches": int(launches_d), "api": "MolANN.value_and_grad(x, cotangent)",
+                       "roofline": roofline(spec.bytes_fwd_dx(), ms_d, launches_d, "fwd_dx"), "e2e": e2e_dx,
+                       "timing": st_d, "via_autograd": via_autograd},
+            "e2e": e2e, "cross_rank_checksum": checksum,
+        }
+        if layers is not None:
+            out["layers"] = layers
+        if world == 1 and not args.no_cpu_baseline:
+            ff, fd = cpu_sample_sizes(spec)
+            cf, cd, cores, kind, where = time_cpu(spec, ff, fd, reps=3 if full else 2)
+            out["cpu_baseline"] = {"value": cf, "unit": UNIT, "cores": cores, "kind": kind,
+                                   "sample": "best of %d: %d frames fwd (no_grad), %d frames fwd+dx (autograd); %s; "
+                                             "torch.set_num_threads(%d)" % (3 if full else 2, ff, fd, where, cores),
+                                   "fwd_dx_value": cd}
+    del model, x, cot
+    torch.cuda.empty_cache()
+    return out
+
+
+def latency_probe(dd):
+    """What an MD plugin sends: L = 1 ... 128 frames per call.  Microseconds per call (host wall clock around a
+    synchronised loop of calls through the module API), forward and value_and_grad, workload C2."""
+    from molann_b200 import synthetic as S
+    spec = S.get_spec("C2")
+    model, _ = S.build_model(spec)
+    model = model.cuda()
+    res = {}
+    for L in (1, 32, 128):
+        x = S.make_frames(spec, L, device="cuda", seed=5)
+        cot = torch.ones(L, spec.out_dim(), device="cuda")
+        with torch.no_grad():
+            for _ in range(20):
+                model(x)
+                model.value_and_grad(x, cot)
+            torch.cuda.synchronize()
+            n = 200
+            t0 = time.perf_counter()
+            for _ in range(n):
+                model(x)
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            for _ in range(n):
+                model.value_and_grad(x, cot)
+            torch.cuda.synchronize()
+            t2 = time.perf_counter()
+            # one call at a time, result needed on the host before the next MD step can start
+            t3 = time.perf_counter()
+            for _ in range(n):
+                y, g = model.value_and_grad(x, cot)
+                y.cpu()
+            t4 = time.perf_counter()
+        res["L=%d" % L] = {"forward_us_per_call": 1e6 * (t1 - t0) / n, "value_and_grad_us_per_call": 1e6 * (t2 - t1) / n,
+                           "value_and_grad_sync_us_per_call": 1e6 * (t4 - t3) / n}
+    res["note"] = ("C2 model, back-to-back calls through MolANN.forward / MolANN.value_and_grad (host wall clock / "
+                   "calls); *_sync: each call followed by a device->host read of y")
+    return res
+
+
+def compact(line):
+    """What the default line keeps of a secondary workload."""
+    if line is None:
+        return None
+    keep = {"value": line["value"], "unit": line["unit"], "ms_per_step": line["ms_per_step"],
+            "frames_per_gpu_per_step": line["config"]["frames_per_gpu_per_step"],
+            "gpu_launches_per_step": line["gpu_launches"] / float(line["steps"]),
+            "roofline": {k: line["roofline"][k] for k in ("frac", "achieved", "traffic", "algorithmic_bytes_per_launch")},
+            "fwd_dx": {"value": line["fwd_dx"]["value"], "ms_per_step": line["fwd_dx"]["ms_per_step"],
+                       "gpu_launches_per_step": line["fwd_dx"]["gpu_launches"] / float(line["steps"]),
+                       "roofline": {k: line["fwd_dx"]["roofline"][k]
+                                    for k in ("frac", "achieved", "traffic", "algorithmic_bytes_per_launch")}},
+            "e2e": line.get("e2e"), "cross_rank_checksum": line.get("cross_rank_checksum"),
+            "workload": line["config"]["workload"]}
+    if "cpu_baseline" in line:
+        keep["cpu_baseline"] = line["cpu_baseline"]
+    return keep
 
 
 def main():
@@ -490,195 +801,36 @@ def main():
         bind_to_gpu_numa_node(local_rank)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+    dd = Dist(world)
+    torch.set_num_threads(os.cpu_count() or 1)
 
     if args.workload == "C4":
-        torch.set_num_threads(os.cpu_count() or 1)
-        run_training(args, rank, local_rank, world)
+        line = run_training(args, rank, local_rank, world)
+        if rank == 0:
+            emit(line)
         if world > 1:
             dist.destroy_process_group()
         return
 
-    from molann_b200 import _lib
-    from molann_b200 import synthetic as S
-    from molann_b200.stream import HostPipeline
-
-    spec = S.get_spec(args.workload)
-    frames = args.frames or spec.default_frames
-    model, _ = S.build_model(spec)
-    model = model.cuda()
-    x = S.make_frames(spec, frames, device="cuda", seed=spec.seed + rank)
-    cot = torch.zeros(frames, spec.out_dim(), device="cuda")
-    cot[:, 0] = 1.0                                        # d y_0 / dx: one collective-variable force
-    xg = x.clone().requires_grad_(True)
-    K, W = args.steps, max(args.warmup, 3)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    def max_over_ranks(ms):
-        if world > 1:
-            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            return float(t.item())
-        return ms
-
-    def fwd_step():
-        with torch.no_grad():
-            return model(x)
-
-    def fwd_dx_step():
-        # outputs + coordinate gradient in ONE fused launch (MolANN.value_and_grad, the biasing-force entry)
-        return model.value_and_grad(x, cot)
-
-    def fwd_dx_autograd_step():
-        y = model(xg)
-        (g,) = torch.autograd.grad(y, xg, cot)
-        return g
-
-    sampler = ClockSampler(local_rank)
-
-    def timed(step, k, w, sample_clocks):
-        for _ in range(w):
-            step()
-        barrier()
-        l0 = _lib.launch_count()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        if sample_clocks:
-            sampler.start()
-        e0.record()
-        for _ in range(k):
-            step()
-        e1.record()
-        barrier()
-        if sample_clocks:
-            sampler.pause()
-        return max_over_ranks(e0.elapsed_time(e1)), _lib.launch_count() - l0
-
-    ms_f, launches_f = timed(fwd_step, K, W, True)
-    ms_d, launches_d = timed(fwd_dx_step, K, W, True)
-    ms_da, launches_da = timed(fwd_dx_autograd_step, K, W, False)
-    clocks = sampler.summary()
-    sampler.close()
-
-    # ---- the stand-alone layers of the same model: AlignmentLayer, PreprocessingANN ----
-    layers = None
-    pp = model.get_preprocessing_layer()
-    if not args.no_layers and getattr(pp, "align_layer", None) is not None and hasattr(pp.align_layer, "ref_x"):
-        n3b, db = 12 * spec.n_inp, 4 * spec.feature_dim()
-        gfe = torch.zeros(frames, spec.feature_dim(), device="cuda")
-        gfe[:, 0] = 1.0
-
-        def rate(step, nbytes):
-            ms_l, _ = timed(step, K, W, False)
-            v = world * frames * K / (ms_l * 1e-3)
-            return {"value": v, "unit": UNIT, "ms_per_step": ms_l / K, "bytes_per_frame": nbytes,
-                    "frac_of_hbm_peak": v / world * nbytes / 1e9 / peaks()[0]}
-
-        def al_f():
-            with torch.no_grad():
-                return pp.align_layer(x)
-
-        def pp_f():
-            with torch.no_grad():
-                return pp(x)
-
-        za = pp.align_layer(xg)
-        fa = pp(xg)
-        layers = {
-            "AlignmentLayer.forward": rate(al_f, 2 * n3b),
-            "AlignmentLayer.backward": rate(lambda: torch.autograd.grad(za, xg, x, retain_graph=True), 3 * n3b),
-            "PreprocessingANN.forward": rate(pp_f, n3b + db),
-            "PreprocessingANN.backward": rate(lambda: torch.autograd.grad(fa, xg, gfe, retain_graph=True),
-                                              2 * n3b + db),
-        }
-        del za, fa, gfe
-
-    # ---- end to end through the public API with host buffers ----
-    e2e = e2e_dx = None
-    if not args.no_e2e:
-        xh = x.cpu().pin_memory()
-        yh = torch.empty(frames, spec.out_dim()).pin_memory()
-        pipe = HostPipeline(model, spec.n_inp, spec.out_dim(), chunk_frames=int(os.environ.get("MOLANN_BENCH_E2E_CHUNK", max(1 << 12, frames // 8))))
-        ke = max(3, min(K, 10))
-
-        def e2e_step():
-            pipe.run(xh, yh)
-
-        for _ in range(2):
-            e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(ke):
-            e2e_step()
-        torch.cuda.synchronize()
-        ms_e = max_over_ranks(1e3 * (time.perf_counter() - t0))
-        checksum = float(yh[:: max(1, frames // 1024)].double().sum())
-        e2e = {"value": world * frames * ke / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes,
-               "d2h_bytes_per_step": pipe.d2h_bytes, "steps": ke, "ms_per_step": ms_e / ke,
-               "api": "molann_b200.stream.HostPipeline(MolANN).run(pinned x, pinned y)", "result_checksum": checksum}
-        coth = cot.cpu().pin_memory()
-        gxh = torch.empty(frames, spec.n_inp, 3).pin_memory()
-        pipe.run(xh, yh, coth, gxh)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(ke):
-            pipe.run(xh, yh, coth, gxh)
-        torch.cuda.synchronize()
-        ms_ed = max_over_ranks(1e3 * (time.perf_counter() - t0))
-        e2e_dx = {"value": world * frames * ke / (ms_ed * 1e-3), "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes,
-                  "d2h_bytes_per_step": pipe.d2h_bytes, "steps": ke, "ms_per_step": ms_ed / ke}
-        del xh, yh, coth, gxh
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
-    peak, peak_src = peaks()
-    value = world * frames * K / (ms_f * 1e-3)
-    value_dx = world * frames * K / (ms_d * 1e-3)
-
-    def roofline(bytes_per_frame, ms_total, launches, which):
-        # SURVEY 8(d) honesty guard: credit min(algorithmic bytes, DRAM bytes ncu measured for this launch shape),
-        # so a kernel is never credited for bytes it did not move (write-backs still in L2 at kernel end count
-        # against us).  The ncu figure only applies to the launch shape it was captured on.
-        per_launch_s = ms_total * 1e-3 / K
-        alg = bytes_per_frame * frames
-        traffic = ncu_traffic(spec.name, which) if frames == spec.default_frames else None
-        credited = min(alg, traffic) if traffic else alg
-        achieved = credited / per_launch_s / 1e9
-        return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
-                "credited_bytes_per_launch": credited, "kernel_launches_per_step": launches / K,
-                "frac_of_nominal_8TBs": achieved / 8000.0}
-
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms_f / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": workload_config(spec, frames, world),
-        "roofline": roofline(spec.bytes_fwd(), ms_f, launches_f, "fwd"),
-        "gpu_launches": int(launches_f), "clocks": clocks,
-        "fwd_dx": {"value": value_dx, "unit": UNIT, "ms_per_step": ms_d / K, "gpu_launches": int(launches_d),
-                   "api": "MolANN.value_and_grad(x, cotangent)",
-                   "roofline": roofline(spec.bytes_fwd_dx(), ms_d, launches_d, "fwd_dx"), "e2e": e2e_dx,
-                   "via_autograd": {"value": world * frames * K / (ms_da * 1e-3), "ms_per_step": ms_da / K,
-                                    "gpu_launches": int(launches_da),
-                                    "api": "y = model(x); torch.autograd.grad(y, x, cotangent)"}},
-        "e2e": e2e,
-    }
-    if layers is not None:
-        line["layers"] = layers
-    if world == 1 and not args.no_cpu_baseline:
-        ff, fd = cpu_sample_sizes(spec)
-        cf, cd, cores, kind, where = time_cpu(spec, ff, fd)
-        line["cpu_baseline"] = {"value": cf, "unit": UNIT, "cores": cores, "kind": kind,
-                                "sample": "best of 3: %d frames fwd (no_grad), %d frames fwd+dx (autograd); %s; "
-                                          "torch.set_num_threads(%d)" % (ff, fd, where, cores),
-                                "fwd_dx_value": cd}
-    emit(line)
+    line = measure_workload(args.workload, args, rank, local_rank, world, dd, full=True)
+    # the other BASELINE configs ride along in the default line (C2) so the driver's record covers every one of them
+    others = {}
+    if args.workload == "C2" and not args.frames and not args.no_workloads:
+        for name in ("C1", "C3", "C5"):
+            others[name] = compact(measure_workload(name, args, rank, local_rank, world, dd, full=False))
+        c4 = run_training(args, rank, local_rank, world)
+        if c4 is not None:
+            others["C4"] = {"metric": c4["metric"], "value": c4["value"], "unit": c4["unit"], "scaling": c4["scaling"],
+                            "ms_per_step": c4["ms_per_step"], "allreduce_ms": c4["allreduce_ms"],
+                            "gpu_launches": c4["gpu_launches"], "cuda_graph": c4["cuda_graph"]["used"],
+                            "e2e": c4["e2e"], "final_loss": c4["final_loss"], "workload": c4["config"]["workload"],
+                            "cpu_baseline": c4.get("cpu_baseline")}
+        if world == 1:
+            others["latency_C2"] = latency_probe(dd)
+    if rank == 0:
+        if others:
+            line["workloads"] = others
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

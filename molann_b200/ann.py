@@ -284,10 +284,28 @@ class MolANN(torch.nn.Module):
         self._act_id = act if act >= 0 else 0
         self._fused = (self._mode != 0)            # bool constants give TorchScript a static `if`
         self._fused_align = (self._mode == 2)
+        self._n_mlp_modules = len(ann_layers._modules) if isinstance(ann_layers, torch.nn.Sequential) else -1
+
+    @torch.jit.unused
+    def _mlp_unchanged(self) -> bool:
+        """Eager-mode guard: the fused kernel was chosen for the ``ann_layers`` seen at construction.  If the user
+        has since added / swapped a child (another activation, an extra layer), fall back to the composition the
+        reference always evaluates instead of silently running the stale structure.  (A scripted module is frozen,
+        so the check is not needed -- nor possible -- there.)"""
+        if len(self.ann_layers._modules) != self._n_mlp_modules:
+            return False
+        return _fusable_activation(self.ann_layers) == self._act_id
 
     def get_preprocessing_layer(self):
         """the :class:`PreprocessingANN` of this model"""
         return self.preprocessing_layer
+
+    @torch.jit.unused
+    def _value_and_grad_composed(self, x, cotangent):
+        xg = x.detach().requires_grad_(True)
+        y = self.ann_layers(self.preprocessing_layer(xg))
+        (g,) = torch.autograd.grad(y, xg, cotangent)
+        return y.detach(), g.detach()
 
     @torch.jit.export
     def value_and_grad(self, x, cotangent):
@@ -298,6 +316,9 @@ class MolANN(torch.nn.Module):
         """
         assert x.size(1) == self.preprocessing_layer.feature_layer.input_atom_num and x.size(2) == 3, \
             'Input should be a 3d torch tensor with sizes [*, n_inp, 3]'
+        if not torch.jit.is_scripting():
+            if self._fused and not self._mlp_unchanged():
+                return self._value_and_grad_composed(x, cotangent)
         if not self._fused:
             xg = x.detach().requires_grad_(True)
             y = self.forward(xg)
@@ -324,6 +345,9 @@ class MolANN(torch.nn.Module):
 
     def forward(self, x):
         """the forward map ``[l, n_inp, 3] -> [l, k]``"""
+        if not torch.jit.is_scripting():
+            if self._fused and not self._mlp_unchanged():
+                return self.ann_layers(self.preprocessing_layer(x))
         if not self._fused:
             return self.ann_layers(self.preprocessing_layer(x))
         else:

@@ -33,15 +33,26 @@ struct DeviceInfo {
   bool ok = false;
 };
 
+// The attributes of a device never change: queried once per device and cached (an MD plugin calls with a handful
+// of frames, where three attribute queries per call are a measurable part of the host-side cost).  The CURRENT
+// device is still asked for on every call, so switching devices between calls stays correct.
 DeviceInfo device_info() {
-  // re-queried per call: cheap, and correct when the caller switches devices between calls
+  constexpr int kMaxDev = 64;
+  static DeviceInfo cache[kMaxDev];
+  static std::atomic<int> ready[kMaxDev];
   DeviceInfo d;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return d;
+  const bool cacheable = dev >= 0 && dev < kMaxDev;
+  if (cacheable && ready[dev].load(std::memory_order_acquire)) return cache[dev];
   if (cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return d;
   if (cudaDeviceGetAttribute(&d.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return d;
   if (cudaDeviceGetAttribute(&d.smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev) != cudaSuccess) return d;
   d.ok = true;
+  if (cacheable) {                       // racing first calls write identical values
+    cache[dev] = d;
+    ready[dev].store(1, std::memory_order_release);
+  }
   return d;
 }
 

@@ -15,6 +15,9 @@
 #include <ATen/ATen.h>
 #include <torch/csrc/autograd/custom_function.h>
 
+#include <nvtx3/nvToolsExt.h>
+
+#include <cstring>
 #include <tuple>
 #include <vector>
 
@@ -34,6 +37,29 @@ void check_status(int status, const char* what) {
                 ")");
   }
   TORCH_CHECK(false, "molann_b200: ", what, " failed: ", molann_b200_strerror(status));
+}
+
+// NVTX range around every op (tracing); a no-op unless a profiler is attached
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+
+// The backward kernels return plain tensors: a second differentiation through them (create_graph=True, e.g. a
+// force-matching or gradient-norm loss) would silently treat d/dx as a constant.  The autograd engine enables grad
+// mode inside backward only for create_graph=True, so that is the condition to refuse.
+void refuse_double_backward(const char* op) {
+  TORCH_CHECK(!at::GradMode::is_enabled(), "molann_b200::", op,
+              ": double backward (torch.autograd.grad(..., create_graph=True)) is not supported -- the coordinate "
+              "gradient comes from a closed-form kernel and carries no autograd history");
+}
+
+void check_cotangent(const Tensor& g, const Tensor& x, const char* op) {
+  TORCH_CHECK(g.defined(), "molann_b200::", op, ": undefined output gradient");
+  TORCH_CHECK(g.device() == x.device(), "molann_b200::", op, ": the output gradient lives on ", g.device(),
+              " but the input on ", x.device());
+  TORCH_CHECK(g.scalar_type() == at::kFloat, "molann_b200::", op, ": the output gradient must be float32, got ",
+              g.scalar_type());
 }
 
 void check_x(const Tensor& x, const char* op) {
@@ -111,6 +137,7 @@ void* cur_stream() { return static_cast<void*>(at::cuda::getCurrentCUDAStream().
 // ------------------------------------------------------------------------------------------
 Tensor align_fwd_impl(const Tensor& x, const Tensor& align_idx, const Tensor& ref_x) {
   check_x(x, "align");
+  NvtxRange nvtx("molann_b200::align");
   c10::cuda::CUDAGuard guard(x.device());
   PlanHolder h;
   fill_geometry(h, x, align_idx, ref_x);
@@ -122,6 +149,8 @@ Tensor align_fwd_impl(const Tensor& x, const Tensor& align_idx, const Tensor& re
 }
 
 Tensor align_bwd_impl(const Tensor& x, const Tensor& align_idx, const Tensor& ref_x, const Tensor& gout_in) {
+  check_cotangent(gout_in, x, "align backward");
+  NvtxRange nvtx("molann_b200::align backward");
   c10::cuda::CUDAGuard guard(x.device());
   PlanHolder h;
   fill_geometry(h, x, align_idx, ref_x);
@@ -136,6 +165,7 @@ Tensor align_bwd_impl(const Tensor& x, const Tensor& align_idx, const Tensor& re
 Tensor preprocess_fwd_impl(const Tensor& x, const Tensor& align_idx, const Tensor& ref_x, const Tensor& entries,
                            int64_t d_feat, bool use_angle_value) {
   check_x(x, "preprocess");
+  NvtxRange nvtx("molann_b200::preprocess");
   c10::cuda::CUDAGuard guard(x.device());
   PlanHolder h;
   fill_geometry(h, x, align_idx, ref_x);
@@ -149,6 +179,8 @@ Tensor preprocess_fwd_impl(const Tensor& x, const Tensor& align_idx, const Tenso
 
 Tensor preprocess_bwd_impl(const Tensor& x, const Tensor& align_idx, const Tensor& ref_x, const Tensor& entries,
                            int64_t d_feat, bool use_angle_value, const Tensor& gfeat_in) {
+  check_cotangent(gfeat_in, x, "preprocess backward");
+  NvtxRange nvtx("molann_b200::preprocess backward");
   c10::cuda::CUDAGuard guard(x.device());
   PlanHolder h;
   fill_geometry(h, x, align_idx, ref_x);
@@ -164,6 +196,7 @@ Tensor preprocess_bwd_impl(const Tensor& x, const Tensor& align_idx, const Tenso
 Tensor molann_fwd_impl(const Tensor& x, const Tensor& align_idx, const Tensor& ref_x, const Tensor& entries,
                        int64_t d_feat, bool use_angle_value, at::TensorList params, int64_t act) {
   check_x(x, "molann");
+  NvtxRange nvtx("molann_b200::molann");
   c10::cuda::CUDAGuard guard(x.device());
   PlanHolder h;
   fill_geometry(h, x, align_idx, ref_x);
@@ -189,6 +222,8 @@ std::vector<Tensor> molann_bwd_impl(const Tensor& x, const Tensor& align_idx, co
                                     const Tensor& entries, int64_t d_feat, bool use_angle_value,
                                     at::TensorList params, int64_t act, const Tensor& gy_in, bool want_params,
                                     bool want_x = true) {
+  check_cotangent(gy_in, x, "molann backward");
+  NvtxRange nvtx("molann_b200::molann backward");
   c10::cuda::CUDAGuard guard(x.device());
   PlanHolder h;
   fill_geometry(h, x, align_idx, ref_x);
@@ -232,6 +267,7 @@ std::tuple<Tensor, Tensor> value_and_grad_impl(const Tensor& x, const Tensor& gy
                                                const Tensor& ref_x, const Tensor& entries, int64_t d_feat,
                                                bool use_angle_value, at::TensorList params, int64_t act) {
   check_x(x, "value_and_grad");
+  NvtxRange nvtx("molann_b200::value_and_grad");
   c10::cuda::CUDAGuard guard(x.device());
   PlanHolder h;
   fill_geometry(h, x, align_idx, ref_x);
@@ -239,9 +275,9 @@ std::tuple<Tensor, Tensor> value_and_grad_impl(const Tensor& x, const Tensor& gy
   fill_mlp(h, x, params, act);
   const int64_t L = x.size(0);
   const int64_t kout = h.plan.dims[h.plan.n_layers];
-  TORCH_CHECK(gy_in.is_cuda() && gy_in.scalar_type() == at::kFloat && gy_in.dim() == 2 && gy_in.size(0) == L &&
-                  gy_in.size(1) == kout,
-              "molann_b200::value_and_grad: cotangent must be a float32 CUDA tensor of shape [L, ", kout, "]");
+  check_cotangent(gy_in, x, "value_and_grad");
+  TORCH_CHECK(gy_in.dim() == 2 && gy_in.size(0) == L && gy_in.size(1) == kout,
+              "molann_b200::value_and_grad: cotangent must have shape [L, ", kout, "]");
   Tensor gy = gy_in.contiguous();
   Tensor y = at::empty({L, kout}, x.options());
   Tensor gx = at::empty_like(x);
@@ -269,6 +305,7 @@ struct AlignFn : public torch::autograd::Function<AlignFn> {
     return align_fwd_impl(x, align_idx, ref_x);
   }
   static variable_list backward(AutogradContext* ctx, variable_list grads) {
+    refuse_double_backward("align");
     auto saved = ctx->get_saved_variables();
     Tensor gx = align_bwd_impl(saved[0], saved[1], saved[2], grads[0]);
     return {gx, Tensor(), Tensor()};
@@ -285,6 +322,7 @@ struct PreprocessFn : public torch::autograd::Function<PreprocessFn> {
     return preprocess_fwd_impl(x, align_idx, ref_x, entries, d_feat, use_angle_value);
   }
   static variable_list backward(AutogradContext* ctx, variable_list grads) {
+    refuse_double_backward("preprocess");
     auto saved = ctx->get_saved_variables();
     Tensor gx = preprocess_bwd_impl(saved[0], saved[1], saved[2], saved[3], ctx->saved_data["d_feat"].toInt(),
                                     ctx->saved_data["use_angle_value"].toBool(), grads[0]);
@@ -312,6 +350,7 @@ struct MolannFn : public torch::autograd::Function<MolannFn> {
     return molann_fwd_impl(x, align_idx, ref_x, entries, d_feat, use_angle_value, params, act);
   }
   static variable_list backward(AutogradContext* ctx, variable_list grads) {
+    refuse_double_backward("molann");
     auto saved = ctx->get_saved_variables();
     const int64_t np = ctx->saved_data["n_params"].toInt();
     std::vector<Tensor> params(saved.begin() + 4, saved.begin() + 4 + np);
@@ -347,6 +386,18 @@ Tensor molann_autograd(const Tensor& x, const Tensor& align_idx, const Tensor& r
   return MolannFn::apply(x, align_idx, ref_x, entries, d_feat, use_angle_value, params, act);
 }
 
+// value_and_grad is an explicit "no graph" entry point: its outputs never carry autograd history, whatever the
+// requires_grad flags of x and the MLP parameters say (without this kernel PyTorch's autograd-not-implemented
+// fallback would hand back tensors with requires_grad=True and a grad_fn that only warns).
+std::tuple<Tensor, Tensor> value_and_grad_autograd(const Tensor& x, const Tensor& gy, const Tensor& align_idx,
+                                                   const Tensor& ref_x, const Tensor& entries, int64_t d_feat,
+                                                   bool use_angle_value, at::TensorList params, int64_t act) {
+  at::AutoDispatchBelowADInplaceOrView g;
+  std::vector<Tensor> plain;
+  for (const Tensor& p : params) plain.push_back(p.detach());
+  return value_and_grad_impl(x.detach(), gy.detach(), align_idx, ref_x, entries, d_feat, use_angle_value, plain, act);
+}
+
 int64_t launch_count() { return molann_b200_launch_count(); }
 
 }  // namespace
@@ -372,4 +423,5 @@ TORCH_LIBRARY_IMPL(molann_b200, Autograd, m) {
   m.impl("align", &align_autograd);
   m.impl("preprocess", &preprocess_autograd);
   m.impl("molann", &molann_autograd);
+  m.impl("value_and_grad", &value_and_grad_autograd);
 }

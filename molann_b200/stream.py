@@ -52,8 +52,12 @@ class HostPipeline(object):
 
     Args:
         model: a CUDA-resident module from :mod:`molann_b200.ann` (``MolANN`` or ``PreprocessingANN``).
+        n_inp, out_dim: atoms per frame / model outputs per frame.
         chunk_frames: frames per H2D chunk.
-        with_grad: also return d<cot, y>/dx for a cotangent supplied per call.
+
+    ``run`` returns only after the last device->host copy has landed (it synchronises on the copy-out stream), so
+    the caller may read ``y_host`` / ``gx_host`` and reuse ``x_host`` immediately.  Nothing it writes carries
+    autograd history.
     """
 
     def __init__(self, model, n_inp: int, out_dim: int, chunk_frames: int = 1 << 18, device=None):
@@ -71,8 +75,11 @@ class HostPipeline(object):
 
     def run(self, x_host: torch.Tensor, y_host: torch.Tensor, cot_host: Optional[torch.Tensor] = None,
             gx_host: Optional[torch.Tensor] = None):
-        """``y_host[:] = model(x_host)``; with ``cot_host``/``gx_host`` also ``gx_host[:] = d<cot,y>/dx``."""
+        """``y_host[:] = model(x_host)``; with ``cot_host``/``gx_host`` also ``gx_host[:] = d<cot,y>/dx``.
+        Blocks the host until the results are in the host buffers."""
         assert x_host.is_pinned() and y_host.is_pinned(), "host buffers must be pinned"
+        assert not y_host.requires_grad and (gx_host is None or not gx_host.requires_grad), \
+            "result buffers must be plain tensors"
         L = x_host.shape[0]
         want_grad = gx_host is not None
         if want_grad and self.gbuf is None:
@@ -107,13 +114,14 @@ class HostPipeline(object):
                     xb = xb.detach().requires_grad_(True)
                     y = self.model(xb)
                     (gx,) = torch.autograd.grad(y, xb, self.gbuf[b][:m])
-                self.ybuf[b][:m].copy_(y.detach())
-                keep[b] = gx
+                with torch.no_grad():
+                    self.ybuf[b][:m].copy_(y.detach())
+                keep[b] = gx.detach()
             else:
                 with torch.no_grad():
                     self.ybuf[b][:m].copy_(self.model(xb))
             comp_done[b].record(main)
-            with torch.cuda.stream(self.copy_out):
+            with torch.cuda.stream(self.copy_out), torch.no_grad():
                 self.copy_out.wait_event(comp_done[b])
                 y_host[s:e].copy_(self.ybuf[b][:m], non_blocking=True)
                 self.d2h_bytes += m * self.out_dim * 4
@@ -123,4 +131,7 @@ class HostPipeline(object):
                     self.d2h_bytes += m * self.n_inp * 12
                 out_done[b].record(self.copy_out)
         main.wait_stream(self.copy_out)
+        done = torch.cuda.Event()
+        done.record(self.copy_out)
+        done.synchronize()                  # the D2H copies (and every H2D read of x_host before them) have finished
         return y_host

@@ -1,0 +1,210 @@
+"""On-device edge cases of the alignment path and regressions for the autograd contract (-m gpu).
+
+Reference behaviour being checked: the SVD route with its det < 0 correction (molann/ann.py:188-195), a 3-atom
+alignment selection (rank-2 covariance), and frames whose top quaternion eigenvalue is nearly
+degenerate (the kernels then leave the polynomial fast path for the cyclic Jacobi fallback, geometry.cuh).  Random
+point clouds give all three at once: about half of the frames need the reflection correction and about half take the
+fallback (measured on the host emulation, tests/test_device_math_host.py)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import R, S, assert_parity, frame_rel_err, oracle_value_and_grad
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+
+def _clouds(L, n, seed, offset=30.0):
+    g = torch.Generator().manual_seed(seed)
+    return (2.0 * torch.randn(L, n, 3, generator=g) + offset).float()
+
+
+def _conditioning(x, aidx, ref):
+    """(reflection mask, |s2 + d s3| / s1): the gap that conditions both R and its derivative."""
+    xs = x[:, aidx, :].double()
+    H = torch.matmul((xs - xs.mean(1, True)).permute(0, 2, 1), ref.double())
+    u, s, vh = torch.linalg.svd(H)
+    d = torch.sign(torch.linalg.det(u @ vh))
+    return d < 0, ((s[:, 1] + d * s[:, 2]) / s[:, 0]).abs()
+
+
+@pytest.mark.parametrize("aidx", [[0, 3, 7], [1, 2, 4, 5, 8], list(range(12))])
+def test_alignment_layer_on_random_clouds(aidx):
+    """AlignmentLayer forward and backward on the device: reflection frames, n_a = 3, Jacobi fallback."""
+    from molann_b200.ann import AlignmentLayer
+    from molann_b200.atomgroup import Universe
+    n, L = 12, 4000
+    rng = np.random.RandomState(len(aidx))
+    refpos = rng.randn(n, 3).astype(np.float32) * 2
+    u = Universe(refpos)
+    layer = AlignmentLayer(u.select_ix(aidx), u.atoms).cuda()
+    ref = torch.from_numpy(refpos[aidx])
+    ref = ref - ref.mean(0)
+    x = _clouds(L, n, 7 + len(aidx))
+    reflect, gap = _conditioning(x, aidx, ref)
+    assert int(reflect.sum()) > L // 10 and int((~reflect).sum()) > L // 10
+    ok = gap > 0.05
+    assert int(ok.sum()) > L // 2
+    gout = torch.randn(L, n, 3, generator=torch.Generator().manual_seed(3))
+    fn64 = lambda xx: R.align_forward(xx, aidx, ref.double())
+    fn32 = lambda xx: R.align_forward(xx, aidx, ref)
+    z64, gx64 = oracle_value_and_grad(fn64, x, gout)
+    z32, gx32 = oracle_value_and_grad(fn32, x, gout, torch.float32)
+    xd = x.cuda().requires_grad_(True)
+    z = layer(xd)
+    (gx,) = torch.autograd.grad(z, xd, gout.cuda())
+    assert torch.isfinite(z).all() and torch.isfinite(gx).all()
+    assert_parity(z.detach().cpu()[ok], z64[ok], z32[ok], TOL, "align z n_a=%d" % len(aidx))
+    assert_parity(gx.cpu()[ok], gx64[ok], gx32[ok], TOL, "align gx n_a=%d" % len(aidx))
+    # reflection frames specifically (they are the ones a det = +1-only solver gets wrong)
+    sel = ok & reflect
+    assert float(frame_rel_err(z.detach().cpu()[sel], z64[sel]).max()) < 5e-5
+    # ill-conditioned frames: no parity claim (the reference's own fp32 answer is off there), but finite and proper
+    zc = z.detach().cpu().double()
+    d0 = (zc[:, aidx] - zc[:, aidx].mean(1, True)).norm(dim=2)
+    d1 = (x[:, aidx].double() - x[:, aidx].double().mean(1, True)).norm(dim=2)
+    assert float((d0 - d1).abs().max()) < 1e-3            # a rigid motion whatever the conditioning
+
+
+@pytest.mark.parametrize("with_mlp", [False, True])
+def test_preprocess_and_molann_on_random_clouds(with_mlp):
+    """PreprocessingANN / MolANN (fused kernels) on random clouds with a 3-atom and a 6-atom selection."""
+    rng = np.random.RandomState(4)
+    n, L = 14, 3000
+    for aidx in ([2, 5, 11], [0, 1, 4, 6, 9, 13]):
+        pos = rng.randn(n, 3).astype(np.float32) * 2
+        spec = S.SystemSpec(
+            name="cloud", positions=pos, input_ix=list(range(n)), align_ix=list(aidx),
+            features=[("p", "position", [0, 3, 5, 8, 11]), ("d", "dihedral", [1, 2, 6, 7]), ("b", "bond", [4, 9]),
+                      ("a", "angle", [10, 12, 13])],
+            use_angle_value=False, layer_dims=[19, 32, 32, 2] if with_mlp else None, noise=0.0, trans_sigma=0.0,
+            rotate=False, seed=1, default_frames=L)
+        model, _ = S.build_model(spec, init_seed=2)
+        x = _clouds(L, n, 40 + len(aidx))
+        ref = torch.from_numpy(pos[aidx])
+        ref = ref - ref.mean(0)
+        _, gap = _conditioning(x, aidx, ref)
+        ok = gap > 0.05
+        feats = [(3, [0, 3, 5, 8, 11]), (2, [1, 2, 6, 7]), (1, [4, 9]), (0, [10, 12, 13])]
+        if with_mlp:
+            sd = model.state_dict()
+            ws = [sd["ann_layers.%dth_layer.weight" % k] for k in (1, 2, 3)]
+            bs = [sd["ann_layers.%dth_layer.bias" % k] for k in (1, 2, 3)]
+            fn = lambda dt: (lambda xx: R.molann_forward(xx, list(aidx), ref.to(dt), feats, False,
+                                                         [w.to(dt) for w in ws], [b.to(dt) for b in bs], "tanh"))
+        else:
+            fn = lambda dt: (lambda xx: R.preprocess_forward(xx, list(aidx), ref.to(dt), feats, False))
+        cot = torch.randn(L, spec.out_dim(), generator=torch.Generator().manual_seed(9))
+        y64, gx64 = oracle_value_and_grad(fn(torch.float64), x, cot)
+        y32, gx32 = oracle_value_and_grad(fn(torch.float32), x, cot, torch.float32)
+        model = model.cuda()
+        xd = x.cuda().requires_grad_(True)
+        y = model(xd)
+        (gx,) = torch.autograd.grad(y, xd, cot.cuda())
+        assert torch.isfinite(y).all() and torch.isfinite(gx).all()
+        what = "cloud %s n_a=%d" % ("molann" if with_mlp else "preprocess", len(aidx))
+        assert_parity(y.detach().cpu()[ok], y64[ok], y32[ok], TOL, what + " y")
+        assert_parity(gx.cpu()[ok], gx64[ok], gx32[ok], TOL, what + " gx")
+        if with_mlp:
+            y2, g2 = model.value_and_grad(x.cuda(), cot.cuda())
+            assert_parity(y2.cpu()[ok], y64[ok], y32[ok], TOL, what + " y (value_and_grad)")
+            assert_parity(g2.cpu()[ok], gx64[ok], gx32[ok], TOL, what + " gx (value_and_grad)")
+
+
+def test_double_backward_is_refused():
+    """The backward kernels carry no autograd history: create_graph=True must fail loudly, not return a constant."""
+    spec = S.get_spec("C2")
+    model, _ = S.build_model(spec)
+    model = model.cuda()
+    x = S.make_frames(spec, 64, device="cuda").requires_grad_(True)
+    y = model(x)
+    with pytest.raises(RuntimeError, match="double backward"):
+        torch.autograd.grad(y.sum(), x, create_graph=True)
+    pp = model.get_preprocessing_layer()
+    with pytest.raises(RuntimeError, match="double backward"):
+        torch.autograd.grad(pp(x).sum(), x, create_graph=True)
+    with pytest.raises(RuntimeError, match="double backward"):
+        torch.autograd.grad(pp.align_layer(x).sum(), x, create_graph=True)
+    (g,) = torch.autograd.grad(model(x).sum(), x)                    # the ordinary backward still works
+    assert torch.isfinite(g).all() and not g.requires_grad
+
+
+def test_value_and_grad_returns_plain_tensors():
+    """No graph is attached to value_and_grad outputs, although the Linear parameters require grad."""
+    from molann_b200.stream import HostPipeline
+    spec = S.get_spec("C2")
+    model, _ = S.build_model(spec)
+    model = model.cuda()
+    assert all(p.requires_grad for p in model.parameters())
+    x = S.make_frames(spec, 500, device="cuda")
+    cot = torch.randn(500, 2, device="cuda")
+    y, gx = model.value_and_grad(x, cot)
+    assert not y.requires_grad and not gx.requires_grad and y.grad_fn is None and gx.grad_fn is None
+    y, gx = model.value_and_grad(x.clone().requires_grad_(True), cot)
+    assert not y.requires_grad and not gx.requires_grad
+    xh, yh = x.cpu().pin_memory(), torch.empty(500, 2).pin_memory()
+    coth, gxh = cot.cpu().pin_memory(), torch.empty(500, 22, 3).pin_memory()
+    pipe = HostPipeline(model, 22, 2, chunk_frames=128)
+    for _ in range(2):
+        pipe.run(xh, yh, coth, gxh)
+    assert not gxh.requires_grad and not yh.requires_grad and gxh.grad_fn is None
+    gxh.numpy()                                                       # raised before the fix
+    assert torch.equal(gxh, gx.cpu()) and torch.equal(yh, y.cpu())    # no extra synchronize needed after run()
+
+
+def test_cotangent_on_wrong_device_or_dtype_raises():
+    spec = S.get_spec("C2")
+    model, _ = S.build_model(spec)
+    model = model.cuda()
+    x = S.make_frames(spec, 16, device="cuda")
+    with pytest.raises(RuntimeError, match="float32"):
+        model.value_and_grad(x, torch.zeros(16, 2, device="cuda", dtype=torch.float64))
+    with pytest.raises(RuntimeError, match="lives on"):
+        model.value_and_grad(x, torch.zeros(16, 2))
+    with pytest.raises(RuntimeError, match="shape"):
+        model.value_and_grad(x, torch.zeros(16, 3, device="cuda"))
+
+
+def test_mutated_ann_layers_fall_back_to_composition():
+    """The fused kernel was chosen for the MLP seen at construction; a later structural change must not be ignored."""
+    from molann_b200 import _lib
+    spec = S.get_spec("C2")
+    model, _ = S.build_model(spec)
+    model = model.cuda()
+    x = S.make_frames(spec, 300, device="cuda")
+    with torch.no_grad():
+        y0 = model(x)
+        model.ann_layers.add_module("squash", torch.nn.Sigmoid().cuda())
+        y1 = model(x)
+        want = model.ann_layers(model.preprocessing_layer(x))
+    assert torch.allclose(y1, want, atol=1e-6) and not torch.allclose(y1, y0, atol=1e-3)
+    yv, gv = model.value_and_grad(x, torch.ones(300, 2, device="cuda"))
+    assert torch.allclose(yv, want, atol=1e-6) and torch.isfinite(gv).all()
+
+
+def test_host_pipeline_against_the_oracle():
+    """End-to-end entry (pinned host buffers in, pinned host buffers out) against the fp64 oracle."""
+    from helpers import oracle_model
+    from molann_b200.stream import HostPipeline
+    spec = S.get_spec("C2")
+    model, _ = S.build_model(spec)
+    sd = model.state_dict()
+    ws = [sd["ann_layers.%dth_layer.weight" % k] for k in (1, 2, 3)]
+    bs = [sd["ann_layers.%dth_layer.bias" % k] for k in (1, 2, 3)]
+    model = model.cuda()
+    L = 5000
+    x = S.make_frames(spec, L, seed=5)
+    cot = torch.randn(L, 2, generator=torch.Generator().manual_seed(2))
+    y64, gx64 = oracle_value_and_grad(oracle_model(spec, ws, bs), x, cot)
+    y32, gx32 = oracle_value_and_grad(oracle_model(spec, ws, bs, torch.float32), x, cot, torch.float32)
+    xh, yh = x.pin_memory(), torch.empty(L, 2).pin_memory()
+    coth, gxh = cot.pin_memory(), torch.empty(L, 22, 3).pin_memory()
+    pipe = HostPipeline(model, 22, 2, chunk_frames=1024)            # 5 chunks, the last one ragged
+    pipe.run(xh, yh)
+    assert_parity(yh, y64, y32, TOL, "pipeline y")
+    yh.zero_()
+    pipe.run(xh, yh, coth, gxh)
+    assert_parity(yh, y64, y32, TOL, "pipeline y (with gradient)")
+    assert_parity(gxh, gx64, gx32, TOL, "pipeline gx")
