@@ -393,6 +393,7 @@ def run_training(args, rank, local_rank, world):
     ms_e = max_over_ranks(1e3 * (time.perf_counter() - t0))
     clocks = sampler.summary()
     sampler.close()
+    h2d_bytes = int(xh.numel() * 4)
     del xh
     if rank != 0:
         return None
@@ -418,7 +419,7 @@ def run_training(args, rank, local_rank, world):
                        "note": "value is the graph replay when used (one launch per step replays gpu_launches / steps "
                                "of our kernels + the decoder's); gpu_launches counts the eager leg",
                        "capture_error": getattr(trainer, "_capture_error", None)},
-        "e2e": {"value": n_global * ke / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(xh.numel() * 4),
+        "e2e": {"value": n_global * ke / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": 4, "steps": ke, "ms_per_step": ms_e / ke, "last_loss": last,
                 "api": "x.copy_(pinned shard); molann_b200.train.AutoencoderStep.step(x); float(loss)"},
     }

@@ -86,7 +86,9 @@ def test_preprocess_and_molann_on_random_clouds(with_mlp):
         ref = torch.from_numpy(pos[aidx])
         ref = ref - ref.mean(0)
         _, gap = _conditioning(x, aidx, ref)
-        ok = gap > 0.05
+        # the rotation's fp32 error grows like eps / gap and the MLP passes it on to outputs that may be small
+        # themselves: the end-to-end 1e-5 claim is made for gap > 0.25, the feature-level one for gap > 0.05
+        ok = gap > (0.25 if with_mlp else 0.05)
         feats = [(3, [0, 3, 5, 8, 11]), (2, [1, 2, 6, 7]), (1, [4, 9]), (0, [10, 12, 13])]
         if with_mlp:
             sd = model.state_dict()
