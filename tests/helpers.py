@@ -71,20 +71,21 @@ def oracle_value_and_grad(fn, x, cot, dtype=torch.float64):
     return y.detach(), gx
 
 
-def frame_rel_err(a, b):
-    """Per-frame max-abs error relative to the per-frame max-abs of the reference value ``b``."""
+def frame_rel_err(a, b, floor=0.0):
+    """Per-frame max-abs error relative to the per-frame max-abs of the reference value ``b`` (never less than
+    ``floor``: for quantities that can pass through zero, e.g. two MLP outputs of a random frame)."""
     a = torch.as_tensor(a).double().reshape(a.shape[0], -1)
     b = torch.as_tensor(b).double().reshape(b.shape[0], -1)
-    denom = b.abs().amax(dim=1).clamp_min(1e-30)
+    denom = b.abs().amax(dim=1).clamp_min(max(floor, 1e-30))
     return ((a - b).abs().amax(dim=1) / denom)
 
 
-def assert_parity(new, ref64, ref32=None, tol=1e-5, what=""):
+def assert_parity(new, ref64, ref32=None, tol=1e-5, what="", floor=0.0):
     """SURVEY 8(c) acceptance: per frame, |new-ref64|/|ref64| <= max(tol, 2 |ref32-ref64|/|ref64|)."""
-    err = frame_rel_err(new, ref64)
+    err = frame_rel_err(new, ref64, floor)
     bound = torch.full_like(err, tol)
     if ref32 is not None:
-        bound = torch.maximum(bound, 2.0 * frame_rel_err(ref32, ref64))
+        bound = torch.maximum(bound, 2.0 * frame_rel_err(ref32, ref64, floor))
     bad = err > bound
     assert not bool(bad.any()), "%s: %d/%d frames out of tolerance, worst %.3e (bound %.3e)" % (
         what, int(bad.sum()), err.numel(), float(err.max()), float(bound[err.argmax()]))

@@ -107,11 +107,14 @@ def test_preprocess_and_molann_on_random_clouds(with_mlp):
         (gx,) = torch.autograd.grad(y, xd, cot.cuda())
         assert torch.isfinite(y).all() and torch.isfinite(gx).all()
         what = "cloud %s n_a=%d" % ("molann" if with_mlp else "preprocess", len(aidx))
-        assert_parity(y.detach().cpu()[ok], y64[ok], y32[ok], TOL, what + " y")
+        # the two MLP outputs of a random cloud can both be ~0 (|y| 0.01 against a typical 0.3, where the reference's
+        # own fp32 answer is 3.5e-5 off in relative terms): measure against at least half the typical magnitude
+        fl = 0.5 * float(y64.abs().amax(dim=1).median()) if with_mlp else 0.0
+        assert_parity(y.detach().cpu()[ok], y64[ok], y32[ok], TOL, what + " y", floor=fl)
         assert_parity(gx.cpu()[ok], gx64[ok], gx32[ok], TOL, what + " gx")
         if with_mlp:
             y2, g2 = model.value_and_grad(x.cuda(), cot.cuda())
-            assert_parity(y2.cpu()[ok], y64[ok], y32[ok], TOL, what + " y (value_and_grad)")
+            assert_parity(y2.cpu()[ok], y64[ok], y32[ok], TOL, what + " y (value_and_grad)", floor=fl)
             assert_parity(g2.cpu()[ok], gx64[ok], gx32[ok], TOL, what + " gx (value_and_grad)")
 
 
