@@ -119,6 +119,32 @@ int molann_b200_align_forward(const MolannPlan* plan, const float* x, int64_t L,
 int molann_b200_align_backward(const MolannPlan* plan, const float* x, const float* gout, int64_t L,
                                float* gx, void* stream);
 
+/* ---- prepared plans (big systems with a wide first layer: BASELINE configs[2], [4]) -------------------------------
+ * Everything that depends only on the plan -- the feature program regrouped in the kernel's operand order and the MLP
+ * weights permuted, split into TF32 hi / lo and laid out per K-chunk for the tensor cores -- is built ONCE into a
+ * caller-owned DEVICE buffer; afterwards MolANN.forward (molann/ann.py:620-624) is ONE persistent kernel per call with
+ * no packing launches (csrc/fused_wide.cuh).  `MolannPrepared` is a small opaque HOST object describing that buffer.
+ *
+ *   molann_b200_prepared_bytes   device bytes the buffer needs (upper bound; 0: the plan is not eligible)
+ *   molann_b200_prepare          builds it.  Copies the feature program to the host once (synchronises `stream`; do
+ *                                not call while capturing a CUDA graph).  MOLANN_ERR_UNSUPPORTED if not eligible.
+ *   molann_b200_prepared_refresh re-packs the weights after the caller changed them (asynchronous, two small kernels)
+ *   molann_b200_prepared_workspace_bytes / molann_b200_forward_prepared   scratch size and the forward itself
+ *   molann_b200_prepared_destroy frees the host object (the device buffer stays the caller's)
+ * The plan passed to the later calls must be the one prepared (same sizes; pointers may have moved only for W / b,
+ * followed by a refresh). */
+typedef struct MolannPrepared MolannPrepared;
+/* 1 if molann_b200_forward_prepared is the kernel of choice for this plan (supported shape and no small-system
+ * fused kernel applies; MOLANN_B200_WIDE = 0 / 1 forces never / whenever the shape is supported), else 0 */
+int molann_b200_wide_eligible(const MolannPlan* plan);
+size_t molann_b200_prepared_bytes(const MolannPlan* plan);
+int molann_b200_prepare(const MolannPlan* plan, void* device_buffer, size_t bytes, void* stream, MolannPrepared** out);
+int molann_b200_prepared_refresh(MolannPrepared* prepared, const MolannPlan* plan, void* stream);
+size_t molann_b200_prepared_workspace_bytes(const MolannPrepared* prepared, int64_t L);
+int molann_b200_forward_prepared(const MolannPrepared* prepared, const MolannPlan* plan, const float* x, int64_t L,
+                                 float* y, void* workspace, size_t workspace_bytes, void* stream);
+void molann_b200_prepared_destroy(MolannPrepared* prepared);
+
 /* Tuning / introspection: which kernel family the dispatcher picks for this plan.
  * 0 = general (warp-per-frame geometry + layered GEMMs), 1 = fused small-system kernel. */
 int molann_b200_path_for(const MolannPlan* plan, int want_backward);

@@ -66,6 +66,16 @@ def cabi():
     lib.molann_b200_preprocess_backward.argtypes = [P, vp, vp, i64, vp, vp]
     lib.molann_b200_align_forward.argtypes = [P, vp, i64, vp, vp]
     lib.molann_b200_align_backward.argtypes = [P, vp, vp, i64, vp, vp]
+    lib.molann_b200_wide_eligible.argtypes = [P]
+    lib.molann_b200_prepared_bytes.restype = sz
+    lib.molann_b200_prepared_bytes.argtypes = [P]
+    lib.molann_b200_prepare.argtypes = [P, vp, sz, vp, ctypes.POINTER(vp)]
+    lib.molann_b200_prepared_refresh.argtypes = [vp, P, vp]
+    lib.molann_b200_prepared_workspace_bytes.restype = sz
+    lib.molann_b200_prepared_workspace_bytes.argtypes = [vp, i64]
+    lib.molann_b200_forward_prepared.argtypes = [vp, P, vp, i64, vp, vp, sz, vp]
+    lib.molann_b200_prepared_destroy.restype = None
+    lib.molann_b200_prepared_destroy.argtypes = [vp]
     _cabi = lib
     return lib
 

@@ -9,11 +9,14 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <new>
+#include <vector>
 
 #include "common.cuh"
 #include "fused_small.cuh"
 #include "fused_tc.cuh"
 #include "fused_ws.cuh"
+#include "fused_wide.cuh"
 #include "gemm_tc.cuh"
 #include "staged_block.cuh"
 #include "small_tile.cuh"
@@ -126,6 +129,8 @@ int pick_tm(int F, int NT, int n_out) {
     if ((F / cands[c]) * nog >= NT) return cands[c];
   return 1;
 }
+
+size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 
 struct Carver {
   int off = 0;
@@ -547,6 +552,183 @@ int run_tc_vg(const TcVgChoice& ch, const DevPlan& dp, const float* x, const flo
 #undef VG_CASE
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// fused wide path (fused_wide.cuh): prepared plans
+// ---------------------------------------------------------------------------------------------
+}  // namespace
+
+struct MolannPrepared {
+  uint32_t magic;
+  // sizes the plan must still have when the handle is used
+  int n_inp, n_align, n_entries, d_feat, n_layers, act, dims[MOLANN_MAX_LAYERS + 1];
+  // kernel-order program
+  int n_pos, n_inv_ent, n_inv, n_units, n_hidden;
+  int nkc1, n1, n1p, nkc2, n2, n2p, nlast, nlastp, kout, kpad;
+  // device pointers into the caller's buffer
+  int* pos_atom;
+  int* inv_ent;
+  int* colmap;
+  float* w1p;
+  float* w2p;
+  float* b1s;
+  float* b2s;
+  float* w3;
+  float* b3;
+};
+
+namespace {
+
+constexpr uint32_t kPreparedMagic = 0x4d4c5750u;   // "MLWP"
+
+// MOLANN_B200_WIDE = 0 never takes the fused wide kernel, = 1 takes it for every plan of a supported shape (tests),
+// default: plans no small-system kernel serves.
+bool wide_shape_ok(const MolannPlan* p) {
+  if (validate_full(p) != MOLANN_OK) return false;
+  const int nl = p->n_layers;
+  if (nl != 2 && nl != 3) return false;
+  if (p->dims[1] > FW_NMAX) return false;
+  if (nl == 3 && p->dims[2] > FW_NMAX) return false;
+  if (p->dims[nl] > 8) return false;
+  if (12LL * p->n_inp + 64 > 100 * 1024) return false;          // two frames must fit next to the operand ring
+  return true;
+}
+
+struct WideCounts {
+  int n_pos = 0, n_inv_ent = 0, n_inv = 0, n_units = 0;
+};
+int wide_units(int n_pos, int n_inv) { return n_pos + (n_inv > n_pos ? (n_inv - n_pos + 3) / 4 : 0); }
+
+size_t wide_prepared_bytes_for(const MolannPlan* p, int n_pos_max, int n_inv_ent_max, int n_units_max) {
+  const int nl = p->n_layers;
+  const int n1p = round_up(p->dims[1], 16);
+  const int nkc1 = (n_units_max + FW_KU - 1) / FW_KU;
+  size_t b = 0;
+  b += align256((size_t)n_pos_max * 4);
+  b += align256((size_t)n_inv_ent_max * ENTRY_INTS * 4);
+  b += align256((size_t)nkc1 * FW_KC * 4);                                  // colmap
+  b += align256((size_t)nkc1 * 2 * FW_KC * n1p * 4);                        // w1p
+  b += align256((size_t)n1p * 4);
+  if (nl == 3) {
+    const int n2p = round_up(p->dims[2], 16);
+    b += align256((size_t)(n1p / FW_KC) * 2 * FW_KC * n2p * 4);             // w2p
+    b += align256((size_t)n2p * 4);
+    b += align256((size_t)p->dims[nl] * n2p * 4);
+  } else {
+    b += align256((size_t)p->dims[nl] * n1p * 4);
+  }
+  b += align256((size_t)p->dims[nl] * 4);
+  return b;
+}
+
+int wide_pack_weights(const MolannPrepared* h, const MolannPlan* p, cudaStream_t st) {
+  const float scale = ws_scale_for_act(p->act_id);
+  {
+    const long long total = (long long)h->n1p * h->kpad;
+    unsigned blocks = (unsigned)((total + 255) / 256);
+    if (blocks > 2048u) blocks = 2048u;
+    fw_pack_kernel<<<blocks, 256, 0, st>>>(p->W[0], p->d_feat, h->n1, h->colmap, h->kpad, h->n1p, scale, h->w1p);
+    int s = post_launch();
+    if (s) return s;
+  }
+  if (h->n_hidden == 2) {
+    const long long total = (long long)h->n2p * h->n1p;
+    unsigned blocks = (unsigned)((total + 255) / 256);
+    if (blocks > 2048u) blocks = 2048u;
+    fw_pack_kernel<<<blocks, 256, 0, st>>>(p->W[1], h->n1, h->n2, nullptr, h->n1p, h->n2p, scale, h->w2p);
+    int s = post_launch();
+    if (s) return s;
+  }
+  const int last = p->n_layers - 1;
+  fw_pack_small_kernel<<<8, 256, 0, st>>>(p->b[0], h->n1, h->n1p, scale, h->b1s,
+                                         h->n_hidden == 2 ? p->b[1] : nullptr, h->n2, h->n2p, scale, h->b2s,
+                                         p->W[last], h->kout, h->nlast, h->nlastp, h->w3, p->b[last], h->b3);
+  return post_launch();
+}
+
+bool prepared_matches(const MolannPrepared* h, const MolannPlan* p) {
+  if (!h || h->magic != kPreparedMagic || !p) return false;
+  if (h->n_inp != p->n_inp || h->n_align != p->n_align || h->n_entries != p->n_entries || h->d_feat != p->d_feat ||
+      h->n_layers != p->n_layers || h->act != p->act_id)
+    return false;
+  for (int k = 0; k <= p->n_layers; ++k)
+    if (h->dims[k] != p->dims[k]) return false;
+  return true;
+}
+
+struct WideChoice {
+  bool ok = false;
+  FwParams P;
+  long long grid = 0;
+};
+
+// shared-memory layout and scratch geometry for L frames.  MOLANN_B200_WIDE_STAGES / _RING / _SLOTS override the
+// operand-ring depth, the frame-ring depth and the scratch sub-tiles per CTA.
+WideChoice choose_wide(const MolannPrepared* h, const MolannPlan* p, long long L, const DeviceInfo& dev) {
+  WideChoice ch;
+  FwParams& P = ch.P;
+  std::memset(&P, 0, sizeof(P));
+  P.pos_atom = h->pos_atom; P.align_idx = p->align_idx; P.ref_x = p->ref_x; P.inv_ent = h->inv_ent;
+  P.n_inp = p->n_inp; P.n_align = p->n_align; P.n_pos = h->n_pos; P.n_inv_ent = h->n_inv_ent; P.n_inv = h->n_inv;
+  P.n_units = h->n_units; P.use_angle = p->use_angle_value;
+  P.n_hidden = h->n_hidden; P.nkc1 = h->nkc1; P.n1p = h->n1p; P.nkc2 = h->nkc2; P.n2p = h->n2p;
+  P.nlastp = h->nlastp; P.kout = h->kout;
+  P.w1p = h->w1p; P.w2p = h->w2p; P.b1s = h->b1s; P.b2s = h->b2s; P.w3 = h->w3; P.b3 = h->b3;
+  P.slot_floats = FW_HDR_FLOATS + h->nkc1 * FW_CHUNK_FLOATS;
+  int slots = env_int("MOLANN_B200_WIDE_SLOTS", 6);
+  if (slots < 5) slots = 5;                       // a tile (4 sub-tiles) + at least one the geometry can run ahead in
+  if (slots > FW_MAX_SLOTS) slots = FW_MAX_SLOTS;
+  P.n_slots = slots;
+  P.cta_floats = (long long)slots * P.slot_floats;
+  P.ring_slot_bytes = round_up(12 * p->n_inp + 32, 128);
+  Carver c;
+  c.take((int)sizeof(FwBars), 16);
+  P.off_b1 = c.take(h->n1p * 4, 16);
+  P.off_b2 = c.take((h->n_hidden == 2 ? h->n2p : 1) * 4, 16);
+  P.off_w3 = c.take(h->kout * h->nlastp * 4, 16);
+  P.off_ypart = c.take(4 * FW_M * h->kout * 4, 16);
+  const int fixed = c.off;
+  // operand stages and the frame ring share what is left; plan tables move in when there is room
+  int stages = env_int("MOLANN_B200_WIDE_STAGES", 2);
+  if (stages < 2) stages = 2;
+  if (stages > FW_MAX_STAGES) stages = FW_MAX_STAGES;
+  int ring = env_int("MOLANN_B200_WIDE_RING", 4);
+  if (ring > FW_MAX_RING) ring = FW_MAX_RING;
+  const int budget = dev.max_smem_optin;
+  auto need = [&](int st, int rg) { return round_up(fixed, 1024) + st * FW_STAGE_BYTES + rg * P.ring_slot_bytes; };
+  while (ring > 2 && need(stages, ring) > budget) --ring;
+  while (stages > 2 && need(stages, ring) > budget) --stages;
+  if (ring < 2 || need(stages, ring) > budget) return ch;
+  P.n_stages = stages;
+  P.n_ring = ring;
+  P.off_stage = c.take(stages * FW_STAGE_BYTES, 1024);
+  P.off_ring = c.take(ring * P.ring_slot_bytes, 128);
+  P.off_pos = P.off_aidx = P.off_ref = P.off_ent = -1;
+  if (c.off + h->n_inv_ent * ENTRY_INTS * 4 + 16 <= budget && h->n_inv_ent > 0)
+    P.off_ent = c.take(h->n_inv_ent * ENTRY_INTS * 4, 16);
+  if (c.off + p->n_align * 16 + 32 <= budget && p->n_align > 0) {
+    P.off_aidx = c.take(p->n_align * 4, 16);
+    P.off_ref = c.take(p->n_align * 12, 16);
+  }
+  if (c.off + h->n_pos * 4 + 16 <= budget && h->n_pos > 0) P.off_pos = c.take(h->n_pos * 4, 16);
+  P.total_smem = round_up(c.off, 128);
+  if (P.total_smem > budget) return ch;
+  const long long ntiles = (L + FW_M - 1) / FW_M;
+  ch.grid = dev.sm_count < ntiles ? dev.sm_count : ntiles;
+  if (ch.grid < 1) ch.grid = 1;
+  ch.ok = true;
+  return ch;
+}
+
+template <int ACT>
+int launch_wide_act(const WideChoice& ch, const float* x, float* y, long long L, cudaStream_t st) {
+  auto kern = fused_wide_forward_kernel<ACT>;
+  int s = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ch.P.total_smem));
+  if (s) return s;
+  kern<<<(unsigned)ch.grid, FW_THREADS, ch.P.total_smem, st>>>(ch.P, x, y, L);
+  return post_launch();
+}
+
 #define SMALL_DISPATCH(ch, FN, ...)                                   \
   ((ch).F == 128 ? ((ch).NT == 256 ? FN<128, 256>(__VA_ARGS__) : FN<128, 128>(__VA_ARGS__)) \
                  : ((ch).NT == 256 ? FN<64, 256>(__VA_ARGS__) : FN<64, 128>(__VA_ARGS__)))
@@ -581,7 +763,6 @@ int max_dim(const MolannPlan* p) {
   return m;
 }
 
-size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 
 // scratch for the packed (TF32 hi/lo, chunk-major) weights of ONE tensor-core GEMM; packed right before each use
 size_t gemm_pack_bytes(const MolannPlan* p) {
@@ -1130,6 +1311,160 @@ int molann_b200_value_and_grad(const MolannPlan* plan, const float* x, const flo
   }
   // layered path: ONE pass -- the backward's forward recompute also writes y
   return general_backward(plan, x, gy, L, gx, nullptr, nullptr, workspace, workspace_bytes, dev, st, y);
+}
+
+// ---- prepared plans (fused wide kernel) ----
+int molann_b200_wide_eligible(const MolannPlan* plan) {
+  if (!wide_shape_ok(plan)) return 0;
+  const int mode = env_int("MOLANN_B200_WIDE", -1);
+  if (mode == 0 || env_int("MOLANN_B200_TC", 1) == 0) return 0;
+  if (mode == 1) return 1;
+  if (env_int("MOLANN_B200_PATH", -1) == 0) return 0;             // tests forcing the layered path
+  return molann_b200_kernel_family(plan, 0) == 0 ? 1 : 0;
+}
+
+size_t molann_b200_prepared_bytes(const MolannPlan* plan) {
+  if (!wide_shape_ok(plan)) return 0;
+  // the program lives in device memory: bound its regrouped size from the plan's scalar fields
+  const int n_units_max = plan->n_entries + (plan->d_feat + 3) / 4 + 1;
+  return wide_prepared_bytes_for(plan, plan->n_entries, plan->n_entries, n_units_max);
+}
+
+int molann_b200_prepare(const MolannPlan* plan, void* device_buffer, size_t bytes, void* stream,
+                        MolannPrepared** out) {
+  if (!out) return MOLANN_ERR_NULL;
+  *out = nullptr;
+  int s = validate_full(plan);
+  if (s) return s;
+  if (!wide_shape_ok(plan)) return MOLANN_ERR_UNSUPPORTED;
+  if (!device_buffer) return MOLANN_ERR_NULL;
+  if (bytes < molann_b200_prepared_bytes(plan)) return MOLANN_ERR_WORKSPACE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // the feature program, regrouped on the host: position atoms first (one 16-byte unit each), invariant features after
+  std::vector<int32_t> ent((size_t)plan->n_entries * ENTRY_INTS);
+  s = check_cuda(cudaMemcpyAsync(ent.data(), plan->entries, ent.size() * 4, cudaMemcpyDeviceToHost, st));
+  if (s) return s;
+  s = check_cuda(cudaStreamSynchronize(st));
+  if (s) return s;
+  std::vector<int32_t> pos_atom, pos_col, inv_ent, inv_col;
+  const int inv_dim_dihedral = plan->use_angle_value ? 1 : 2;
+  for (int e = 0; e < plan->n_entries; ++e) {
+    const int32_t* en = &ent[(size_t)e * ENTRY_INTS];
+    if (en[0] == MOLANN_FEAT_POSITION) {
+      pos_atom.push_back(en[1]);
+      pos_col.push_back(en[5]);
+    } else {
+      const int dim = en[0] == MOLANN_FEAT_DIHEDRAL ? inv_dim_dihedral : 1;
+      for (int q = 0; q < 5; ++q) inv_ent.push_back(en[q]);
+      inv_ent.push_back((int32_t)inv_col.size());               // first invariant column of this entry
+      for (int q = 0; q < dim; ++q) inv_col.push_back(en[5] + q);
+    }
+    for (int q = 1; q <= 4; ++q)
+      if (en[q] < 0 || en[q] >= plan->n_inp) return MOLANN_ERR_PLAN;
+  }
+  MolannPrepared* h = new (std::nothrow) MolannPrepared;
+  if (!h) return MOLANN_ERR_NULL;
+  std::memset(h, 0, sizeof(*h));
+  h->magic = kPreparedMagic;
+  h->n_inp = plan->n_inp; h->n_align = plan->n_align; h->n_entries = plan->n_entries; h->d_feat = plan->d_feat;
+  h->n_layers = plan->n_layers; h->act = plan->act_id;
+  for (int k = 0; k <= plan->n_layers; ++k) h->dims[k] = plan->dims[k];
+  h->n_pos = (int)pos_atom.size();
+  h->n_inv_ent = (int)inv_ent.size() / ENTRY_INTS;
+  h->n_inv = (int)inv_col.size();
+  h->n_units = wide_units(h->n_pos, h->n_inv);
+  h->nkc1 = (h->n_units + FW_KU - 1) / FW_KU;
+  if (h->nkc1 < 1) h->nkc1 = 1;
+  h->kpad = h->nkc1 * FW_KC;
+  h->n_hidden = plan->n_layers - 1;
+  h->n1 = plan->dims[1]; h->n1p = round_up(h->n1, 16);
+  h->n2 = h->n_hidden == 2 ? plan->dims[2] : 0; h->n2p = h->n_hidden == 2 ? round_up(h->n2, 16) : 16;
+  h->nkc2 = h->n_hidden == 2 ? h->n1p / FW_KC : 0;
+  h->nlast = h->n_hidden == 2 ? h->n2 : h->n1;
+  h->nlastp = h->n_hidden == 2 ? h->n2p : h->n1p;
+  h->kout = plan->dims[plan->n_layers];
+  // internal K index -> original feature column (-1: padding)
+  std::vector<int32_t> colmap((size_t)h->kpad, -1);
+  for (int u = 0; u < h->n_pos; ++u)
+    for (int q = 0; q < 3; ++q) colmap[(size_t)4 * u + q] = pos_col[u] + q;
+  for (int v = 0; v < h->n_inv; ++v) colmap[(size_t)(v < h->n_pos ? 4 * v + 3 : 3 * h->n_pos + v)] = inv_col[v];
+  // carve the caller's buffer
+  char* base = static_cast<char*>(device_buffer);
+  auto take = [&](size_t nbytes) { char* r = base; base += align256(nbytes); return r; };
+  h->pos_atom = reinterpret_cast<int*>(take((size_t)h->n_pos * 4));
+  h->inv_ent = reinterpret_cast<int*>(take((size_t)h->n_inv_ent * ENTRY_INTS * 4));
+  h->colmap = reinterpret_cast<int*>(take((size_t)h->kpad * 4));
+  h->w1p = reinterpret_cast<float*>(take((size_t)h->nkc1 * 2 * FW_KC * h->n1p * 4));
+  h->b1s = reinterpret_cast<float*>(take((size_t)h->n1p * 4));
+  if (h->n_hidden == 2) {
+    h->w2p = reinterpret_cast<float*>(take((size_t)h->nkc2 * 2 * FW_KC * h->n2p * 4));
+    h->b2s = reinterpret_cast<float*>(take((size_t)h->n2p * 4));
+  }
+  h->w3 = reinterpret_cast<float*>(take((size_t)h->kout * h->nlastp * 4));
+  h->b3 = reinterpret_cast<float*>(take((size_t)h->kout * 4));
+  if ((size_t)(base - static_cast<char*>(device_buffer)) > bytes) { delete h; return MOLANN_ERR_WORKSPACE; }
+  cudaError_t ce = cudaSuccess;
+  if (h->n_pos) ce = cudaMemcpyAsync(h->pos_atom, pos_atom.data(), pos_atom.size() * 4, cudaMemcpyHostToDevice, st);
+  if (ce == cudaSuccess && h->n_inv_ent)
+    ce = cudaMemcpyAsync(h->inv_ent, inv_ent.data(), inv_ent.size() * 4, cudaMemcpyHostToDevice, st);
+  if (ce == cudaSuccess)
+    ce = cudaMemcpyAsync(h->colmap, colmap.data(), colmap.size() * 4, cudaMemcpyHostToDevice, st);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);          // the host vectors go out of scope below
+  if (ce != cudaSuccess) { delete h; return check_cuda(ce); }
+  s = wide_pack_weights(h, plan, st);
+  if (s) { delete h; return s; }
+  *out = h;
+  return MOLANN_OK;
+}
+
+int molann_b200_prepared_refresh(MolannPrepared* prepared, const MolannPlan* plan, void* stream) {
+  if (!prepared || !plan) return MOLANN_ERR_NULL;
+  int s = validate_full(plan);
+  if (s) return s;
+  if (!prepared_matches(prepared, plan)) return MOLANN_ERR_PLAN;
+  return wide_pack_weights(prepared, plan, static_cast<cudaStream_t>(stream));
+}
+
+size_t molann_b200_prepared_workspace_bytes(const MolannPrepared* prepared, int64_t L) {
+  if (!prepared || prepared->magic != kPreparedMagic || L <= 0) return 0;
+  DeviceInfo dev = device_info();
+  if (!dev.ok) dev.sm_count = 148;
+  const long long ntiles = (L + FW_M - 1) / FW_M;
+  const long long grid = dev.sm_count < ntiles ? dev.sm_count : ntiles;
+  const long long slot_floats = FW_HDR_FLOATS + (long long)prepared->nkc1 * FW_CHUNK_FLOATS;
+  return (size_t)grid * FW_MAX_SLOTS * slot_floats * 4;
+}
+
+int molann_b200_forward_prepared(const MolannPrepared* prepared, const MolannPlan* plan, const float* x, int64_t L,
+                                 float* y, void* workspace, size_t workspace_bytes, void* stream) {
+  int s = validate_full(plan);
+  if (s) return s;
+  if (!prepared_matches(prepared, plan)) return MOLANN_ERR_PLAN;
+  if (L < 0) return MOLANN_ERR_PLAN;
+  if (L == 0) return MOLANN_OK;
+  if (!x || !y) return MOLANN_ERR_NULL;
+  if (misaligned4(x) || misaligned4(y)) return MOLANN_ERR_ALIGNMENT;
+  const DeviceInfo dev = device_info();
+  if (!dev.ok) return MOLANN_ERR_CUDA;
+  WideChoice ch = choose_wide(prepared, plan, (long long)L, dev);
+  if (!ch.ok) return MOLANN_ERR_UNSUPPORTED;
+  const size_t need = (size_t)ch.grid * (size_t)ch.P.cta_floats * 4;
+  if (!workspace || workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 15u)) return MOLANN_ERR_WORKSPACE;
+  ch.P.scratch = static_cast<float*>(workspace);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (plan->act_id) {
+    case MOLANN_ACT_TANH: return launch_wide_act<ACT_TANH>(ch, x, y, (long long)L, st);
+    case MOLANN_ACT_RELU: return launch_wide_act<ACT_RELU>(ch, x, y, (long long)L, st);
+    case MOLANN_ACT_SIGMOID: return launch_wide_act<ACT_SIGMOID>(ch, x, y, (long long)L, st);
+    default: return launch_wide_act<ACT_IDENTITY>(ch, x, y, (long long)L, st);
+  }
+}
+
+void molann_b200_prepared_destroy(MolannPrepared* prepared) {
+  if (prepared && prepared->magic == kPreparedMagic) {
+    prepared->magic = 0;
+    delete prepared;
+  }
 }
 
 int molann_b200_preprocess_forward(const MolannPlan* plan, const float* x, int64_t L, float* feat, void* stream) {

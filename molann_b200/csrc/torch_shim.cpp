@@ -18,6 +18,8 @@
 #include <nvtx3/nvToolsExt.h>
 
 #include <cstring>
+#include <list>
+#include <mutex>
 #include <tuple>
 #include <vector>
 
@@ -133,6 +135,78 @@ void fill_mlp(PlanHolder& h, const Tensor& x, at::TensorList params, int64_t act
 void* cur_stream() { return static_cast<void*>(at::cuda::getCurrentCUDAStream().stream()); }
 
 // ------------------------------------------------------------------------------------------
+// prepared plans (include/molann_b200.h): built on first use of a (feature program, MLP) pair and kept in a small
+// LRU; when only the weights changed (training: a new `_version`, or new storage) they are re-packed in place.
+// ------------------------------------------------------------------------------------------
+struct PreparedEntry {
+  int device = -1;
+  const void* entries = nullptr;
+  const void* align = nullptr;
+  const void* ref = nullptr;
+  int64_t n_inp = 0, d_feat = 0, act = 0;
+  bool use_angle = false;
+  std::vector<const void*> param_ptr;
+  std::vector<int64_t> param_version;
+  std::vector<int64_t> dims;
+  Tensor buffer;
+  MolannPrepared* handle = nullptr;
+  ~PreparedEntry() { molann_b200_prepared_destroy(handle); }
+};
+std::mutex g_prepared_mutex;
+std::list<std::shared_ptr<PreparedEntry>> g_prepared;          // most recently used first
+constexpr size_t kPreparedCacheSize = 16;
+
+std::shared_ptr<PreparedEntry> prepared_for(const PlanHolder& h, const Tensor& x, const Tensor& entries,
+                                            const Tensor& align_idx, const Tensor& ref_x, at::TensorList params,
+                                            int64_t act, bool use_angle_value) {
+  std::lock_guard<std::mutex> lock(g_prepared_mutex);
+  const int device = x.get_device();
+  std::vector<int64_t> dims(h.plan.dims, h.plan.dims + h.plan.n_layers + 1);
+  for (auto it = g_prepared.begin(); it != g_prepared.end(); ++it) {
+    PreparedEntry& e = **it;
+    if (e.device != device || e.entries != entries.data_ptr() || e.n_inp != h.plan.n_inp || e.d_feat != h.plan.d_feat ||
+        e.act != act || e.use_angle != use_angle_value || e.dims != dims ||
+        e.align != (align_idx.numel() ? align_idx.data_ptr() : nullptr) ||
+        e.ref != (ref_x.numel() ? ref_x.data_ptr() : nullptr))
+      continue;
+    bool same_weights = e.param_ptr.size() == params.size();
+    for (size_t i = 0; same_weights && i < params.size(); ++i)
+      same_weights = e.param_ptr[i] == params[i].data_ptr() && e.param_version[i] == (int64_t)params[i]._version();
+    if (!same_weights) {
+      check_status(molann_b200_prepared_refresh(e.handle, &h.plan, cur_stream()), "prepared_refresh");
+      e.param_ptr.clear();
+      e.param_version.clear();
+      for (const Tensor& p : params) {
+        e.param_ptr.push_back(p.data_ptr());
+        e.param_version.push_back((int64_t)p._version());
+      }
+    }
+    auto keep = *it;
+    g_prepared.erase(it);
+    g_prepared.push_front(keep);
+    return keep;
+  }
+  auto e = std::make_shared<PreparedEntry>();
+  e->device = device;
+  e->entries = entries.data_ptr();
+  e->align = align_idx.numel() ? align_idx.data_ptr() : nullptr;
+  e->ref = ref_x.numel() ? ref_x.data_ptr() : nullptr;
+  e->n_inp = h.plan.n_inp; e->d_feat = h.plan.d_feat; e->act = act; e->use_angle = use_angle_value;
+  e->dims = dims;
+  for (const Tensor& p : params) {
+    e->param_ptr.push_back(p.data_ptr());
+    e->param_version.push_back((int64_t)p._version());
+  }
+  const size_t bytes = molann_b200_prepared_bytes(&h.plan);
+  TORCH_CHECK(bytes > 0, "molann_b200: plan is not eligible for the prepared path");
+  e->buffer = at::empty({static_cast<int64_t>(bytes)}, x.options().dtype(at::kByte));
+  check_status(molann_b200_prepare(&h.plan, e->buffer.data_ptr(), bytes, cur_stream(), &e->handle), "prepare");
+  g_prepared.push_front(e);
+  while (g_prepared.size() > kPreparedCacheSize) g_prepared.pop_back();
+  return e;
+}
+
+// ------------------------------------------------------------------------------------------
 // raw (non-differentiable) implementations
 // ------------------------------------------------------------------------------------------
 Tensor align_fwd_impl(const Tensor& x, const Tensor& align_idx, const Tensor& ref_x) {
@@ -207,6 +281,16 @@ Tensor molann_fwd_impl(const Tensor& x, const Tensor& align_idx, const Tensor& r
   Tensor ws;
   void* wsp = nullptr;
   size_t ws_bytes = 0;
+  if (L > 0 && molann_b200_wide_eligible(&h.plan)) {
+    // big system, wide first layer: ONE persistent kernel on a prepared plan (csrc/fused_wide.cuh)
+    auto prep = prepared_for(h, x, entries, align_idx, ref_x, params, act, use_angle_value);
+    ws_bytes = molann_b200_prepared_workspace_bytes(prep->handle, L);
+    ws = at::empty({static_cast<int64_t>(ws_bytes)}, x.options().dtype(at::kByte));
+    check_status(molann_b200_forward_prepared(prep->handle, &h.plan, x.data_ptr<float>(), L, y.data_ptr<float>(),
+                                              ws.data_ptr(), ws_bytes, cur_stream()),
+                 "forward_prepared");
+    return y;
+  }
   if (molann_b200_path_for(&h.plan, 0) != 1) {
     ws_bytes = molann_b200_workspace_bytes(&h.plan, L, 0);
     ws = at::empty({static_cast<int64_t>(ws_bytes)}, x.options().dtype(at::kByte));

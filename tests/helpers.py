@@ -144,6 +144,41 @@ class CPlan(object):
                                                 self._stream()), "forward")
         return y
 
+    def prepare(self):
+        """Build the prepared plan (include/molann_b200.h) once; returns the opaque handle."""
+        from molann_b200 import _lib
+        if getattr(self, "_prep", None):
+            return self._prep
+        n = self.lib.molann_b200_prepared_bytes(ctypes.byref(self.p))
+        assert n > 0, "plan not eligible for the prepared (wide) path"
+        self._prep_buf = torch.empty(n, dtype=torch.uint8, device=self.device)
+        h = ctypes.c_void_p()
+        _lib.check(self.lib.molann_b200_prepare(ctypes.byref(self.p), self._prep_buf.data_ptr(), n, self._stream(),
+                                                ctypes.byref(h)), "prepare")
+        self._prep = h
+        return h
+
+    def forward_prepared(self, x):
+        from molann_b200 import _lib
+        h = self.prepare()
+        L = x.shape[0]
+        y = torch.empty(L, self.p.dims[self.p.n_layers], device=self.device)
+        n = self.lib.molann_b200_prepared_workspace_bytes(h, L)
+        ws = torch.empty(max(n, 1), dtype=torch.uint8, device=self.device)
+        _lib.check(self.lib.molann_b200_forward_prepared(h, ctypes.byref(self.p), x.data_ptr(), L, y.data_ptr(),
+                                                         ws.data_ptr(), n, self._stream()), "forward_prepared")
+        return y
+
+    def refresh(self):
+        from molann_b200 import _lib
+        _lib.check(self.lib.molann_b200_prepared_refresh(self.prepare(), ctypes.byref(self.p), self._stream()),
+                   "prepared_refresh")
+
+    def __del__(self):
+        if getattr(self, "_prep", None):
+            self.lib.molann_b200_prepared_destroy(self._prep)
+            self._prep = None
+
     def backward(self, x, gy, want_params=False):
         from molann_b200 import _lib
         L = x.shape[0]

@@ -83,6 +83,30 @@ def test_dispatch_table_and_workspace():
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_wide_path_eligibility(monkeypatch):
+    """Big systems with a wide first layer take the prepared (fused wide) forward; small ones keep their kernels."""
+    lib = _lib.cabi()
+    for k in list(os.environ):
+        if k.startswith("MOLANN_B200_"):
+            monkeypatch.delenv(k, raising=False)
+    for name, want in (("C1", 0), ("C2", 0), ("C3", 1), ("C5", 1)):
+        p = host_plan(S.get_spec(name))
+        assert lib.molann_b200_wide_eligible(ctypes.byref(p)) == want, name
+    p = host_plan(S.get_spec("C3"))
+    nbytes = lib.molann_b200_prepared_bytes(ctypes.byref(p))
+    assert 800 * 256 * 8 < nbytes < 64 << 20              # hi + lo copies of W1 and some tables
+    monkeypatch.setenv("MOLANN_B200_WIDE", "0")
+    assert lib.molann_b200_wide_eligible(ctypes.byref(p)) == 0
+    monkeypatch.setenv("MOLANN_B200_WIDE", "1")
+    assert lib.molann_b200_wide_eligible(ctypes.byref(host_plan(S.get_spec("C2")))) == 1
+    four = host_plan(S.get_spec("C2"), n_layers=None)
+    four.n_layers = 4
+    four.dims[4] = 2
+    four.W[3], four.b[3] = 0x9000, 0x9100
+    assert lib.molann_b200_wide_eligible(ctypes.byref(four)) == 0     # three hidden layers: not this kernel
+    assert lib.molann_b200_prepared_workspace_bytes(None, 100) == 0
+
+
 def test_compute_entry_points_fail_without_gpu():
     lib = _lib.cabi()
     p = host_plan(S.get_spec("C2"))
