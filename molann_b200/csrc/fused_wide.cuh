@@ -18,8 +18,9 @@
 //      rigid-motion invariant and final as soon as they are computed.
 //   2. A PER-CTA TRANSPOSITION SCRATCH IN L2.  Each CTA owns a small ring of 32-frame sub-tiles in global memory
 //      (C3: 5 x 104 KB per CTA, 77 MB for the chip -- it is overwritten every tile, so it lives in the 126 MB L2 and
-//      DRAM never sees it; x streams through with no reuse).  Geometry warps write frame rows, converter warps read
-//      K-chunks.  Layout per sub-tile: [32 rows x 16 header floats][chunk][32 rows][16 floats].
+//      DRAM never sees it; x streams through with no reuse).  A geometry warp builds a frame's row in a shared-memory
+//      staging buffer and sends it out with ONE asynchronous bulk store (no release stall on scattered global stores);
+//      converter threads read 64 bytes of their row per K-chunk.  Row = [16 header floats][units].
 // Internal feature order ("units" of 4 floats = 16 bytes, the K-major granule of the tensor-core operand): unit u <
 // n_pos = (x, y, z of position atom u, invariant feature u); further invariant features follow four per unit.  With
 // as many invariant columns as position atoms (C3, C5) K stays exactly d.  The first layer's weights are permuted,
@@ -28,23 +29,28 @@
 //
 // Roles (28 warps, persistent CTA per SM, everything hands over through mbarriers):
 //   X producer (1 warp)   cp.async.bulk of whole frames into a shared-memory ring
-//   geometry   (4 warps)  warp = frame: pivoted moments (warp-shuffle sums), raw position atoms, invariant features
-//                         -> scratch sub-tile;  no rotation here
+//   geometry   (4 warps)  the four warps share ONE frame at a time (thread = alignment atom / position atom /
+//                         invariant entry): pivoted moments (shuffle + fixed-order sum), raw position atoms,
+//                         invariant features -> staging row -> scratch sub-tile;  no rotation here
 //   converter  (4 warps)  thread = frame: quaternion rotation from the moments (polynomial fast path / Jacobi
 //                         fallback, geometry.cuh) once per tile, then per K-chunk: 64 bytes from the scratch ->
 //                         (p - c) R -> TF32 hi / lo (round to nearest) -> canonical K-major operand tile in smem
 //   W producer (1 warp)   cp.async.bulk of the pre-packed weight block of each chunk (layer 1, then layer 2)
-//   MMA        (1 warp)   elected lane: tcgen05.mma 3xTF32, SS form, M = 128, N = N1 (layer 1) / N2 (layer 2), K = 8;
-//                         32-wide K segments into alternating TMEM accumulators (the tensor core truncates its fp32
-//                         accumulator at every step: long sums in one accumulator cost 1e-5, gemm_tc.cuh)
+//   MMA        (1 warp)   elected lane: tcgen05.mma 3xTF32, SS form, M = 128, N = N1 (layer 1) / N2 (layer 2), K = 8.
+//                         Layer 1: 32-wide K segments into two alternating 256-column TMEM accumulators (the tensor
+//                         core truncates its fp32 accumulator at every step: long sums in one accumulator cost 1e-5,
+//                         gemm_tc.cuh).  Layer 2 (K <= 256): the four chunks of one epilogue warpgroup go into one of
+//                         four 128-column accumulators (two of 256 when N2 > 128) -- 24 steps each and no drain
+//                         between its MMAs, so the epilogue can hand all of h1 over before it reads anything back
 //   epilogue   (16 warps) thread = row x 64 columns: fp32 sum of the segments in registers, bias + activation, the
-//                         activations go straight back into the operand ring as layer 2's A chunks (hi / lo), second
-//                         round of sums, activation, last (narrow) layer as register dot products, y.
+//                         activations go straight back into the operand ring as layer 2's A chunks (hi / lo), sum of
+//                         the layer-2 accumulators, activation, last (narrow) layer as register dot products, y.
 #pragma once
 #include "common.cuh"
 #include "fused_tc.cuh"
 #include "fused_ws.cuh"
 #include "geometry.cuh"
+#include "staged_block.cuh"
 #include "tc.cuh"
 
 namespace molann {
@@ -56,17 +62,35 @@ constexpr int FW_KC = 4 * FW_KU;          // K per chunk
 constexpr int FW_SEGC = 2;                // chunks per accumulation segment (32 K = 12 MMA steps)
 constexpr int FW_NMAX = 256;              // widest tensor-core layer
 constexpr int FW_CW = 64;                 // accumulator columns per epilogue thread
-constexpr int FW_WARPS = 28;
+constexpr int FW_WARPS = 32;
 constexpr int FW_THREADS = FW_WARPS * 32;
 constexpr int FW_W_EPI = 4, FW_W_WPROD = 20, FW_W_MMA = 21, FW_W_XPROD = 22, FW_W_GEO = 24;
-constexpr int FW_NGW = 4;                 // geometry warps
-// setmaxnreg budgets; pool = 896 threads x 72 registers = 64512 = 32 x (4 x 72 + 16 x 88 + 4 x 24 + 4 x 56)
-constexpr int FW_REGS_CONV = 72, FW_REGS_EPI = 88, FW_REGS_CTRL = 24, FW_REGS_GEO = 56;
+constexpr int FW_NGW = 4;                 // geometry warps per group (one group works on one frame)
+constexpr int FW_NGG = 2;                 // geometry groups (alternate frames)
+// setmaxnreg budgets; pool = 1024 threads x 64 registers = 65536 = 32 x (4 x 56 + 16 x 80 + 4 x 24 + 8 x 56).  The
+// geometry role bounds the kernel (tests/cuda/fw_trace.cu), so it gets two groups of spill-free warps; the MMA chain
+// has slack and pays for it with a few spill reloads per chunk.
+constexpr int FW_REGS_CONV = 56, FW_REGS_EPI = 80, FW_REGS_CTRL = 24, FW_REGS_GEO = 56;
+static_assert(4 * FW_REGS_CONV + 16 * FW_REGS_EPI + 4 * FW_REGS_CTRL + 4 * FW_REGS_GEO <= 28 * 72, "register pool");
+constexpr uint32_t FW_PIECE = 2048;      // bytes per bulk copy of the frame ring
+constexpr int FW_REGS_LAUNCH = 72;        // 65536 / 896 rounded down to a multiple of 8: what the CTA starts with
 constexpr int FW_A_HALF = FW_M * FW_KC * 4;                               // one of hi / lo: 8 KB
 constexpr int FW_STAGE_BYTES = 2 * FW_A_HALF + 2 * FW_NMAX * FW_KC * 4;   // 16 KB A + 32 KB W
 constexpr int FW_MAX_STAGES = 4, FW_MAX_RING = 8, FW_MAX_SLOTS = 8;
-constexpr int FW_HDR_FLOATS = FW_SUB * 16;                                // per sub-tile: 32 rows x (H[9], c[3], pad)
-constexpr int FW_CHUNK_FLOATS = FW_SUB * FW_KC;                           // per sub-tile and chunk: 32 rows x 16
+constexpr int FW_HDR_FLOATS = 16;                                         // per scratch row: H[9], sum d[3], pad
+
+// Development aid (tests/cuda/fw_trace.cu): clock64() stamps of CTA 0, one lane per role.  Compiled out of the product.
+#ifdef MOLANN_WS_TRACE
+__device__ long long g_fw_trace[4 * 256 * 8];       // [role][item][event]
+#define FW_EVT(role, i, ev)                                                                      \
+  do {                                                                                           \
+    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (i) < 256) g_fw_trace[((role) * 256 + (i)) * 8 + (ev)] = clock64(); \
+  } while (0)
+#else
+#define FW_EVT(role, i, ev) \
+  do {                      \
+  } while (0)
+#endif
 
 struct FwBars {
   unsigned long long empty[FW_MAX_STAGES], a_full[FW_MAX_STAGES], b_full[FW_MAX_STAGES];
@@ -74,6 +98,7 @@ struct FwBars {
   unsigned long long x_full[FW_MAX_RING], x_empty[FW_MAX_RING];
   unsigned long long s_full[FW_MAX_SLOTS], s_free[FW_MAX_SLOTS];
   unsigned long long turn[4];
+  unsigned long long l2_full, l2_free;
   uint32_t tptr;
 };
 
@@ -84,6 +109,7 @@ struct FwParams {
   const float* ref_x;        // [3 n_align]        centred reference
   const int* inv_ent;        // [n_inv_ent][6]     {type, a0, a1, a2, a3, first invariant column}
   int n_inp, n_align, n_pos, n_inv_ent, n_inv, n_units, use_angle;
+  int pos_is_align;          // the position atoms ARE the alignment selection, in the same order (one pass serves both)
   // MLP
   int n_hidden;              // tensor-core layers: 1 or 2
   int nkc1, n1p;             // layer 1: K-chunks, padded width
@@ -99,10 +125,10 @@ struct FwParams {
   // transposition scratch (global memory, L2 resident): per CTA n_slots sub-tiles of slot_floats
   float* scratch;
   long long cta_floats;
-  int slot_floats, n_slots;
+  int slot_floats, n_slots, row_floats;
   // shared memory
   int n_stages, n_ring, ring_slot_bytes;
-  int off_stage, off_ring, off_b1, off_b2, off_w3, off_ypart;
+  int off_stage, off_ring, off_b1, off_b2, off_w3, off_ypart, off_rowbuf;   // rowbuf: FW_NGW staging rows
   int off_pos, off_aidx, off_ref, off_ent;      // plan tables staged in smem (-1: read from global memory)
   int total_smem;
 };
@@ -113,12 +139,10 @@ __device__ __forceinline__ float fw_act(float zs) { return ws_act<ACT>(zs); }
 
 // writer of an invariant feature column into this frame's scratch row
 struct FwInvOut {
-  float* units;              // sub-tile's unit area
-  int rr, n_pos;
+  float* units;              // unit area of the frame's staging row
+  int n_pos;
   __device__ __forceinline__ void operator()(int v, float val) {
-    const int idx = v < n_pos ? 4 * v + 3 : 3 * n_pos + v;          // unit * 4 + component
-    const int u = idx >> 2;
-    units[((u >> 2) * FW_SUB + rr) * FW_KC + (u & 3) * 4 + (idx & 3)] = val;
+    units[v < n_pos ? 4 * v + 3 : 3 * n_pos + v] = val;             // unit * 4 + component
   }
 };
 
@@ -133,6 +157,13 @@ __device__ __forceinline__ void fw_stage_of(unsigned g, int n_stages, int& s, ui
   const unsigned q = g / (unsigned)n_stages;
   s = (int)(g - q * (unsigned)n_stages);
   par = q & 1u;
+}
+// ... `by` chunks further on
+__device__ __forceinline__ void fw_stage_skip(int& s, uint32_t& par, int by, int n_stages) {
+  const unsigned t = (unsigned)s + (unsigned)by;
+  const unsigned q = t / (unsigned)n_stages;
+  s = (int)(t - q * (unsigned)n_stages);
+  par ^= q & 1u;
 }
 
 // one row's 16 values of a K-chunk -> TF32 hi / lo -> canonical K-major operand tile (unit j at j * 2048 + row * 16)
@@ -152,13 +183,15 @@ __device__ __forceinline__ void fw_store_units(unsigned char* a_hi, int row, con
 
 // fp32 sum of `nseg` accumulator segments into acc[64] (columns col0 .. col0 + 63 of this thread's row)
 __device__ __forceinline__ void fw_sum_segments(float (&acc)[FW_CW], int nseg, int col0, int np, uint32_t lane_base,
-                                                FwBars* bars, unsigned& sg) {
+                                                FwBars* bars, unsigned& sg, bool trace) {
 #pragma unroll
   for (int i = 0; i < FW_CW; ++i) acc[i] = 0.f;
   for (int q = 0; q < nseg; ++q, ++sg) {
     const int db = (int)(sg & 1u);
+    if (trace) FW_EVT(2, 16 + q, 0);
     mbar_wait_hint(&bars->d_full[db], (sg >> 1) & 1u);
     tc_fence_after_sync();
+    if (trace) FW_EVT(2, 16 + q, 1);
 #pragma unroll
     for (int c = 0; c < FW_CW; c += 8) {
       if (col0 + c < np) {
@@ -174,7 +207,34 @@ __device__ __forceinline__ void fw_sum_segments(float (&acc)[FW_CW], int nseg, i
     }
     tc_fence_before_sync();
     mbar_arrive(&bars->d_free[db]);
+    if (trace) FW_EVT(2, 16 + q, 2);
   }
+}
+
+// reciprocal square root to fp32 rounding: MUFU seed + one Newton step (the IEEE sqrt / div sequences of the generic
+// feature code are ~100 dependent cycles each, and an entry's latency is what bounds the geometry role)
+__device__ __forceinline__ float fw_rsqrt(float a) {
+  const float y = rsqrtf(a);
+  return y * fmaf(-0.5f * a, y * y, 1.5f);
+}
+// dihedral as [cos, sin] (reference ann.py:338-351): C = n1.n2, S = (n1.r34) |r23|, out = (C, S) / sqrt(C^2 + S^2)
+template <class Out>
+__device__ __forceinline__ void fw_dihedral_cos_sin(const Entry& e, const float* __restrict__ xf, Out& out) {
+  const V3 x0 = ld3(xf, e.a0), x1 = ld3(xf, e.a1), x2 = ld3(xf, e.a2), x3 = ld3(xf, e.a3);
+  const V3 r12 = sub(x1, x0), r23 = sub(x2, x1), r34 = sub(x3, x2);
+  const V3 n1 = cross(r12, r23), n2 = cross(r23, r34);
+  const float d23 = dot(r23, r23);
+  const float C = dot(n1, n2);
+  const float S = dot(n1, r34) * (d23 * fw_rsqrt(d23));
+  const float ir = fw_rsqrt(fmaf(C, C, S * S));
+  out(e.off, C * ir);
+  out(e.off + 1, S * ir);
+}
+
+// A frame is copied from the 16-byte boundary below it, rounded up to 16 bytes: up to 15 bytes past its end.  That is
+// inside x for every frame but the last one of the batch, which is staged only if it ends on the grid.
+__device__ __forceinline__ bool fw_frame_is_staged(long long f, long long L, uint32_t off, uint32_t fbytes) {
+  return f + 1 < L || ((off + fbytes) & 15u) == 0u;
 }
 
 template <int ACT>
@@ -195,14 +255,16 @@ fused_wide_forward_kernel(const __grid_constant__ FwParams P, const float* __res
       mbar_init(&bars->d_free[s], 16 * 32);
     }
     for (int s = 0; s < FW_MAX_RING; ++s) {
-      mbar_init(&bars->x_full[s], 1);
+      mbar_init(&bars->x_full[s], 32);             // every lane of the X producer arrives (cp.async completion)
       mbar_init(&bars->x_empty[s], 1);
     }
     for (int s = 0; s < FW_MAX_SLOTS; ++s) {
-      mbar_init(&bars->s_full[s], FW_SUB);
+      mbar_init(&bars->s_full[s], FW_SUB * FW_NGW);  // the four warps of a frame's group each publish their part
       mbar_init(&bars->s_free[s], 1);
     }
     for (int s = 0; s < 4; ++s) mbar_init(&bars->turn[s], 128);
+    mbar_init(&bars->l2_full, 1);
+    mbar_init(&bars->l2_free, 16 * 32);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(&bars->tptr, 512u);
@@ -238,45 +300,55 @@ fused_wide_forward_kernel(const __grid_constant__ FwParams P, const float* __res
   tc_fence_after_sync();
   if (bars->tptr != 0u) __trap();             // full allocation: base 0 (keeps tcgen05 addresses warp-uniform)
 
-  const long long ntiles = (L + FW_M - 1) / FW_M;
-  const int n3 = 3 * P.n_inp;
-  const int nchunks_tile = P.nkc1 + (P.n_hidden == 2 ? P.nkc2 : 0);
-  const int nseg1 = (P.nkc1 + FW_SEGC - 1) / FW_SEGC;
-  const int nseg2 = P.n_hidden == 2 ? (P.nkc2 + FW_SEGC - 1) / FW_SEGC : 0;
-  float* const cta_scratch = P.scratch + (long long)blockIdx.x * P.cta_floats;
-  unsigned char* const stages = smem + P.off_stage;
-  unsigned char* const ring = smem + P.off_ring;
+  // Nothing long-lived is computed here: every role derives what it needs from the (constant-bank) parameters itself.
+  // Values that stay live across the role dispatch are spilled under the small per-role register budgets, and with
+  // 200+ KB of shared memory configured there is next to no L1 left: a spill reload costs an L2 round trip
+  // (tests/cuda/fw_trace.cu: 15 k cycles for the 7-iteration moment loop of a frame instead of 1.3 k).
+#define FW_NTILES ((int)((L + FW_M - 1) / FW_M))
+#define FW_NCHUNKS_TILE (P.nkc1 + (P.n_hidden == 2 ? P.nkc2 : 0))
+#define FW_STAGES (smem + P.off_stage)
+#define FW_RING (smem + P.off_ring)
+#define FW_CTA_SCRATCH (P.scratch + (long long)blockIdx.x * P.cta_floats)
 
   if (warp >= FW_W_GEO) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(FW_REGS_GEO));
   else if (warp >= FW_W_WPROD) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(FW_REGS_CTRL));
 
   if (warp == FW_W_XPROD) {
     // ================= X producer: whole frames into the shared-memory ring =================
+    // 16-byte cp.async (LDGSTS) copies, NOT the bulk-copy engine: that engine is one in-order queue per SM, and with
+    // 24 KB frame loads (HBM latency) always in flight every small bulk store and every fence.proxy.async of the
+    // other roles waited 4.6 k cycles behind them (tests/cuda/fw_trace.cu).  A copy starts at the 16-byte boundary
+    // below the frame and may run up to 15 bytes past it -- never past the end of x (fw_plain_frame_copy).
     int rs = 0;
     uint32_t rpar = 0;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      for (int r = 0; r < FW_M; ++r) {
-        const long long f = tile * FW_M + r;
-        if (f >= L) break;
-        const float* src = x + f * n3;
+    const uint32_t fbytes = 12u * (uint32_t)P.n_inp;
+    const int ntiles = FW_NTILES;
+    // x is read exactly once: mark its lines evict-first so that the stream does not push the CTA's transposition
+    // scratch (re-used every tile) out of L2
+    unsigned long long pol_stream;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+#pragma unroll 1
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const long long f0 = (long long)tile * FW_M;
+      const int nf = L - f0 < FW_M ? (int)(L - f0) : FW_M;
+      const unsigned char* src = reinterpret_cast<const unsigned char*>(x) + f0 * (long long)fbytes;
+#pragma unroll 1
+      for (int r = 0; r < nf; ++r, src += fbytes) {
         const uint32_t off = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15u);
-        const uint32_t bytes = ((uint32_t)n3 * 4u + off + 15u) & ~15u;
-        unsigned char* dst = ring + (size_t)rs * P.ring_slot_bytes;
+        const uint32_t bytes = (fbytes + off + 15u) & ~15u;
+        const uint32_t d0 = smem_u32(FW_RING) + (uint32_t)rs * (uint32_t)P.ring_slot_bytes;
+        // the batch's very last frame is not staged when its copy would run past the end of x: the geometry role
+        // reads that one frame straight from global memory (fw_frame_is_staged)
+        if (!fw_frame_is_staged(f0 + r, L, off, fbytes)) break;
         if (lane == 0) mbar_wait_hint(&bars->x_empty[rs], rpar ^ 1u);
         __syncwarp();
-        // the bulk copy starts at the 16-byte boundary below the frame and may run up to 15 bytes past it:
-        // never past the end of x (last frame of the batch unless it ends on the grid)
-        if (f + 1 < L || ((off + (uint32_t)n3 * 4u) & 15u) == 0u) {
-          if (lane == 0) {
-            mbar_expect_tx(&bars->x_full[rs], bytes);
-            bulk_g2s(dst, reinterpret_cast<const unsigned char*>(src) - off, bytes, &bars->x_full[rs]);
-          }
-        } else {
-          float* d = reinterpret_cast<float*>(dst + off);
-          for (int i = lane; i < n3; i += 32) d[i] = __ldg(src + i);
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bars->x_full[rs]);
-        }
+        const unsigned char* s0 = src - off + lane * 16;
+        for (uint32_t o = (uint32_t)lane * 16u; o < bytes; o += 512u, s0 += 512)
+          asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(d0 + o), "l"(s0),
+                       "l"(pol_stream)
+                       : "memory");
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&bars->x_full[rs]))
+                     : "memory");
         if (++rs == P.n_ring) {
           rs = 0;
           rpar ^= 1u;
@@ -285,131 +357,188 @@ fused_wide_forward_kernel(const __grid_constant__ FwParams P, const float* __res
     }
   } else if (warp >= FW_W_GEO) {
     // ================= geometry: moments, raw position atoms, invariant features -> scratch =================
-    const int gw = warp - FW_W_GEO;
-    const int* pos_atom = P.off_pos >= 0 ? reinterpret_cast<const int*>(smem + P.off_pos) : P.pos_atom;
-    const int* aidx = P.off_aidx >= 0 ? reinterpret_cast<const int*>(smem + P.off_aidx) : P.align_idx;
-    const float* refx = P.off_ref >= 0 ? reinterpret_cast<const float*>(smem + P.off_ref) : P.ref_x;
-    const int* ient = P.off_ent >= 0 ? reinterpret_cast<const int*>(smem + P.off_ent) : P.inv_ent;
+    // The four warps work on ONE frame at a time (thread = alignment atom / position atom / invariant entry), so
+    // the frames behind it in the ring are pure prefetch and a frame's latency is that of one entry, not of
+    // n_entries / 32 iterations of a single warp (tests/cuda/fw_trace.cu: 18 k cycles per frame per warp before).
+    // Two such groups take alternate frames (frame ic goes to group ic mod 2), which doubles the chains in flight.
+    const int grp = (warp - FW_W_GEO) / FW_NGW;
+    const int gw = (warp - FW_W_GEO) % FW_NGW;
+    const int gt = gw * 32 + lane;                    // 0 .. 127 within the group
     const bool aligned = P.n_align > 0;
-    const float inv_n = aligned ? 1.0f / (float)P.n_align : 0.f;
-    unsigned it = 0;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-      for (int r = gw; r < FW_M; r += FW_NGW) {
-        const long long f = tile * FW_M + r;
-        // scratch sub-tile of this frame
-        const unsigned j = it * (FW_M / FW_SUB) + (unsigned)(r / FW_SUB);
-        const unsigned use = j / (unsigned)P.n_slots;
-        const int slot = (int)(j - use * (unsigned)P.n_slots);
-        const int rr = r & (FW_SUB - 1);
-        if (rr < FW_NGW) {                           // this warp's first frame in the sub-tile: the slot must be free
-          if (lane == 0) mbar_wait_hint(&bars->s_free[slot], (use & 1u) ^ 1u);
-          __syncwarp();
+    const int n3 = 3 * P.n_inp;
+    // geo (per group): [2][row_floats] staging rows, then [2][4][12] per-warp moment partials (double-buffered)
+    float* const geo = reinterpret_cast<float*>(smem + P.off_rowbuf) + (size_t)grp * (2 * P.row_floats + 96);
+    float* const red_base = geo + 2 * (size_t)P.row_floats;
+    const unsigned nfr = (unsigned)((FW_NTILES - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * FW_M;
+    int slot = 0, rs = grp % P.n_ring, prev_slot = -1;
+    uint32_t spar = 0, rpar = (uint32_t)(grp / P.n_ring) & 1u;
+    unsigned k2 = 0;                                   // this group's frame counter (buffer parity)
+#pragma unroll 1
+    for (unsigned ic = (unsigned)grp; ic < nfr; ic += FW_NGG, ++k2) {
+      const unsigned it = ic / FW_M;
+      const int r = (int)(ic & (FW_M - 1));
+      const long long f = ((long long)blockIdx.x + (long long)it * gridDim.x) * FW_M + r;
+      const int rr = r & (FW_SUB - 1);
+      if (gw == 0 && grp == 0) FW_EVT(0, k2, 0);
+      if (rr < FW_NGG) {                              // this group's first frame of a scratch sub-tile: slot must be free
+        if (ic >= FW_NGG && ++slot == P.n_slots) {
+          slot = 0;
+          spar ^= 1u;
         }
-        if (f < L) {
-          float* sub = cta_scratch + (long long)slot * P.slot_floats;
-          float* units = sub + FW_HDR_FLOATS;
-          // frame in the ring
-          const unsigned ic = it * FW_M + (unsigned)r;
-          const unsigned ruse = ic / (unsigned)P.n_ring;
-          const int rs = (int)(ic - ruse * (unsigned)P.n_ring);
-          if (lane == 0) mbar_wait_hint(&bars->x_full[rs], ruse & 1u);
+        if (lane == 0) mbar_wait_hint(&bars->s_free[slot], spar ^ 1u);
+        __syncwarp();
+      }
+      if (f < L) {
+        if (gw == 0 && grp == 0) FW_EVT(0, k2, 1);
+        const uint32_t off = (uint32_t)(reinterpret_cast<uintptr_t>(x + f * n3) & 15u);
+        const bool staged = fw_frame_is_staged(f, L, off, 4u * (uint32_t)n3);
+        const float* xf = x + f * n3;                 // (the one unstaged frame of a batch is read in place)
+        if (staged) {
+          if (lane == 0) mbar_wait_hint(&bars->x_full[rs], rpar);
           __syncwarp();
-          const uint32_t off = (uint32_t)(reinterpret_cast<uintptr_t>(x + f * n3) & 15u);
-          const float* xf = reinterpret_cast<const float*>(ring + (size_t)rs * P.ring_slot_bytes + off);
-          float pvx = 0.f, pvy = 0.f, pvz = 0.f;
-          if (aligned) {
-            // pivoted one-pass moments (reference ann.py:179-187): d_k = x_k - x_{A_0}, H = sum d_k^T y_k (the
-            // reference is centred), c_rel = mean d_k
-            const float* p0 = xf + 3 * aidx[0];
-            pvx = p0[0]; pvy = p0[1]; pvz = p0[2];
-            float m[12];
+          xf = reinterpret_cast<const float*>(FW_RING + (size_t)rs * P.ring_slot_bytes + off);
+        }
+        if (gw == 0 && grp == 0) FW_EVT(0, k2, 2);
+        float* const rowbuf = geo + (size_t)(k2 & 1u) * P.row_floats;
+        float* const red = red_base + (k2 & 1u) * 48;
+        float pvx = 0.f, pvy = 0.f, pvz = 0.f;
+        if (aligned) {
+          // pivoted one-pass moments (reference ann.py:179-187): d_k = x_k - x_{A_0}, H = sum d_k^T y_k (the
+          // reference is centred); the header carries H and sum d_k (c_rel = sum / n_a is formed by the converter)
+          const int* aidx = P.off_aidx >= 0 ? reinterpret_cast<const int*>(smem + P.off_aidx) : P.align_idx;
+          const float* refx = P.off_ref >= 0 ? reinterpret_cast<const float*>(smem + P.off_ref) : P.ref_x;
+          const float* p0 = xf + 3 * aidx[0];
+          pvx = p0[0]; pvy = p0[1]; pvz = p0[2];
+          float m[12];
 #pragma unroll
-            for (int i = 0; i < 12; ++i) m[i] = 0.f;
-            for (int k = lane; k < P.n_align; k += 32) {
-              const float* p = xf + 3 * aidx[k];
-              const float px = p[0] - pvx, py = p[1] - pvy, pz = p[2] - pvz;
-              const float y0 = refx[3 * k], y1 = refx[3 * k + 1], y2 = refx[3 * k + 2];
-              m[0] = fmaf(px, y0, m[0]); m[1] = fmaf(px, y1, m[1]); m[2] = fmaf(px, y2, m[2]);
-              m[3] = fmaf(py, y0, m[3]); m[4] = fmaf(py, y1, m[4]); m[5] = fmaf(py, y2, m[5]);
-              m[6] = fmaf(pz, y0, m[6]); m[7] = fmaf(pz, y1, m[7]); m[8] = fmaf(pz, y2, m[8]);
-              m[9] += px; m[10] += py; m[11] += pz;
-            }
-#pragma unroll
-            for (int i = 0; i < 12; ++i) m[i] = gsum<32>(m[i]);
-            if (lane == 0) {
-              float4* h = reinterpret_cast<float4*>(sub + rr * 16);
-              h[0] = make_float4(m[0], m[1], m[2], m[3]);
-              h[1] = make_float4(m[4], m[5], m[6], m[7]);
-              h[2] = make_float4(m[8], m[9] * inv_n, m[10] * inv_n, m[11] * inv_n);
+          for (int i = 0; i < 12; ++i) m[i] = 0.f;
+#pragma unroll 1
+          for (int k = gt; k < P.n_align; k += 4 * 32) {
+            const float* p = xf + 3 * aidx[k];
+            const float px = p[0] - pvx, py = p[1] - pvy, pz = p[2] - pvz;
+            const float y0 = refx[3 * k], y1 = refx[3 * k + 1], y2 = refx[3 * k + 2];
+            m[0] = fmaf(px, y0, m[0]); m[1] = fmaf(px, y1, m[1]); m[2] = fmaf(px, y2, m[2]);
+            m[3] = fmaf(py, y0, m[3]); m[4] = fmaf(py, y1, m[4]); m[5] = fmaf(py, y2, m[5]);
+            m[6] = fmaf(pz, y0, m[6]); m[7] = fmaf(pz, y1, m[7]); m[8] = fmaf(pz, y2, m[8]);
+            m[9] += px; m[10] += py; m[11] += pz;
+            if (P.pos_is_align) {                     // the same atom is position unit k: its raw coordinates are here
+              float* dst = rowbuf + FW_HDR_FLOATS + 4 * k;
+              *reinterpret_cast<float2*>(dst) = make_float2(px, py);
+              dst[2] = pz;
+              if (k >= P.n_inv) dst[3] = 0.f;
             }
           }
-          // raw (pivot-relative) coordinates of the position atoms; the w slot of a unit belongs to invariant
-          // column u when there is one, else it is zero
-          for (int u = lane; u < P.n_pos; u += 32) {
+          sb_reduce12_store(m, red + gw * 12, lane);
+        }
+        if (gw == 0 && grp == 0) FW_EVT(0, k2, 3);
+        float* units = rowbuf + FW_HDR_FLOATS;
+        // raw (pivot-relative) coordinates of the position atoms; the w slot of a unit belongs to invariant
+        // column u when there is one, else it is zero
+        if (!(aligned && P.pos_is_align)) {
+          const int* pos_atom = P.off_pos >= 0 ? reinterpret_cast<const int*>(smem + P.off_pos) : P.pos_atom;
+          for (int u = gt; u < P.n_pos; u += 4 * 32) {
             const float* p = xf + 3 * pos_atom[u];
-            float* dst = units + ((u >> 2) * FW_SUB + rr) * FW_KC + (u & 3) * 4;
+            float* dst = units + 4 * u;
             *reinterpret_cast<float2*>(dst) = make_float2(p[0] - pvx, p[1] - pvy);
             dst[2] = p[2] - pvz;
             if (u >= P.n_inv) dst[3] = 0.f;
           }
-          // invariant features (bond / angle / dihedral, ann.py:323-351) from the raw coordinates
-          FwInvOut out{units, rr, P.n_pos};
+        }
+        if (gw == 0 && grp == 0) FW_EVT(0, k2, 4);
+        // invariant features (bond / angle / dihedral, ann.py:323-351) from the raw coordinates
+        {
+          FwInvOut out{units, P.n_pos};
           Rigid none;
-          for (int e = lane; e < P.n_inv_ent; e += 32) {
+          const int* ient = P.off_ent >= 0 ? reinterpret_cast<const int*>(smem + P.off_ent) : P.inv_ent;
+          for (int e = gt; e < P.n_inv_ent; e += 4 * 32) {
             const Entry en = load_entry(ient + ENTRY_INTS * e);
-            feature_forward(en, xf, false, none, P.use_angle, out);
+            if (en.type == FEAT_DIHEDRAL && !P.use_angle) fw_dihedral_cos_sin(en, xf, out);
+            else feature_forward(en, xf, false, none, P.use_angle, out);
           }
-          if (lane == 0 && P.n_inv > P.n_pos) {       // zero the unused tail of the last invariant unit
+          if (gt == 0 && P.n_inv > P.n_pos) {         // zero the unused tail of the last invariant unit
             for (int v = P.n_inv; ((v - P.n_pos) & 3) != 0; ++v) out(v, 0.f);
           }
-          __syncwarp();
-          if (lane == 0) {
-            mbar_arrive(&bars->x_empty[rs]);
-            mbar_arrive(&bars->s_full[slot]);
-          }
-        } else if (lane == 0) {
-          mbar_arrive(&bars->s_full[slot]);           // past the end of the batch: keep the sub-tile's count whole
         }
+        if (gw == 0 && grp == 0) FW_EVT(0, k2, 5);
+        // the row, the partials; every read of the frame is done (named barrier of this group)
+        asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory");
+        if (gw == 0 && grp == 0) FW_EVT(0, k2, 6);
+        if (lane == 0) {
+          if (gw == 0 && staged) mbar_arrive(&bars->x_empty[rs]);
+          // publish this warp's part of the PREVIOUS frame's row: those stores were issued a whole frame ago, so
+          // the release does not stall
+          if (prev_slot >= 0) mbar_arrive(&bars->s_full[prev_slot]);
+        }
+        prev_slot = slot;
+        if (gw == 0) {                                // header: fixed-order sum of the four warps' partials
+          if (aligned && lane < 12) rowbuf[lane] = (red[lane] + red[12 + lane]) + (red[24 + lane] + red[36 + lane]);
+          __syncwarp();
+        }
+        {                                             // staging row -> scratch, coalesced 16-byte stores
+          float4* dst = reinterpret_cast<float4*>(FW_CTA_SCRATCH + (long long)slot * P.slot_floats +
+                                                  (long long)rr * P.row_floats);
+          const float4* srow = reinterpret_cast<const float4*>(rowbuf);
+          for (int i = gt; i < P.row_floats / 4; i += 4 * 32) dst[i] = srow[i];
+        }
+        if (gw == 0 && grp == 0) FW_EVT(0, k2, 7);
+        rs += FW_NGG;
+        while (rs >= P.n_ring) {
+          rs -= P.n_ring;
+          rpar ^= 1u;
+        }
+      } else if (lane == 0) {
+        mbar_arrive(&bars->s_full[slot]);             // past the end of the batch: keep the sub-tile's count whole
       }
     }
+    __syncwarp();
+    if (lane == 0 && prev_slot >= 0) mbar_arrive(&bars->s_full[prev_slot]);
   } else if (warp < FW_W_EPI) {
     // ================= converter: rotation per frame, then K-chunks scratch -> TF32 hi / lo operand tiles ==========
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(FW_REGS_CONV));
+    if (FW_REGS_CONV > FW_REGS_LAUNCH) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(FW_REGS_CONV));
+    if (FW_REGS_CONV < FW_REGS_LAUNCH) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(FW_REGS_CONV));
     const int row = tid;                               // 0 .. 127
     const bool aligned = P.n_align > 0;
-    unsigned it = 0, g = 0;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    unsigned it = 0;
+    int s = 0;
+    uint32_t par = 0;
+    const int ntiles = FW_NTILES;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       // layer 2's operand chunks of the previous tile share the stage ring: they must all have been written before
       // this role asks for a stage again (a waiter may be at most one phase ahead of an mbarrier)
+      if (warp == 0) FW_EVT(1, it, 0);
       if (it > 0 && P.n_hidden == 2) mbar_wait_hint(&bars->turn[3], (it - 1u) & 1u);
+      if (warp == 0) FW_EVT(1, it, 1);
       const unsigned j = it * (FW_M / FW_SUB) + (unsigned)warp;
       const unsigned use = j / (unsigned)P.n_slots;
       const int slot = (int)(j - use * (unsigned)P.n_slots);
       mbar_wait_hint(&bars->s_full[slot], use & 1u);
-      const float* sub = cta_scratch + (long long)slot * P.slot_floats;
-      const float4* units = reinterpret_cast<const float4*>(sub + FW_HDR_FLOATS) + lane * FW_KU;
-      const bool valid = tile * FW_M + row < L;
+      if (warp == 0) FW_EVT(1, it, 2);
+      const float* myrow = FW_CTA_SCRATCH + (long long)slot * P.slot_floats + (long long)lane * P.row_floats;
+      const float4* units = reinterpret_cast<const float4*>(myrow + FW_HDR_FLOATS);
+      const bool valid = (long long)tile * FW_M + row < L;
       Rigid rg;
       float c0 = 0.f, c1 = 0.f, c2 = 0.f;
       if (aligned) {
-        const float4* h = reinterpret_cast<const float4*>(sub + lane * 16);
+        const float4* h = reinterpret_cast<const float4*>(myrow);
         float4 h0 = make_float4(1.f, 0.f, 0.f, 0.f), h1 = make_float4(1.f, 0.f, 0.f, 0.f),
                h2 = make_float4(1.f, 0.f, 0.f, 0.f);
         if (valid) { h0 = __ldcg(h); h1 = __ldcg(h + 1); h2 = __ldcg(h + 2); }
         rg.H[0] = h0.x; rg.H[1] = h0.y; rg.H[2] = h0.z; rg.H[3] = h0.w;
         rg.H[4] = h1.x; rg.H[5] = h1.y; rg.H[6] = h1.z; rg.H[7] = h1.w; rg.H[8] = h2.x;
-        c0 = h2.y; c1 = h2.z; c2 = h2.w;
+        const float inv_n = 1.0f / (float)P.n_align;
+        c0 = h2.y * inv_n; c1 = h2.z * inv_n; c2 = h2.w * inv_n;
         kabsch_rotation(rg);                          // reference ann.py:188-195 as a quaternion eigenproblem
       }
+      if (warp == 0) FW_EVT(1, it, 3);
       float4 nxt[FW_KU];
 #pragma unroll
       for (int q = 0; q < FW_KU; ++q) nxt[q] = valid ? __ldcg(units + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int kc = 0; kc < P.nkc1; ++kc, ++g) {
+      for (int kc = 0; kc < P.nkc1; ++kc) {
         float4 v[FW_KU];
 #pragma unroll
         for (int q = 0; q < FW_KU; ++q) v[q] = nxt[q];
         if (kc + 1 < P.nkc1 && valid) {
-          const float4* src = units + (size_t)(kc + 1) * (FW_CHUNK_FLOATS / 4);
+          const float4* src = units + (size_t)(kc + 1) * FW_KU;
 #pragma unroll
           for (int q = 0; q < FW_KU; ++q) nxt[q] = __ldcg(src + q);
         }
@@ -425,17 +554,20 @@ fused_wide_forward_kernel(const __grid_constant__ FwParams P, const float* __res
             v[q].z = fmaf(dx, rg.R[2], fmaf(dy, rg.R[5], dz * rg.R[8]));
           }
         }
-        int s;
-        uint32_t par;
-        fw_stage_of(g, P.n_stages, s, par);
+        if (warp == 0 && it == 0) FW_EVT(1, 16 + kc, 0);
         mbar_wait_hint(&bars->empty[s], par ^ 1u);
-        fw_store_units(stages + (size_t)s * FW_STAGE_BYTES, row, v);
+        if (warp == 0 && it == 0) FW_EVT(1, 16 + kc, 1);
+        fw_store_units(FW_STAGES + (size_t)s * FW_STAGE_BYTES, row, v);
+        if (warp == 0 && it == 0) FW_EVT(1, 16 + kc, 2);
         fence_proxy_async_smem();
         mbar_arrive(&bars->a_full[s]);
+        if (warp == 0 && it == 0) FW_EVT(1, 16 + kc, 3);
+        fw_stage_step(s, par, P.n_stages);
       }
       __syncwarp();
+      if (warp == 0) FW_EVT(1, it, 4);
       if (lane == 0) mbar_arrive(&bars->s_free[slot]);
-      g += (unsigned)(nchunks_tile - P.nkc1);
+      if (P.n_hidden == 2) fw_stage_skip(s, par, P.nkc2, P.n_stages);
     }
   } else if (warp == FW_W_WPROD) {
     // ================= W producer: pre-packed weight blocks, layer 1 then layer 2 =================
@@ -443,7 +575,10 @@ fused_wide_forward_kernel(const __grid_constant__ FwParams P, const float* __res
       const uint32_t bytes1 = 2u * FW_KC * (uint32_t)P.n1p * 4u, bytes2 = 2u * FW_KC * (uint32_t)P.n2p * 4u;
       int s = 0;
       uint32_t par = 0;
-      for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int ntiles = FW_NTILES;
+      const int nchunks_tile = FW_NCHUNKS_TILE;
+      unsigned char* const stages = FW_STAGES;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         for (int kc = 0; kc < nchunks_tile; ++kc) {
           const bool l1 = kc < P.nkc1;
           const float* src = l1 ? P.w1p + (size_t)kc * (2 * FW_KC * P.n1p)
@@ -461,24 +596,50 @@ fused_wide_forward_kernel(const __grid_constant__ FwParams P, const float* __res
     const uint32_t leader = elect_one();
     int s = 0;
     uint32_t par = 0;
-    unsigned sg = 0;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    unsigned sg = 0, it = 0;
+    const int stride2 = P.n2p <= 128 ? 128 : 256;            // layer 2: 4 (or 2) accumulators, no drain in between
+    const int cpa2 = (P.nkc2 + (512 / stride2) - 1) / (512 / stride2);
+    const int ntiles = FW_NTILES;
+    unsigned char* const stages = FW_STAGES;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      if (it > 0 && P.n_hidden == 2) {                       // layer 2's accumulators of the previous tile are read
+        mbar_wait_hint(&bars->l2_free, (it - 1u) & 1u);
+        tc_fence_after_sync();
+      }
       for (int layer = 0; layer < P.n_hidden; ++layer) {
         const int nkc = layer == 0 ? P.nkc1 : P.nkc2;
         const int np = layer == 0 ? P.n1p : P.n2p;
         const uint32_t idesc = idesc_tf32(FW_M, np);
         const uint32_t lbo_b = (uint32_t)np * 16u;
+        if (layer == 1) {                                    // every layer-1 segment has been summed by the epilogue
+          if (sg >= 2) mbar_wait_hint(&bars->d_free[(sg - 2u) & 1u], ((sg - 2u) >> 1) & 1u);
+          mbar_wait_hint(&bars->d_free[(sg - 1u) & 1u], ((sg - 1u) >> 1) & 1u);
+          tc_fence_after_sync();
+        }
         for (int kc = 0; kc < nkc; ++kc) {
-          const int db = (int)(sg & 1u);
-          const uint32_t d = (uint32_t)db * FW_NMAX;
-          const bool seg_first = (kc % FW_SEGC) == 0;
-          const bool seg_last = (kc % FW_SEGC) == FW_SEGC - 1 || kc == nkc - 1;
-          if (seg_first) {
-            mbar_wait_hint(&bars->d_free[db], ((sg >> 1) & 1u) ^ 1u);
-            tc_fence_after_sync();
+          uint32_t d;
+          bool first, seg_last = false;
+          const int tci = (int)it * 128 + layer * 64 + kc;     // trace index
+          (void)tci;
+          FW_EVT(3, tci, 0);
+          if (layer == 0) {
+            const int db = (int)(sg & 1u);
+            d = (uint32_t)db * FW_NMAX;
+            first = (kc % FW_SEGC) == 0;
+            seg_last = (kc % FW_SEGC) == FW_SEGC - 1 || kc == nkc - 1;
+            if (first) {
+              mbar_wait_hint(&bars->d_free[db], ((sg >> 1) & 1u) ^ 1u);
+              tc_fence_after_sync();
+            }
+          } else {
+            d = (uint32_t)((kc / cpa2) * stride2);
+            first = (kc % cpa2) == 0;
           }
+          FW_EVT(3, tci, 1);
           mbar_wait_hint(&bars->a_full[s], par);
+          FW_EVT(3, tci, 2);
           mbar_wait_hint(&bars->b_full[s], par);
+          FW_EVT(3, tci, 3);
           tc_fence_after_sync();
           const uint32_t a_hi = smem_u32(stages + (size_t)s * FW_STAGE_BYTES), a_lo = a_hi + FW_A_HALF;
           const uint32_t b_hi = a_hi + 2 * FW_A_HALF, b_lo = b_hi + (uint32_t)np * FW_KC * 4u;
@@ -490,7 +651,7 @@ fused_wide_forward_kernel(const __grid_constant__ FwParams P, const float* __res
             const uint64_t bh = smem_desc_kmajor(b_hi + jj * (2u * lbo_b), lbo_b, 128);
             const uint64_t bl = smem_desc_kmajor(b_lo + jj * (2u * lbo_b), lbo_b, 128);
             if (leader) {
-              mma_tf32_ss(d, al, bh, idesc, (!seg_first || jj > 0) ? 1u : 0u);
+              mma_tf32_ss(d, al, bh, idesc, (!first || jj > 0) ? 1u : 0u);
               mma_tf32_ss(d, ah, bl, idesc, 1);
             }
           }
@@ -502,17 +663,19 @@ fused_wide_forward_kernel(const __grid_constant__ FwParams P, const float* __res
           }
           if (leader) mma_commit(&bars->empty[s]);
           if (seg_last) {
-            if (leader) mma_commit(&bars->d_full[db]);
+            if (leader) mma_commit(&bars->d_full[sg & 1u]);
             ++sg;
           }
+          if (layer == 1 && kc == nkc - 1 && leader) mma_commit(&bars->l2_full);
           __syncwarp();
+          FW_EVT(3, tci, 4);
           fw_stage_step(s, par, P.n_stages);
         }
       }
     }
   } else if (warp < FW_W_WPROD) {
     // ================= epilogue: segment sums, activations, layer 2 operand chunks, last layer, y =================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(FW_REGS_EPI));
+    if (FW_REGS_EPI > FW_REGS_LAUNCH) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(FW_REGS_EPI));
     const int e = (warp - FW_W_EPI) >> 2;            // this warpgroup owns accumulator columns [64 e, 64 e + 64)
     const int row = tid & 127;
     const int col0 = FW_CW * e;
@@ -522,17 +685,22 @@ fused_wide_forward_kernel(const __grid_constant__ FwParams P, const float* __res
     const float* w3 = reinterpret_cast<const float*>(smem + P.off_w3);
     float* ypart = reinterpret_cast<float*>(smem + P.off_ypart);
     unsigned sg = 0, it = 0;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int ntiles = FW_NTILES;
+    const int nseg1 = (P.nkc1 + FW_SEGC - 1) / FW_SEGC;
+    unsigned char* const stages = FW_STAGES;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       float acc[FW_CW];
-      fw_sum_segments(acc, nseg1, col0, P.n1p, lane_base, bars, sg);
+      if (warp == FW_W_EPI) FW_EVT(2, it, 0);
+      fw_sum_segments(acc, nseg1, col0, P.n1p, lane_base, bars, sg, warp == FW_W_EPI && it == 0);
+      if (warp == FW_W_EPI) FW_EVT(2, it, 1);
 #pragma unroll
       for (int c = 0; c < FW_CW; ++c)
         if (col0 + c < P.n1p) acc[c] = fw_act<ACT>(acc[c] + b1[col0 + c]);
-      int nlast = P.n1p;
+      int nlast = P.n1p, lcol0 = col0, lcw = FW_CW;      // columns of the last hidden layer this thread holds
       if (P.n_hidden == 2) {
         // h1 goes back into the operand ring as layer 2's A chunks, warpgroup after warpgroup (chunk order)
         if (e > 0) mbar_wait_hint(&bars->turn[e - 1], it & 1u);
-        const unsigned gbase = it * (unsigned)nchunks_tile + (unsigned)P.nkc1;
+        const unsigned gbase = it * (unsigned)FW_NCHUNKS_TILE + (unsigned)P.nkc1;
 #pragma unroll
         for (int q = 0; q < FW_CW / FW_KC; ++q) {
           const int kc2 = (FW_CW / FW_KC) * e + q;
@@ -552,10 +720,39 @@ fused_wide_forward_kernel(const __grid_constant__ FwParams P, const float* __res
           }
         }
         mbar_arrive(&bars->turn[e]);
-        fw_sum_segments(acc, nseg2, col0, P.n2p, lane_base, bars, sg);
+        if (warp == FW_W_EPI) FW_EVT(2, it, 2);
+        // layer 2: sum of its accumulators (fixed order), this thread's stride2 / 4 columns
+        const int stride2 = P.n2p <= 128 ? 128 : 256;
+        const int cw2 = stride2 / 4;
+        lcol0 = cw2 * e;
+        lcw = cw2;
+#pragma unroll
+        for (int i = 0; i < FW_CW; ++i) acc[i] = 0.f;
+        mbar_wait_hint(&bars->l2_full, it & 1u);
+        tc_fence_after_sync();
+        if (warp == FW_W_EPI) FW_EVT(2, it, 3);
+        const int cpa2 = (P.nkc2 + (512 / stride2) - 1) / (512 / stride2);
+        const int nacc2 = (P.nkc2 + cpa2 - 1) / cpa2;
+        for (int a = 0; a < nacc2; ++a) {
+#pragma unroll
+          for (int c = 0; c < FW_CW; c += 8) {
+            if (c < cw2 && lcol0 + c < P.n2p) {
+              uint32_t u[8];
+              asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                           : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
+                           : "r"(lane_base + (uint32_t)(a * stride2 + lcol0 + c))
+                           : "memory");
+              tmem_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 8; ++i) acc[c + i] += __uint_as_float(u[i]);
+            }
+          }
+        }
+        tc_fence_before_sync();
+        mbar_arrive(&bars->l2_free);
 #pragma unroll
         for (int c = 0; c < FW_CW; ++c)
-          if (col0 + c < P.n2p) acc[c] = fw_act<ACT>(acc[c] + b2[col0 + c]);
+          if (c < cw2 && lcol0 + c < P.n2p) acc[c] = fw_act<ACT>(acc[c] + b2[lcol0 + c]);
         nlast = P.n2p;
       }
       // last (narrow) layer: partial dot products over this thread's columns, summed in a fixed order
@@ -563,12 +760,12 @@ fused_wide_forward_kernel(const __grid_constant__ FwParams P, const float* __res
         float pd = 0.f;
 #pragma unroll
         for (int c = 0; c < FW_CW; ++c)
-          if (col0 + c < nlast) pd = fmaf(acc[c], w3[o * P.nlastp + col0 + c], pd);
+          if (c < lcw && lcol0 + c < nlast) pd = fmaf(acc[c], w3[o * P.nlastp + lcol0 + c], pd);
         ypart[(e * FW_M + row) * P.kout + o] = pd;
       }
       asm volatile("bar.sync 1, %0;" ::"n"(16 * 32) : "memory");
       if (e == 0) {
-        const long long f = tile * FW_M + row;
+        const long long f = (long long)tile * FW_M + row;
         if (f < L) {
           for (int o = 0; o < P.kout; ++o) {
             float v = __ldg(P.b3 + o);
@@ -579,11 +776,17 @@ fused_wide_forward_kernel(const __grid_constant__ FwParams P, const float* __res
         }
       }
       asm volatile("bar.sync 1, %0;" ::"n"(16 * 32) : "memory");
+      if (warp == FW_W_EPI) FW_EVT(2, it, 4);
     }
   }
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(0u, 512u);
+#undef FW_NTILES
+#undef FW_NCHUNKS_TILE
+#undef FW_STAGES
+#undef FW_RING
+#undef FW_CTA_SCRATCH
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -563,7 +563,7 @@ struct MolannPrepared {
   // sizes the plan must still have when the handle is used
   int n_inp, n_align, n_entries, d_feat, n_layers, act, dims[MOLANN_MAX_LAYERS + 1];
   // kernel-order program
-  int n_pos, n_inv_ent, n_inv, n_units, n_hidden;
+  int n_pos, n_inv_ent, n_inv, n_units, n_hidden, pos_is_align;
   int nkc1, n1, n1p, nkc2, n2, n2p, nlast, nlastp, kout, kpad;
   // device pointers into the caller's buffer
   int* pos_atom;
@@ -670,11 +670,12 @@ WideChoice choose_wide(const MolannPrepared* h, const MolannPlan* p, long long L
   std::memset(&P, 0, sizeof(P));
   P.pos_atom = h->pos_atom; P.align_idx = p->align_idx; P.ref_x = p->ref_x; P.inv_ent = h->inv_ent;
   P.n_inp = p->n_inp; P.n_align = p->n_align; P.n_pos = h->n_pos; P.n_inv_ent = h->n_inv_ent; P.n_inv = h->n_inv;
-  P.n_units = h->n_units; P.use_angle = p->use_angle_value;
+  P.n_units = h->n_units; P.use_angle = p->use_angle_value; P.pos_is_align = h->pos_is_align;
   P.n_hidden = h->n_hidden; P.nkc1 = h->nkc1; P.n1p = h->n1p; P.nkc2 = h->nkc2; P.n2p = h->n2p;
   P.nlastp = h->nlastp; P.kout = h->kout;
   P.w1p = h->w1p; P.w2p = h->w2p; P.b1s = h->b1s; P.b2s = h->b2s; P.w3 = h->w3; P.b3 = h->b3;
-  P.slot_floats = FW_HDR_FLOATS + h->nkc1 * FW_CHUNK_FLOATS;
+  P.row_floats = FW_HDR_FLOATS + h->nkc1 * FW_KC;
+  P.slot_floats = FW_SUB * P.row_floats;
   int slots = env_int("MOLANN_B200_WIDE_SLOTS", 6);
   if (slots < 5) slots = 5;                       // a tile (4 sub-tiles) + at least one the geometry can run ahead in
   if (slots > FW_MAX_SLOTS) slots = FW_MAX_SLOTS;
@@ -687,6 +688,7 @@ WideChoice choose_wide(const MolannPrepared* h, const MolannPlan* p, long long L
   P.off_b2 = c.take((h->n_hidden == 2 ? h->n2p : 1) * 4, 16);
   P.off_w3 = c.take(h->kout * h->nlastp * 4, 16);
   P.off_ypart = c.take(4 * FW_M * h->kout * 4, 16);
+  P.off_rowbuf = c.take(FW_NGG * (2 * P.row_floats + 2 * FW_NGW * 12) * 4, 128);   // staging rows + moment partials
   const int fixed = c.off;
   // operand stages and the frame ring share what is left; plan tables move in when there is room
   int stages = env_int("MOLANN_B200_WIDE_STAGES", 2);
@@ -699,6 +701,7 @@ WideChoice choose_wide(const MolannPrepared* h, const MolannPlan* p, long long L
   while (ring > 2 && need(stages, ring) > budget) --ring;
   while (stages > 2 && need(stages, ring) > budget) --stages;
   if (ring < 2 || need(stages, ring) > budget) return ch;
+
   P.n_stages = stages;
   P.n_ring = ring;
   P.off_stage = c.take(stages * FW_STAGE_BYTES, 1024);
@@ -1373,6 +1376,17 @@ int molann_b200_prepare(const MolannPlan* plan, void* device_buffer, size_t byte
   h->n_inv_ent = (int)inv_ent.size() / ENTRY_INTS;
   h->n_inv = (int)inv_col.size();
   h->n_units = wide_units(h->n_pos, h->n_inv);
+  // position atoms == alignment selection (same order)?  Then the moments pass also delivers the position units.
+  h->pos_is_align = 0;
+  if (plan->n_align > 0 && plan->n_align == h->n_pos) {
+    std::vector<int32_t> al((size_t)plan->n_align);
+    s = check_cuda(cudaMemcpyAsync(al.data(), plan->align_idx, al.size() * 4, cudaMemcpyDeviceToHost, st));
+    if (!s) s = check_cuda(cudaStreamSynchronize(st));
+    if (s) { delete h; return s; }
+    h->pos_is_align = 1;
+    for (int u = 0; u < h->n_pos; ++u)
+      if (al[u] != pos_atom[u]) { h->pos_is_align = 0; break; }
+  }
   h->nkc1 = (h->n_units + FW_KU - 1) / FW_KU;
   if (h->nkc1 < 1) h->nkc1 = 1;
   h->kpad = h->nkc1 * FW_KC;
@@ -1431,7 +1445,7 @@ size_t molann_b200_prepared_workspace_bytes(const MolannPrepared* prepared, int6
   if (!dev.ok) dev.sm_count = 148;
   const long long ntiles = (L + FW_M - 1) / FW_M;
   const long long grid = dev.sm_count < ntiles ? dev.sm_count : ntiles;
-  const long long slot_floats = FW_HDR_FLOATS + (long long)prepared->nkc1 * FW_CHUNK_FLOATS;
+  const long long slot_floats = (long long)FW_SUB * (FW_HDR_FLOATS + prepared->nkc1 * FW_KC);
   return (size_t)grid * FW_MAX_SLOTS * slot_floats * 4;
 }
 

@@ -150,6 +150,7 @@ struct PreparedEntry {
   std::vector<int64_t> dims;
   Tensor buffer;
   MolannPrepared* handle = nullptr;
+  bool unsupported = false;      // the fused wide kernel does not fit this plan on this device: use the layered path
   ~PreparedEntry() { molann_b200_prepared_destroy(handle); }
 };
 std::mutex g_prepared_mutex;
@@ -284,12 +285,17 @@ Tensor molann_fwd_impl(const Tensor& x, const Tensor& align_idx, const Tensor& r
   if (L > 0 && molann_b200_wide_eligible(&h.plan)) {
     // big system, wide first layer: ONE persistent kernel on a prepared plan (csrc/fused_wide.cuh)
     auto prep = prepared_for(h, x, entries, align_idx, ref_x, params, act, use_angle_value);
-    ws_bytes = molann_b200_prepared_workspace_bytes(prep->handle, L);
-    ws = at::empty({static_cast<int64_t>(ws_bytes)}, x.options().dtype(at::kByte));
-    check_status(molann_b200_forward_prepared(prep->handle, &h.plan, x.data_ptr<float>(), L, y.data_ptr<float>(),
-                                              ws.data_ptr(), ws_bytes, cur_stream()),
-                 "forward_prepared");
-    return y;
+    if (!prep->unsupported) {
+      ws_bytes = molann_b200_prepared_workspace_bytes(prep->handle, L);
+      ws = at::empty({static_cast<int64_t>(ws_bytes)}, x.options().dtype(at::kByte));
+      const int st = molann_b200_forward_prepared(prep->handle, &h.plan, x.data_ptr<float>(), L, y.data_ptr<float>(),
+                                                  ws.data_ptr(), ws_bytes, cur_stream());
+      if (st != MOLANN_ERR_UNSUPPORTED) {
+        check_status(st, "forward_prepared");
+        return y;
+      }
+      prep->unsupported = true;          // e.g. frames too big for the shared-memory ring: the layered kernels serve it
+    }
   }
   if (molann_b200_path_for(&h.plan, 0) != 1) {
     ws_bytes = molann_b200_workspace_bytes(&h.plan, L, 0);
