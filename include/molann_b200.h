@@ -109,6 +109,15 @@ int molann_b200_backward(const MolannPlan* plan, const float* x, const float* gy
 int molann_b200_value_and_grad(const MolannPlan* plan, const float* x, const float* gy, int64_t L, float* y,
                                float* gx, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Jacobian / all-forces entry point: y[L, k] = model(x) and jac[k][L][n_inp][3] with
+ * jac[o] = d y[:, o] / dx -- every output's gradient plane from ONE pass over x (plane-major so that each plane is a
+ * dense [L, n_inp, 3] array like gx above).  What an MD plugin driving several collective variables needs per step;
+ * the reference does it with one autograd call per output (README.rst:51, molann/ann.py:109-111).  One kernel launch
+ * for the tensor-core small-system class, otherwise one value-and-gradient pass per output. */
+size_t molann_b200_jacobian_workspace_bytes(const MolannPlan* plan, int64_t L);
+int molann_b200_value_and_jacobian(const MolannPlan* plan, const float* x, int64_t L, float* y, float* jac,
+                                   void* workspace, size_t workspace_bytes, void* stream);
+
 /* feat[L, d_feat] = features(align(x)); the MLP fields of the plan are ignored */
 int molann_b200_preprocess_forward(const MolannPlan* plan, const float* x, int64_t L, float* feat, void* stream);
 int molann_b200_preprocess_backward(const MolannPlan* plan, const float* x, const float* gfeat, int64_t L,

@@ -66,6 +66,9 @@ def cabi():
     lib.molann_b200_preprocess_backward.argtypes = [P, vp, vp, i64, vp, vp]
     lib.molann_b200_align_forward.argtypes = [P, vp, i64, vp, vp]
     lib.molann_b200_align_backward.argtypes = [P, vp, vp, i64, vp, vp]
+    lib.molann_b200_jacobian_workspace_bytes.restype = sz
+    lib.molann_b200_jacobian_workspace_bytes.argtypes = [P, i64]
+    lib.molann_b200_value_and_jacobian.argtypes = [P, vp, i64, vp, vp, vp, sz, vp]
     lib.molann_b200_wide_eligible.argtypes = [P]
     lib.molann_b200_prepared_bytes.restype = sz
     lib.molann_b200_prepared_bytes.argtypes = [P]

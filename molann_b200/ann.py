@@ -301,6 +301,13 @@ class MolANN(torch.nn.Module):
         return self.preprocessing_layer
 
     @torch.jit.unused
+    def _value_and_jacobian_composed(self, x):
+        xg = x.detach().requires_grad_(True)
+        y = self.ann_layers(self.preprocessing_layer(xg))
+        planes = [torch.autograd.grad(y[:, o].sum(), xg, retain_graph=True)[0] for o in range(y.shape[1])]
+        return y.detach(), torch.stack(planes).detach()
+
+    @torch.jit.unused
     def _value_and_grad_composed(self, x, cotangent):
         xg = x.detach().requires_grad_(True)
         y = self.ann_layers(self.preprocessing_layer(xg))
@@ -342,6 +349,40 @@ class MolANN(torch.nn.Module):
                 return torch.ops.molann_b200.value_and_grad(
                     x, cotangent, flayer._no_idx, flayer._no_ref, flayer._entries, flayer._dim,
                     flayer.use_angle_value, params, self._act_id)
+
+    @torch.jit.export
+    def value_and_jacobian(self, x):
+        """``(y, J)`` with ``J[o] = d y[:, o] / dx``, shape ``[k, l, n_inp, 3]``: the force on every atom from every
+        output (collective variable) in ONE pass over ``x`` -- what an MD plugin that biases several CVs needs per
+        step.  Not part of the reference API: it replaces ``k`` calls of ``torch.autograd.grad(y[:, o].sum(), x)``."""
+        assert x.size(1) == self.preprocessing_layer.feature_layer.input_atom_num and x.size(2) == 3, \
+            'Input should be a 3d torch tensor with sizes [*, n_inp, 3]'
+        if not torch.jit.is_scripting():
+            if self._fused and not self._mlp_unchanged():
+                return self._value_and_jacobian_composed(x)
+        if not self._fused:
+            y0 = self.forward(x.detach())
+            planes: List[torch.Tensor] = []
+            for o in range(y0.size(1)):
+                cot = torch.zeros_like(y0)
+                cot[:, o] = 1.0
+                planes.append(self.value_and_grad(x, cot)[1])
+            return y0.detach(), torch.stack(planes)
+        else:
+            flayer = self.preprocessing_layer.feature_layer
+            params: List[torch.Tensor] = []
+            for layer in self.ann_layers:
+                if hasattr(layer, 'weight'):
+                    params.append(layer.weight)
+                    params.append(layer.bias)
+            if self._fused_align:
+                return torch.ops.molann_b200.value_and_jacobian(
+                    x, self.preprocessing_layer.align_layer._align_idx, self.preprocessing_layer.align_layer.ref_x,
+                    flayer._entries, flayer._dim, flayer.use_angle_value, params, self._act_id)
+            else:
+                return torch.ops.molann_b200.value_and_jacobian(
+                    x, flayer._no_idx, flayer._no_ref, flayer._entries, flayer._dim, flayer.use_angle_value,
+                    params, self._act_id)
 
     def forward(self, x):
         """the forward map ``[l, n_inp, 3] -> [l, k]``"""

@@ -75,6 +75,30 @@ def build_torch_shim(force=False, verbose=False):
     return LIB_TORCH
 
 
+CONSUMER_SRC = os.path.join(os.path.dirname(HERE), "tests", "host", "consumer.cpp")
+CONSUMER_BIN = os.path.join(os.path.dirname(HERE), "tests", "host", "consumer")
+
+
+def build_consumer(force=False, verbose=False):
+    """tests/host/consumer: the libtorch-only C++ program that loads an exported model the way an MD plugin does."""
+    import torch
+    from torch.utils import cpp_extension
+    if not force and _newer(CONSUMER_BIN, [CONSUMER_SRC]):
+        return CONSUMER_BIN
+    inc = []
+    for p in cpp_extension.include_paths():
+        inc += ["-isystem", p]
+    torch_lib = os.path.join(os.path.dirname(torch.__file__), "lib")
+    abi = int(torch._C._GLIBCXX_USE_CXX11_ABI)
+    cmd = ["g++", "-O1", "-std=c++17", "-D_GLIBCXX_USE_CXX11_ABI=%d" % abi, CONSUMER_SRC, "-o", CONSUMER_BIN] + inc + [
+        "-L" + torch_lib, "-Wl,--no-as-needed", "-ltorch", "-ltorch_cpu", "-lc10", "-ltorch_cuda", "-lc10_cuda",
+        "-ldl", "-Wl,-rpath," + torch_lib]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.run(cmd, check=True)
+    return CONSUMER_BIN
+
+
 def build_all(force=False, verbose=False):
     build_kernels(force=force, verbose=verbose)
     build_torch_shim(force=force, verbose=verbose)

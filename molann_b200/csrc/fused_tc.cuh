@@ -525,11 +525,16 @@ __device__ __forceinline__ long long vg_gtime() {
 // ACT is a template parameter: with the activation chosen at run time every element carried its own branch, the
 // 16 elements of a chunk could not overlap, and the two epilogues took 8k + 11k of a tile's 42k cycles
 // (tests/cuda/ws_trace.cu).
-template <int TILES, int ACT>
+// JAC: Jacobian mode (value_and_jacobian): no cotangent; the forward runs once per tile, act'(z) of
+// BOTH hidden layers stays parked in TMEM (64 more columns: needs TILES == 1), and the backward chain -- two small
+// contractions, feature + alignment backward, tile store -- runs once per output with gz = W_last[o, :] * act'(z),
+// writing plane o of gx[kout][L][n_inp][3] (plane-major, so a tile of a plane is one contiguous bulk store).
+template <int TILES, int ACT, bool JAC = false>
 __global__ void __launch_bounds__(TILES * TC_F, 1)
 fused_tc_value_grad_kernel(const __grid_constant__ DevPlan p, const __grid_constant__ TcVgLayout vl,
                            const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ y,
                            float* __restrict__ gx, long long L, int use_tma) {
+  static_assert(!JAC || TILES == 1, "Jacobian mode keeps five 64-column blocks per tile in TMEM");
   extern __shared__ __align__(1024) unsigned char smem[];
   constexpr int NT = TILES * TC_F;
   const TcLayout& lay = vl.base;
@@ -569,14 +574,15 @@ fused_tc_value_grad_kernel(const __grid_constant__ DevPlan p, const __grid_const
     mbar_init(mbar_mma, 1);
     fence_mbar_init();
   }
-  if (warp == 0) tmem_alloc(tptr, TILES * 256);
+  constexpr uint32_t TMEM_COLS = JAC ? 512u : (uint32_t)TILES * 256u;
+  if (warp == 0) tmem_alloc(tptr, TMEM_COLS);
   fence_proxy_async_smem();
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tbase = *tptr + (uint32_t)wg * 256u;
   const uint32_t lane_addr = tbase + ((uint32_t)((warp & 3) * 32) << 16);
-  constexpr uint32_t COL_AHI = 0, COL_ALO = 64, COL_D = 128, COL_H1 = 192;
+  constexpr uint32_t COL_AHI = 0, COL_ALO = 64, COL_D = 128, COL_H1 = 192, COL_H2 = 256;
 
   const long long ntiles = (L + TC_F - 1) / TC_F;
   const uint32_t tile_bytes = (uint32_t)TC_F * (uint32_t)n3 * 4u;
@@ -631,7 +637,7 @@ fused_tc_value_grad_kernel(const __grid_constant__ DevPlan p, const __grid_const
     VG_EVT(vg_it, 1);
     float go[8];                               // this frame's output cotangent: issued now, consumed after two MMAs
 #pragma unroll
-    for (int o = 0; o < 8; ++o) go[o] = (o < kout && wt < nf) ? __ldg(gy + (f_base + wt) * kout + o) : 0.f;
+    for (int o = 0; o < 8; ++o) go[o] = (!JAC && o < kout && wt < nf) ? __ldg(gy + (f_base + wt) * kout + o) : 0.f;
     // ---- geometry ----
     const int f = wt < nf ? wt : nf - 1;
     const float* xf = xs + f * n3;
@@ -743,11 +749,16 @@ fused_tc_value_grad_kernel(const __grid_constant__ DevPlan p, const __grid_const
             float hh, dd;
             act_value_and_grad_t<ACT>(z[4 * q + i] + bb[i], hh, dd);
             z[4 * q + i] = hh;
-            split_tf32_rn(gh[4 * q + i] * dd, hi[4 * q + i], lo[4 * q + i]);      // gz of the last hidden layer
+            if (JAC) hi[4 * q + i] = __float_as_uint(dd);                         // parked: every plane needs it
+            else split_tf32_rn(gh[4 * q + i] * dd, hi[4 * q + i], lo[4 * q + i]); // gz of the last hidden layer
           }
         }
-        tmem_st16(lane_addr + COL_AHI + c, hi);
-        tmem_st16(lane_addr + COL_ALO + c, lo);
+        if (JAC) {
+          tmem_st16(lane_addr + COL_H2 + c, hi);
+        } else {
+          tmem_st16(lane_addr + COL_AHI + c, hi);
+          tmem_st16(lane_addr + COL_ALO + c, lo);
+        }
         if (y != nullptr) {
 #pragma unroll
           for (int o = 0; o < 8; ++o) {
@@ -774,6 +785,24 @@ fused_tc_value_grad_kernel(const __grid_constant__ DevPlan p, const __grid_const
       }
     }
     VG_EVT(vg_it, 8);
+    const int nplanes = JAC ? kout : 1;
+#pragma unroll 1
+    for (int plane = 0; plane < nplanes; ++plane) {
+    if (JAC) {                   // gz of the last hidden layer for output `plane`: W_last[plane, :] * act'(z)
+      const float* wl = reinterpret_cast<const float*>(smem + lay.wlast_off) + plane * TC_MAXW;
+      const int np = lay.np[nh - 1];
+#pragma unroll 1
+      for (int c = 0; c < np; c += 16) {
+        float dk[16];
+        tmem_ld16(lane_addr + COL_H2 + c, dk);
+        tmem_wait_ld();
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) split_tf32_rn(wl[c + i] * dk[i], hi[i], lo[i]);
+        tmem_st16(lane_addr + COL_AHI + c, hi);
+        tmem_st16(lane_addr + COL_ALO + c, lo);
+      }
+    }
     // ---- backward through the tensor-core layers: gh_k = gz_{k+1} W_k  (operand W^T, K-major) ----
     for (int k = nh - 1; k >= 0; --k) {
       const int kb = lay.np[k];            // contraction width (outputs of forward layer k)
@@ -845,8 +874,8 @@ fused_tc_value_grad_kernel(const __grid_constant__ DevPlan p, const __grid_const
     fence_proxy_async_smem();
     wg_sync(wg);
     const long long next = tile + tstride;
-    if (next < ntiles && is_tma_tile(next)) issue_x(next);       // xs is free
-    float* dst = gx + f_base * n3;
+    if (plane == nplanes - 1 && next < ntiles && is_tma_tile(next)) issue_x(next);       // xs is free
+    float* dst = gx + ((long long)plane * L + f_base) * n3;
     if (is_tma_tile(tile)) {
       if (wt == 0) {
         bulk_s2g(dst, gxs, tile_bytes);
@@ -866,6 +895,7 @@ fused_tc_value_grad_kernel(const __grid_constant__ DevPlan p, const __grid_const
         atomicExch(gx_lock, 0);
       }
     }
+    }                            // planes
   }
   if (wt == 0) bulk_wait0();
 #ifdef MOLANN_WS_TRACE
@@ -873,7 +903,7 @@ fused_tc_value_grad_kernel(const __grid_constant__ DevPlan p, const __grid_const
 #endif
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(*tptr, TILES * 256);
+  if (warp == 0) tmem_dealloc(*tptr, TMEM_COLS);
 }
 
 }  // namespace molann

@@ -459,7 +459,7 @@ struct TcVgChoice {
   TcVgLayout vl;
 };
 
-TcVgChoice choose_tc_vg(const MolannPlan* p, const DeviceInfo& dev) {
+TcVgChoice choose_tc_vg(const MolannPlan* p, const DeviceInfo& dev, int force_tiles = 0) {
   TcVgChoice ch;
   std::memset(&ch.vl, 0, sizeof(ch.vl));
   if (env_int("MOLANN_B200_TC", 1) == 0 || env_int("MOLANN_B200_PATH", -1) == 0) return ch;
@@ -471,7 +471,7 @@ TcVgChoice choose_tc_vg(const MolannPlan* p, const DeviceInfo& dev) {
   if ((long long)p->n_entries * ENTRY_INTS * 4 > 32 * 1024) return ch;
   const int xs_bytes = TC_F * 3 * p->n_inp * 4;
   if (xs_bytes > 64 * 1024) return ch;
-  const int want_tiles = env_int("MOLANN_B200_VG_TILES", 2);
+  const int want_tiles = force_tiles > 0 ? force_tiles : env_int("MOLANN_B200_VG_TILES", 2);
   for (int tiles = (want_tiles == 1 ? 1 : 2); tiles >= 1; --tiles) {
     TcVgLayout vl;
     std::memset(&vl, 0, sizeof(vl));
@@ -730,6 +730,27 @@ int launch_wide_act(const WideChoice& ch, const float* x, float* y, long long L,
   if (s) return s;
   kern<<<(unsigned)ch.grid, FW_THREADS, ch.P.total_smem, st>>>(ch.P, x, y, L);
   return post_launch();
+}
+
+// Jacobian mode of the same kernel (one tile per CTA: five 64-column TMEM blocks per tile)
+template <int ACT>
+int launch_tc_jac(const DevPlan& dp, const TcVgLayout& vl, const float* x, float* y, float* jac, long long L,
+                  const DeviceInfo& dev, cudaStream_t st) {
+  auto kern = fused_tc_value_grad_kernel<1, ACT, true>;
+  int s = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, vl.total_bytes));
+  if (s) return s;
+  const long long ntiles = (L + TC_F - 1) / TC_F;
+  long long grid = dev.sm_count;                        // 512 TMEM columns per CTA: one CTA per SM
+  if (grid > ntiles) grid = ntiles;
+  const int use_tma = ((reinterpret_cast<uintptr_t>(x) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(jac) & 15u) == 0) &&
+                      ((TC_F * 3 * dp.n_inp * 4) % 16 == 0) && ((L * 3 * dp.n_inp * 4) % 16 == 0);
+  kern<<<(unsigned)grid, TC_F, vl.total_bytes, st>>>(dp, vl, x, nullptr, y, jac, L, use_tma);
+  return post_launch();
+}
+
+__global__ void onehot_rows_kernel(float* __restrict__ cot, long long L, int k, int plane) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < L * k; i += (long long)gridDim.x * blockDim.x)
+    cot[i] = (int)(i % k) == plane ? 1.f : 0.f;
 }
 
 #define SMALL_DISPATCH(ch, FN, ...)                                   \
@@ -1479,6 +1500,54 @@ void molann_b200_prepared_destroy(MolannPrepared* prepared) {
     prepared->magic = 0;
     delete prepared;
   }
+}
+
+size_t molann_b200_jacobian_workspace_bytes(const MolannPlan* plan, int64_t L) {
+  if (validate_full(plan) != MOLANN_OK || plan->n_layers < 1 || L <= 0) return 0;
+  return general_ws_bytes(plan, L, true) + align256((size_t)L * plan->dims[plan->n_layers] * 4);
+}
+
+int molann_b200_value_and_jacobian(const MolannPlan* plan, const float* x, int64_t L, float* y, float* jac,
+                                   void* workspace, size_t workspace_bytes, void* stream) {
+  int s = validate_full(plan);
+  if (s) return s;
+  if (plan->n_layers < 1) return MOLANN_ERR_UNSUPPORTED;
+  if (L < 0) return MOLANN_ERR_PLAN;
+  if (L == 0) return MOLANN_OK;
+  if (!x || !y || !jac) return MOLANN_ERR_NULL;
+  if (misaligned4(x) || misaligned4(y) || misaligned4(jac)) return MOLANN_ERR_ALIGNMENT;
+  const DeviceInfo dev = device_info();
+  if (!dev.ok) return MOLANN_ERR_CUDA;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int kout = plan->dims[plan->n_layers];
+  if (env_int("MOLANN_B200_JAC_FUSED", 1) != 0) {
+    const TcVgChoice vg = choose_tc_vg(plan, dev, 1);
+    if (vg.ok && vg.tiles == 1) {                  // ONE launch: every plane while the tile is on chip
+      const DevPlan dp = to_dev(plan);
+      switch (plan->act_id) {
+        case MOLANN_ACT_TANH: return launch_tc_jac<ACT_TANH>(dp, vg.vl, x, y, jac, (long long)L, dev, st);
+        case MOLANN_ACT_RELU: return launch_tc_jac<ACT_RELU>(dp, vg.vl, x, y, jac, (long long)L, dev, st);
+        case MOLANN_ACT_SIGMOID: return launch_tc_jac<ACT_SIGMOID>(dp, vg.vl, x, y, jac, (long long)L, dev, st);
+        default: return launch_tc_jac<ACT_IDENTITY>(dp, vg.vl, x, y, jac, (long long)L, dev, st);
+      }
+    }
+  }
+  // other kernel families: one value-and-gradient pass per output with a one-hot cotangent
+  const size_t cot_bytes = align256((size_t)L * kout * 4);
+  if (!workspace || workspace_bytes < molann_b200_jacobian_workspace_bytes(plan, L)) return MOLANN_ERR_WORKSPACE;
+  float* cot = static_cast<float*>(workspace);
+  char* rest = static_cast<char*>(workspace) + cot_bytes;
+  for (int o = 0; o < kout; ++o) {
+    unsigned blocks = (unsigned)(((long long)L * kout + 255) / 256);
+    if (blocks > 1184u) blocks = 1184u;
+    onehot_rows_kernel<<<blocks, 256, 0, st>>>(cot, (long long)L, kout, o);
+    s = post_launch();
+    if (s) return s;
+    s = molann_b200_value_and_grad(plan, x, cot, L, y, jac + (size_t)o * (size_t)L * 3 * plan->n_inp, rest,
+                                   workspace_bytes - cot_bytes, stream);
+    if (s) return s;
+  }
+  return MOLANN_OK;
 }
 
 int molann_b200_preprocess_forward(const MolannPlan* plan, const float* x, int64_t L, float* feat, void* stream) {

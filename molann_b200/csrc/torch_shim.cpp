@@ -385,6 +385,29 @@ std::tuple<Tensor, Tensor> value_and_grad_impl(const Tensor& x, const Tensor& gy
   return std::make_tuple(y, gx);
 }
 
+// y = model(x) and jac[k, L, n_inp, 3] = d y[:, o] / dx for every output o (no autograd graph)
+std::tuple<Tensor, Tensor> value_and_jacobian_impl(const Tensor& x, const Tensor& align_idx, const Tensor& ref_x,
+                                                   const Tensor& entries, int64_t d_feat, bool use_angle_value,
+                                                   at::TensorList params, int64_t act) {
+  check_x(x, "value_and_jacobian");
+  NvtxRange nvtx("molann_b200::value_and_jacobian");
+  c10::cuda::CUDAGuard guard(x.device());
+  PlanHolder h;
+  fill_geometry(h, x, align_idx, ref_x);
+  fill_features(h, x, entries, d_feat, use_angle_value);
+  fill_mlp(h, x, params, act);
+  const int64_t L = x.size(0);
+  const int64_t kout = h.plan.dims[h.plan.n_layers];
+  Tensor y = at::empty({L, kout}, x.options());
+  Tensor jac = at::empty({kout, L, x.size(1), 3}, x.options());
+  const size_t ws_bytes = molann_b200_jacobian_workspace_bytes(&h.plan, L);
+  Tensor ws = at::empty({static_cast<int64_t>(ws_bytes > 0 ? ws_bytes : 1)}, x.options().dtype(at::kByte));
+  check_status(molann_b200_value_and_jacobian(&h.plan, x.data_ptr<float>(), L, y.data_ptr<float>(),
+                                              jac.data_ptr<float>(), ws.data_ptr(), ws_bytes, cur_stream()),
+               "value_and_jacobian");
+  return std::make_tuple(y, jac);
+}
+
 // ------------------------------------------------------------------------------------------
 // autograd
 // ------------------------------------------------------------------------------------------
@@ -488,6 +511,15 @@ std::tuple<Tensor, Tensor> value_and_grad_autograd(const Tensor& x, const Tensor
   return value_and_grad_impl(x.detach(), gy.detach(), align_idx, ref_x, entries, d_feat, use_angle_value, plain, act);
 }
 
+std::tuple<Tensor, Tensor> value_and_jacobian_autograd(const Tensor& x, const Tensor& align_idx, const Tensor& ref_x,
+                                                       const Tensor& entries, int64_t d_feat, bool use_angle_value,
+                                                       at::TensorList params, int64_t act) {
+  at::AutoDispatchBelowADInplaceOrView g;
+  std::vector<Tensor> plain;
+  for (const Tensor& p : params) plain.push_back(p.detach());
+  return value_and_jacobian_impl(x.detach(), align_idx, ref_x, entries, d_feat, use_angle_value, plain, act);
+}
+
 int64_t launch_count() { return molann_b200_launch_count(); }
 
 }  // namespace
@@ -499,6 +531,8 @@ TORCH_LIBRARY(molann_b200, m) {
         "Tensor[] params, int act) -> Tensor");
   m.def("value_and_grad(Tensor x, Tensor gy, Tensor align_idx, Tensor ref_x, Tensor entries, int d_feat, "
         "bool use_angle_value, Tensor[] params, int act) -> (Tensor, Tensor)");
+  m.def("value_and_jacobian(Tensor x, Tensor align_idx, Tensor ref_x, Tensor entries, int d_feat, "
+        "bool use_angle_value, Tensor[] params, int act) -> (Tensor, Tensor)");
   m.def("launch_count() -> int", &launch_count);
 }
 
@@ -507,6 +541,7 @@ TORCH_LIBRARY_IMPL(molann_b200, CUDA, m) {
   m.impl("preprocess", &preprocess_fwd_impl);
   m.impl("molann", &molann_fwd_impl);
   m.impl("value_and_grad", &value_and_grad_impl);
+  m.impl("value_and_jacobian", &value_and_jacobian_impl);
 }
 
 TORCH_LIBRARY_IMPL(molann_b200, Autograd, m) {
@@ -514,4 +549,5 @@ TORCH_LIBRARY_IMPL(molann_b200, Autograd, m) {
   m.impl("preprocess", &preprocess_autograd);
   m.impl("molann", &molann_autograd);
   m.impl("value_and_grad", &value_and_grad_autograd);
+  m.impl("value_and_jacobian", &value_and_jacobian_autograd);
 }
