@@ -653,6 +653,24 @@ def measure_workload(name, args, rank, local_rank, world, dd, full):
                "result_checksum": float(yh[:: max(1, frames // 1024)].double().sum()),
                "per_rank_h2d_GBps": [pipe.h2d_bytes * ke / (r * 1e-3) / 1e9 for r in ranks]}
         if full:
+            # the same leg over the int16 wire format (half the H2D bytes; decode = one small kernel per chunk)
+            from molann_b200.stream import quantize_frames
+            qh, origin, res = quantize_frames(xh)
+            qh = qh.pin_memory()
+            for _ in range(2):
+                pipe.run_wire(qh, origin, res, yh)
+            dd.barrier()
+            t0 = time.perf_counter()
+            for _ in range(ke):
+                pipe.run_wire(qh, origin, res, yh)
+            torch.cuda.synchronize()
+            ms_w = max(dd.gather(1e3 * (time.perf_counter() - t0)))
+            e2e["int16_wire"] = {"value": world * frames * ke / (ms_w * 1e-3), "unit": UNIT,
+                                 "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes,
+                                 "ms_per_step": ms_w / ke, "resolution": res,
+                                 "api": "HostPipeline.run_wire(quantize_frames(x)): lossy transport, NOT the parity "
+                                        "default (outputs are exact functions of the decoded coordinates)"}
+            del qh
             coth = cot.cpu().pin_memory()
             gxh = torch.empty(frames, spec.n_inp, 3).pin_memory()
             pipe.run(xh, yh, coth, gxh)
@@ -744,8 +762,51 @@ def latency_probe(dd):
                 y, g = model.value_and_grad(x, cot)
                 y.cpu()
             t4 = time.perf_counter()
+            t5 = time.perf_counter()
+            for _ in range(n):
+                y, jac = model.value_and_jacobian(x)
+                y.cpu()
+            t6 = time.perf_counter()
         res["L=%d" % L] = {"forward_us_per_call": 1e6 * (t1 - t0) / n, "value_and_grad_us_per_call": 1e6 * (t2 - t1) / n,
-                           "value_and_grad_sync_us_per_call": 1e6 * (t4 - t3) / n}
+                           "value_and_grad_sync_us_per_call": 1e6 * (t4 - t3) / n,
+                           "value_and_jacobian_sync_us_per_call": 1e6 * (t6 - t5) / n}
+    # the reference's way on the host cores: y = model(x), then one autograd call per output
+    try:
+        import warnings
+        api, kind, where = reference_api()
+        if api is not None:
+            cpu_model_, _ = S.build_model(spec, api)
+            for L in (1, 32, 128):
+                xc = S.make_frames(spec, L, seed=5).requires_grad_(True)
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    for _ in range(3):
+                        yc = cpu_model_(xc)
+                        [torch.autograd.grad(yc[:, o].sum(), xc, retain_graph=True) for o in range(yc.shape[1])]
+                    t0 = time.perf_counter()
+                    nrep = 50
+                    for _ in range(nrep):
+                        yc = cpu_model_(xc)
+                        [torch.autograd.grad(yc[:, o].sum(), xc, retain_graph=True) for o in range(yc.shape[1])]
+                    res["L=%d" % L]["reference_cpu_value_and_jacobian_us_per_call"] = 1e6 * (time.perf_counter() - t0) / nrep
+            res["reference"] = "%s (%s), %d torch threads" % (kind, where, torch.get_num_threads())
+    except Exception as exc:  # noqa: BLE001
+        res["reference_error"] = repr(exc)
+    # throughput of the all-outputs Jacobian at the bench size
+    xb = S.make_frames(spec, 1 << 20, device="cuda", seed=6)
+    for _ in range(3):
+        model.value_and_jacobian(xb)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        model.value_and_jacobian(xb)
+    e1.record()
+    torch.cuda.synchronize()
+    res["value_and_jacobian_2^20_frames"] = {"ms_per_call": e0.elapsed_time(e1) / 10,
+                                            "frames_per_s": (1 << 20) * 10 / (e0.elapsed_time(e1) * 1e-3),
+                                            "planes": spec.out_dim(), "launches_per_call": 1}
+    del xb
     res["note"] = ("C2 model, back-to-back calls through MolANN.forward / MolANN.value_and_grad (host wall clock / "
                    "calls); *_sync: each call followed by a device->host read of y")
     return res

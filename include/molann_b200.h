@@ -118,6 +118,13 @@ size_t molann_b200_jacobian_workspace_bytes(const MolannPlan* plan, int64_t L);
 int molann_b200_value_and_jacobian(const MolannPlan* plan, const float* x, int64_t L, float* y, float* jac,
                                    void* workspace, size_t workspace_bytes, void* stream);
 
+/* Trajectory wire format (the reference only ever builds a frame as torch.tensor(ag.positions),
+ * molann/ann.py:106): coordinates travel over PCIe as int16 steps of `resolution` around a batch origin, half the
+ * bytes of fp32.  x[i] = origin_host[i % 3] + q[i] * resolution, one fp32 FMA (a host decoder doing the same FMA gets
+ * the same bits, which is how the parity tests compare).  n_values = L * n_inp * 3.  `origin_host` is a HOST array. */
+int molann_b200_decode_frames_i16(const int16_t* q, int64_t n_values, const float* origin_host, float resolution,
+                                  float* x, void* stream);
+
 /* feat[L, d_feat] = features(align(x)); the MLP fields of the plan are ignored */
 int molann_b200_preprocess_forward(const MolannPlan* plan, const float* x, int64_t L, float* feat, void* stream);
 int molann_b200_preprocess_backward(const MolannPlan* plan, const float* x, const float* gfeat, int64_t L,

@@ -66,6 +66,7 @@ def cabi():
     lib.molann_b200_preprocess_backward.argtypes = [P, vp, vp, i64, vp, vp]
     lib.molann_b200_align_forward.argtypes = [P, vp, i64, vp, vp]
     lib.molann_b200_align_backward.argtypes = [P, vp, vp, i64, vp, vp]
+    lib.molann_b200_decode_frames_i16.argtypes = [vp, i64, ctypes.POINTER(ctypes.c_float), ctypes.c_float, vp, vp]
     lib.molann_b200_jacobian_workspace_bytes.restype = sz
     lib.molann_b200_jacobian_workspace_bytes.argtypes = [P, i64]
     lib.molann_b200_value_and_jacobian.argtypes = [P, vp, i64, vp, vp, vp, sz, vp]

@@ -748,6 +748,43 @@ int launch_tc_jac(const DevPlan& dp, const TcVgLayout& vl, const float* x, float
   return post_launch();
 }
 
+// Wire format of the ingestion path: coordinates as int16 steps of `res` around a batch origin,
+//   x[f, a, c] = origin[c] + q[f, a, c] * res        (one FMA in fp32 -- the host decoder does the same, bit for bit)
+// Eight values per thread: one 16-byte load, two 16-byte stores.
+__global__ void __launch_bounds__(256)
+decode_frames_i16_kernel(const int16_t* __restrict__ q, long long n, float o0, float o1, float o2, float res,
+                         float* __restrict__ x, int vec) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  if (vec) {
+    const long long n8 = n >> 3;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n8; t += stride) {
+      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(q) + t);
+      const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+      int c = (int)((t * 8) % 3);
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int16_t s16 = (int16_t)((w[j >> 1] >> ((j & 1) * 16)) & 0xffffu);
+        const float o = c == 0 ? o0 : (c == 1 ? o1 : o2);
+        v[j] = fmaf((float)s16, res, o);
+        c = c == 2 ? 0 : c + 1;
+      }
+      float4* dst = reinterpret_cast<float4*>(x) + 2 * t;
+      dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+      dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+    for (long long i = (n8 << 3) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+      const int c = (int)(i % 3);
+      x[i] = fmaf((float)q[i], res, c == 0 ? o0 : (c == 1 ? o1 : o2));
+    }
+  } else {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+      const int c = (int)(i % 3);
+      x[i] = fmaf((float)q[i], res, c == 0 ? o0 : (c == 1 ? o1 : o2));
+    }
+  }
+}
+
 __global__ void onehot_rows_kernel(float* __restrict__ cot, long long L, int k, int plane) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < L * k; i += (long long)gridDim.x * blockDim.x)
     cot[i] = (int)(i % k) == plane ? 1.f : 0.f;
@@ -1500,6 +1537,24 @@ void molann_b200_prepared_destroy(MolannPrepared* prepared) {
     prepared->magic = 0;
     delete prepared;
   }
+}
+
+int molann_b200_decode_frames_i16(const int16_t* q, int64_t n_values, const float* origin_host, float resolution,
+                                  float* x, void* stream) {
+  if (n_values < 0 || n_values % 3 != 0) return MOLANN_ERR_PLAN;
+  if (n_values == 0) return MOLANN_OK;
+  if (!q || !x || !origin_host) return MOLANN_ERR_NULL;
+  if ((reinterpret_cast<uintptr_t>(q) & 1u) || misaligned4(x)) return MOLANN_ERR_ALIGNMENT;
+  const DeviceInfo dev = device_info();
+  if (!dev.ok) return MOLANN_ERR_CUDA;
+  const int vec = ((reinterpret_cast<uintptr_t>(q) & 15u) == 0 && (reinterpret_cast<uintptr_t>(x) & 15u) == 0) ? 1 : 0;
+  long long blocks = (n_values / 8 + 255) / 256;
+  const long long cap = (long long)dev.sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  decode_frames_i16_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      q, (long long)n_values, origin_host[0], origin_host[1], origin_host[2], resolution, x, vec);
+  return post_launch();
 }
 
 size_t molann_b200_jacobian_workspace_bytes(const MolannPlan* plan, int64_t L) {

@@ -520,6 +520,23 @@ std::tuple<Tensor, Tensor> value_and_jacobian_autograd(const Tensor& x, const Te
   return value_and_jacobian_impl(x.detach(), align_idx, ref_x, entries, d_feat, use_angle_value, plain, act);
 }
 
+// int16 wire frames -> fp32 coordinates (trajectory ingestion, include/molann_b200.h)
+Tensor decode_frames_impl(const Tensor& q, double ox, double oy, double oz, double resolution) {
+  TORCH_CHECK(q.is_cuda(), "molann_b200::decode_frames: the wire frames must be a CUDA tensor, got ", q.device());
+  TORCH_CHECK(q.scalar_type() == at::kShort, "molann_b200::decode_frames: wire frames must be int16, got ",
+              q.scalar_type());
+  TORCH_CHECK(q.dim() == 3 && q.size(2) == 3 && q.is_contiguous(),
+              "molann_b200::decode_frames: wire frames must be a contiguous [L, n_inp, 3] tensor");
+  NvtxRange nvtx("molann_b200::decode_frames");
+  c10::cuda::CUDAGuard guard(q.device());
+  Tensor x = at::empty(q.sizes(), q.options().dtype(at::kFloat));
+  const float origin[3] = {static_cast<float>(ox), static_cast<float>(oy), static_cast<float>(oz)};
+  check_status(molann_b200_decode_frames_i16(q.data_ptr<int16_t>(), q.numel(), origin, static_cast<float>(resolution),
+                                             x.data_ptr<float>(), cur_stream()),
+               "decode_frames_i16");
+  return x;
+}
+
 int64_t launch_count() { return molann_b200_launch_count(); }
 
 }  // namespace
@@ -533,6 +550,7 @@ TORCH_LIBRARY(molann_b200, m) {
         "bool use_angle_value, Tensor[] params, int act) -> (Tensor, Tensor)");
   m.def("value_and_jacobian(Tensor x, Tensor align_idx, Tensor ref_x, Tensor entries, int d_feat, "
         "bool use_angle_value, Tensor[] params, int act) -> (Tensor, Tensor)");
+  m.def("decode_frames(Tensor q, float ox, float oy, float oz, float resolution) -> Tensor");
   m.def("launch_count() -> int", &launch_count);
 }
 
@@ -542,6 +560,7 @@ TORCH_LIBRARY_IMPL(molann_b200, CUDA, m) {
   m.impl("molann", &molann_fwd_impl);
   m.impl("value_and_grad", &value_and_grad_impl);
   m.impl("value_and_jacobian", &value_and_jacobian_impl);
+  m.impl("decode_frames", &decode_frames_impl);
 }
 
 TORCH_LIBRARY_IMPL(molann_b200, Autograd, m) {

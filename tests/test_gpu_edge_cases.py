@@ -213,3 +213,38 @@ def test_host_pipeline_against_the_oracle():
     pipe.run(xh, yh, coth, gxh)
     assert_parity(yh, y64, y32, TOL, "pipeline y (with gradient)")
     assert_parity(gxh, gx64, gx32, TOL, "pipeline gx")
+
+
+def test_int16_wire_format_pipeline():
+    """Ingestion over the int16 wire format (half the H2D bytes): the device decode is ONE fp32 FMA per coordinate,
+    the host decoder gives the same coordinates, and the model outputs match the oracle evaluated on those."""
+    from helpers import oracle_model
+    from molann_b200.stream import HostPipeline, dequantize_frames, quantize_frames
+    spec = S.get_spec("C2")
+    model, _ = S.build_model(spec)
+    sd = model.state_dict()
+    ws = [sd["ann_layers.%dth_layer.weight" % k] for k in (1, 2, 3)]
+    bs = [sd["ann_layers.%dth_layer.bias" % k] for k in (1, 2, 3)]
+    model = model.cuda()
+    L = 6001
+    x = S.make_frames(spec, L, seed=8)
+    q, origin, res = quantize_frames(x, resolution=0.001)              # XTC-like: 0.001 Angstrom steps or coarser
+    assert q.dtype == torch.int16 and float((dequantize_frames(q, origin, res) - x).abs().max()) <= 0.5 * res + 4e-7 * float(x.abs().max())
+    xd = torch.ops.molann_b200.decode_frames(q.cuda(), origin[0], origin[1], origin[2], res).cpu()
+    xh = dequantize_frames(q, origin, res)
+    assert float((xd - xh).abs().max()) <= 2e-6 * float(xh.abs().max())  # same FMA; at most an ulp from double rounding
+    flat = torch.zeros(q.numel() + 1, dtype=torch.int16, device="cuda")  # a wire buffer 2 bytes off the 16-byte grid
+    qv = flat[1:].view(q.shape)
+    qv.copy_(q)
+    assert torch.equal(torch.ops.molann_b200.decode_frames(qv, origin[0], origin[1], origin[2], res).cpu(), xd)
+    y64 = oracle_model(spec, ws, bs)(xd)
+    y32 = oracle_model(spec, ws, bs, torch.float32)(xd)
+    qh, yh = q.pin_memory(), torch.empty(L, 2).pin_memory()
+    pipe = HostPipeline(model, 22, 2, chunk_frames=1024)
+    pipe.run_wire(qh, origin, res, yh)
+    assert_parity(yh, y64, y32, TOL, "wire pipeline y")
+    assert pipe.h2d_bytes == L * 22 * 3 * 2 and pipe.d2h_bytes == L * 2 * 4
+    # the coding error itself: outputs move by O(resolution), far above 1e-5 -- which is why fp32 stays the default
+    with torch.no_grad():
+        y_exact = model(x.cuda()).cpu()
+    assert float((yh - y_exact).abs().max()) < 50 * res

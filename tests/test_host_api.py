@@ -259,3 +259,20 @@ def test_autoencoder_step_surface():
     g = dec.weight.grad.clone()
     tr.step(x)
     assert torch.allclose(dec.weight.detach(), w0 - 0.1 * g, atol=1e-12)
+
+
+def test_wire_format_host_codec():
+    """int16 wire format (molann_b200.stream): coding error <= resolution / 2, exact round trip of decoded frames."""
+    import torch
+    from molann_b200 import synthetic as S
+    from molann_b200.stream import dequantize_frames, quantize_frames
+    x = S.make_frames(S.get_spec("C2"), 4000)
+    q, origin, res = quantize_frames(x)
+    assert q.dtype == torch.int16 and tuple(q.shape) == tuple(x.shape) and int(q.abs().max()) <= 32767
+    xd = dequantize_frames(q, origin, res)
+    assert float((xd - x).abs().max()) <= 0.5 * res + 4e-7 * float(x.abs().max())   # + fp32 rounding of the sum
+    q2, o2, r2 = quantize_frames(x, resolution=0.01)
+    assert abs(r2 - 0.01) < 1e-9 and float((dequantize_frames(q2, o2, r2) - x).abs().max()) <= 0.5 * 0.01 + 4e-7 * float(x.abs().max())
+    # the decoded frames are fixed points of the codec at the same origin / resolution
+    q3 = torch.round((xd.double() - torch.tensor(origin).double()) / float(torch.tensor(res, dtype=torch.float32)))
+    assert torch.equal(q3.to(torch.int16), q)
