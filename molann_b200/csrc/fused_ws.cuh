@@ -134,6 +134,29 @@ __device__ __forceinline__ float ws_act(float zs) {
   return zs;
 }
 
+// the same activation on two pre-scaled pre-activations: the adds and the final 1 - 2 r as packed f32x2 operations
+template <int ACT>
+__device__ __forceinline__ void ws_act_x2(float z0, float z1, float& h0, float& h1) {
+  if (ACT == ACT_TANH || ACT == ACT_SIGMOID) {
+    float e0, e1, r0, r1;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(z0));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(z1));
+    float s0, s1;
+    f2_unpack(f2_add(f2_pack(e0, e1), f2_pack(1.0f, 1.0f)), s0, s1);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(s0));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(s1));
+    if (ACT == ACT_TANH) {
+      f2_unpack(f2_fma(f2_pack(-2.0f, -2.0f), f2_pack(r0, r1), f2_pack(1.0f, 1.0f)), h0, h1);
+    } else {
+      h0 = r0;
+      h1 = r1;
+    }
+  } else {
+    h0 = ws_act<ACT>(z0);
+    h1 = ws_act<ACT>(z1);
+  }
+}
+
 // weights of MMA layer k, multiplied by `scale`, split into chunk-major hi/lo operands
 __device__ __forceinline__ void ws_stage_weights(const float* __restrict__ Wg, const float* __restrict__ bg, int K, int N,
                                                  int kp, int np, float scale, unsigned char* bhi, unsigned char* blo,
@@ -241,7 +264,11 @@ __device__ __forceinline__ void ws_hidden_epilogue(uint32_t lane_d, uint32_t lan
     }
     uint32_t hi[16], lo[16];
 #pragma unroll
-    for (int c = 0; c < 16; ++c) split_tf32_rn(ws_act<ACT>(z[c]), hi[c], lo[c]);     // bias is already in z
+    for (int c = 0; c < 16; c += 2) {                                                 // bias is already in z
+      float h0, h1;
+      ws_act_x2<ACT>(z[c], z[c + 1], h0, h1);
+      split_tf32_rn_x2(h0, h1, hi[c], hi[c + 1], lo[c], lo[c + 1]);
+    }
     if (c0 == 0) {                             // the MMA that last read this A2 buffer is complete
       mbar_wait_hint(bar_a_empty, par_a_empty);
       tc_fence_after_sync();
@@ -281,19 +308,24 @@ __device__ __forceinline__ void ws_final_epilogue(uint32_t lane_d, const float* 
       mbar_arrive(bar_d_free);
     }
 #pragma unroll
-    for (int c = 0; c < 16; ++c) z[c] = ws_act<ACT>(z[c]);                            // bias is already in z
+    for (int c = 0; c < 16; c += 2) ws_act_x2<ACT>(z[c], z[c + 1], z[c], z[c + 1]);    // bias is already in z
     if (kout == 2) {                            // the common case: two collective variables
+      // packed FMAs: lane x of a pair accumulates the even columns, lane y the odd ones (same order as before)
       const float4* w0 = reinterpret_cast<const float4*>(wl + c0);
       const float4* w1 = reinterpret_cast<const float4*>(wl + TC_MAXW + c0);
-      float a0 = 0.f, a1 = 0.f, d0 = 0.f, d1 = 0.f;
+      unsigned long long p0 = f2_pack(0.f, 0.f), p1 = f2_pack(0.f, 0.f);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float4 u = w0[j], v = w1[j];
-        a0 = fmaf(z[4 * j], u.x, a0); d0 = fmaf(z[4 * j + 1], u.y, d0);
-        a0 = fmaf(z[4 * j + 2], u.z, a0); d0 = fmaf(z[4 * j + 3], u.w, d0);
-        a1 = fmaf(z[4 * j], v.x, a1); d1 = fmaf(z[4 * j + 1], v.y, d1);
-        a1 = fmaf(z[4 * j + 2], v.z, a1); d1 = fmaf(z[4 * j + 3], v.w, d1);
+        const unsigned long long za = f2_pack(z[4 * j], z[4 * j + 1]), zb = f2_pack(z[4 * j + 2], z[4 * j + 3]);
+        p0 = f2_fma(za, f2_pack(u.x, u.y), p0);
+        p0 = f2_fma(zb, f2_pack(u.z, u.w), p0);
+        p1 = f2_fma(za, f2_pack(v.x, v.y), p1);
+        p1 = f2_fma(zb, f2_pack(v.z, v.w), p1);
       }
+      float a0, d0, a1, d1;
+      f2_unpack(p0, a0, d0);
+      f2_unpack(p1, a1, d1);
       acc[0] += a0 + d0;
       acc[1] += a1 + d1;
     } else {

@@ -121,10 +121,53 @@ __device__ __forceinline__ void mma_commit(void* mbar) {
                : "memory");
 }
 
+// ---- packed fp32 (Blackwell f32x2 pipe: one issue slot, two results; SASS FFMA2 / FADD2 / FMUL2) --------------------
+// The fused small-system kernels are bound by CUDA-core instruction issue (profiles/r1_h), so every pair of
+// independent fp32 operations that can share an instruction is an issue slot saved.
+__device__ __forceinline__ unsigned long long f2_pack(float a, float b) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(unsigned long long v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long f2_fma(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ unsigned long long f2_add(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long f2_sub(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long f2_mul(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
 // ---- 3xTF32 split ---------------------------------------------------------------------------------
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
   hi = __float_as_uint(x) & 0xffffe000u;
   lo = __float_as_uint(x - __uint_as_float(hi));
+}
+
+// two values at once: hi = round-to-nearest TF32 (integer ops), lo = x - hi as ONE packed subtraction
+__device__ __forceinline__ void split_tf32_rn_x2(float x0, float x1, uint32_t& hi0, uint32_t& hi1, uint32_t& lo0,
+                                                 uint32_t& lo1) {
+  hi0 = (__float_as_uint(x0) + 0x1000u) & 0xffffe000u;
+  hi1 = (__float_as_uint(x1) + 0x1000u) & 0xffffe000u;
+  float l0, l1;
+  f2_unpack(f2_sub(f2_pack(x0, x1), f2_pack(__uint_as_float(hi0), __uint_as_float(hi1))), l0, l1);
+  lo0 = __float_as_uint(l0);
+  lo1 = __float_as_uint(l1);
 }
 
 // byte offset of element (row n, column k) inside a chunk-major K-major operand with `rows` rows
