@@ -145,7 +145,9 @@ int molann_b200_align_backward(const MolannPlan* plan, const float* x, const flo
  *   molann_b200_prepare          builds it.  Copies the feature program to the host once (synchronises `stream`; do
  *                                not call while capturing a CUDA graph).  MOLANN_ERR_UNSUPPORTED if not eligible.
  *   molann_b200_prepared_refresh re-packs the weights after the caller changed them (asynchronous, two small kernels)
- *   molann_b200_prepared_workspace_bytes / molann_b200_forward_prepared   scratch size and the forward itself
+ *   molann_b200_prepared_workspace_bytes / molann_b200_forward_prepared   scratch size and the forward itself (the
+ *                                fused wide kernel; the layered kernels on the packed operands when a frame does not
+ *                                fit its shared-memory ring)
  *   molann_b200_prepared_destroy frees the host object (the device buffer stays the caller's)
  * The plan passed to the later calls must be the one prepared (same sizes; pointers may have moved only for W / b,
  * followed by a refresh). */
@@ -159,6 +161,10 @@ int molann_b200_prepared_refresh(MolannPrepared* prepared, const MolannPlan* pla
 size_t molann_b200_prepared_workspace_bytes(const MolannPrepared* prepared, int64_t L);
 int molann_b200_forward_prepared(const MolannPrepared* prepared, const MolannPlan* plan, const float* x, int64_t L,
                                  float* y, void* workspace, size_t workspace_bytes, void* stream);
+/* y and gx = d<gy, y>/dx on a prepared plan: the layered tensor-core kernels on operands packed once (no pack launches) */
+int molann_b200_value_and_grad_prepared(const MolannPrepared* prepared, const MolannPlan* plan, const float* x,
+                                        const float* gy, int64_t L, float* y, float* gx, void* workspace,
+                                        size_t workspace_bytes, void* stream);
 void molann_b200_prepared_destroy(MolannPrepared* prepared);
 
 /* Tuning / introspection: which kernel family the dispatcher picks for this plan.

@@ -78,6 +78,7 @@ def cabi():
     lib.molann_b200_prepared_workspace_bytes.restype = sz
     lib.molann_b200_prepared_workspace_bytes.argtypes = [vp, i64]
     lib.molann_b200_forward_prepared.argtypes = [vp, P, vp, i64, vp, vp, sz, vp]
+    lib.molann_b200_value_and_grad_prepared.argtypes = [vp, P, vp, vp, i64, vp, vp, vp, sz, vp]
     lib.molann_b200_prepared_destroy.restype = None
     lib.molann_b200_prepared_destroy.argtypes = [vp]
     _cabi = lib

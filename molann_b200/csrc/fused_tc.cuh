@@ -86,6 +86,40 @@ __device__ __forceinline__ void act_value_and_grad_t(float v, float& h, float& d
   }
 }
 
+// the same for two pre-activations (v0 + b0, v1 + b1) with the fp32 arithmetic as packed f32x2 operations
+// (SASS FFMA2 / FADD2 / FMUL2: one issue slot for two results -- this kernel is issue and latency bound)
+template <int ACT>
+__device__ __forceinline__ void act_value_and_grad_x2(float v0, float v1, float b0, float b1, float& h0, float& h1,
+                                                      float& d0, float& d1) {
+  constexpr int act = ACT;
+  if (act == ACT_TANH || act == ACT_SIGMOID) {
+    const float sc = act == ACT_TANH ? 2.8853900817779268f : -1.4426950408889634f;
+    float s0, s1;
+    f2_unpack(f2_mul(f2_add(f2_pack(v0, v1), f2_pack(b0, b1)), f2_pack(sc, sc)), s0, s1);
+    float e0, e1, r0, r1;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fminf(s0, 126.0f)));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fminf(s1, 126.0f)));
+    const unsigned long long e = f2_pack(e0, e1);
+    float p0, p1;
+    f2_unpack(f2_add(e, f2_pack(1.0f, 1.0f)), p0, p1);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(p0));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(p1));
+    const unsigned long long r = f2_pack(r0, r1);
+    const unsigned long long err = f2_mul(f2_mul(e, r), r);                    // e r^2
+    if (act == ACT_TANH) {
+      f2_unpack(f2_fma(f2_pack(-2.0f, -2.0f), r, f2_pack(1.0f, 1.0f)), h0, h1);
+      f2_unpack(f2_mul(err, f2_pack(4.0f, 4.0f)), d0, d1);
+    } else {
+      h0 = r0;
+      h1 = r1;
+      f2_unpack(err, d0, d1);
+    }
+  } else {
+    act_value_and_grad_t<ACT>(v0 + b0, h0, d0);
+    act_value_and_grad_t<ACT>(v1 + b1, h1, d1);
+  }
+}
+
 // round-to-nearest TF32 split: |x - hi - lo| <= 2^-22 |x| once the MMA truncates lo to TF32
 __device__ __forceinline__ void split_tf32_rn(float x, uint32_t& hi, uint32_t& lo) {
   hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
@@ -689,11 +723,12 @@ fused_tc_value_grad_kernel(const __grid_constant__ DevPlan p, const __grid_const
           const float4 b = b4[q];
           const float bb[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            float hh, dd;
-            act_value_and_grad_t<ACT>(z[4 * q + i] + bb[i], hh, dd);
-            dv[4 * q + i] = __float_as_uint(dd);
-            split_tf32_rn(hh, hi[4 * q + i], lo[4 * q + i]);
+          for (int i = 0; i < 4; i += 2) {
+            float hh0, hh1, dd0, dd1;
+            act_value_and_grad_x2<ACT>(z[4 * q + i], z[4 * q + i + 1], bb[i], bb[i + 1], hh0, hh1, dd0, dd1);
+            dv[4 * q + i] = __float_as_uint(dd0);
+            dv[4 * q + i + 1] = __float_as_uint(dd1);
+            split_tf32_rn_x2(hh0, hh1, hi[4 * q + i], hi[4 * q + i + 1], lo[4 * q + i], lo[4 * q + i + 1]);
           }
         }
         tmem_st16(lane_addr + COL_H1 + c, dv);
@@ -745,12 +780,20 @@ fused_tc_value_grad_kernel(const __grid_constant__ DevPlan p, const __grid_const
           const float4 b = b4[q];
           const float bb[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            float hh, dd;
-            act_value_and_grad_t<ACT>(z[4 * q + i] + bb[i], hh, dd);
-            z[4 * q + i] = hh;
-            if (JAC) hi[4 * q + i] = __float_as_uint(dd);                         // parked: every plane needs it
-            else split_tf32_rn(gh[4 * q + i] * dd, hi[4 * q + i], lo[4 * q + i]); // gz of the last hidden layer
+          for (int i = 0; i < 4; i += 2) {
+            const int c0i = 4 * q + i;
+            float hh0, hh1, dd0, dd1;
+            act_value_and_grad_x2<ACT>(z[c0i], z[c0i + 1], bb[i], bb[i + 1], hh0, hh1, dd0, dd1);
+            z[c0i] = hh0;
+            z[c0i + 1] = hh1;
+            if (JAC) {                                                            // parked: every plane needs it
+              hi[c0i] = __float_as_uint(dd0);
+              hi[c0i + 1] = __float_as_uint(dd1);
+            } else {                                                              // gz of the last hidden layer
+              float g0, g1;
+              f2_unpack(f2_mul(f2_pack(gh[c0i], gh[c0i + 1]), f2_pack(dd0, dd1)), g0, g1);
+              split_tf32_rn_x2(g0, g1, hi[c0i], hi[c0i + 1], lo[c0i], lo[c0i + 1]);
+            }
           }
         }
         if (JAC) {
@@ -818,7 +861,11 @@ fused_tc_value_grad_kernel(const __grid_constant__ DevPlan p, const __grid_const
           tmem_wait_ld();
           uint32_t hi[16], lo[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) split_tf32_rn(gh[i] * dk[i], hi[i], lo[i]);
+          for (int i = 0; i < 16; i += 2) {
+            float g0, g1;
+            f2_unpack(f2_mul(f2_pack(gh[i], gh[i + 1]), f2_pack(dk[i], dk[i + 1])), g0, g1);
+            split_tf32_rn_x2(g0, g1, hi[i], hi[i + 1], lo[i], lo[i + 1]);
+          }
           tmem_st16(lane_addr + COL_AHI + c, hi);
           tmem_st16(lane_addr + COL_ALO + c, lo);
         }

@@ -575,6 +575,11 @@ struct MolannPrepared {
   float* b2s;
   float* w3;
   float* b3;
+  // layered tensor-core GEMMs (gemm_tc.cuh: value-and-gradient of these plans, forward when the wide kernel does not
+  // fit): operands packed once -- forward orientation W_k and the backward-to-input orientation W_k^T; NULL where the
+  // layer is too narrow for that kernel
+  float* gt_fwd[MOLANN_MAX_LAYERS];
+  float* gt_bwd[MOLANN_MAX_LAYERS];
 };
 
 namespace {
@@ -618,7 +623,21 @@ size_t wide_prepared_bytes_for(const MolannPlan* p, int n_pos_max, int n_inv_ent
     b += align256((size_t)p->dims[nl] * n1p * 4);
   }
   b += align256((size_t)p->dims[nl] * 4);
+  for (int k = 0; k < nl; ++k) {
+    if (p->dims[k] >= 32 && p->dims[k + 1] >= 32) {
+      b += align256((size_t)gt_pack_floats(p->dims[k + 1], p->dims[k]) * 4);
+      b += align256((size_t)gt_pack_floats(p->dims[k], p->dims[k + 1]) * 4);
+    }
+  }
   return b;
+}
+
+int launch_gemm_pack(const float* W, long long rs, long long cs, int N, int K, float* out, cudaStream_t st) {
+  const long long total = (long long)((N + GT_NMAX - 1) / GT_NMAX) * GT_NMAX * round_up(K, GT_KC);
+  unsigned pb = (unsigned)((total + 255) / 256);
+  if (pb > 4096u) pb = 4096u;
+  gemm_tc_pack_kernel<<<pb, 256, 0, st>>>(W, rs, cs, N, K, out);
+  return post_launch();
 }
 
 int wide_pack_weights(const MolannPrepared* h, const MolannPlan* p, cudaStream_t st) {
@@ -637,6 +656,14 @@ int wide_pack_weights(const MolannPrepared* h, const MolannPlan* p, cudaStream_t
     if (blocks > 2048u) blocks = 2048u;
     fw_pack_kernel<<<blocks, 256, 0, st>>>(p->W[1], h->n1, h->n2, nullptr, h->n1p, h->n2p, scale, h->w2p);
     int s = post_launch();
+    if (s) return s;
+  }
+  for (int k = 0; k < p->n_layers; ++k) {
+    if (h->gt_fwd[k] == nullptr) continue;
+    const int K = p->dims[k], N = p->dims[k + 1];
+    int s = launch_gemm_pack(p->W[k], (long long)K, 1, N, K, h->gt_fwd[k], st);          // B[n][k] = W[n, k]
+    if (s) return s;
+    s = launch_gemm_pack(p->W[k], 1, (long long)K, K, N, h->gt_bwd[k], st);              // B[j][c] = W[c, j]
     if (s) return s;
   }
   const int last = p->n_layers - 1;
@@ -1062,13 +1089,14 @@ bool use_gemm_tc(long long M, int K, int N, const void* pack) {
 template <int EPI>
 int launch_gemm_tc(const float* A, long long M, int K, const float* W, long long rs, long long cs, int N, float* C,
                    const float* bias, const float* H, int act, int apply_act, float* pack, const DeviceInfo& dev,
-                   cudaStream_t st) {
-  const long long total = (long long)((N + GT_NMAX - 1) / GT_NMAX) * GT_NMAX * round_up(K, GT_KC);
-  unsigned pb = (unsigned)((total + 255) / 256);
-  if (pb > 4096u) pb = 4096u;
-  gemm_tc_pack_kernel<<<pb, 256, 0, st>>>(W, rs, cs, N, K, pack);
-  int s = post_launch();
-  if (s) return s;
+                   cudaStream_t st, const float* prepacked = nullptr) {
+  int s = MOLANN_OK;
+  if (prepacked == nullptr) {                  // no prepared plan: pack into the workspace right before the use
+    s = launch_gemm_pack(W, rs, cs, N, K, pack, st);
+    if (s) return s;
+  } else {
+    pack = const_cast<float*>(prepacked);
+  }
   auto kern = gemm_tc_kernel<EPI>;
   s = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM_BYTES));
   if (s) return s;
@@ -1084,10 +1112,10 @@ int launch_gemm_tc(const float* A, long long M, int K, const float* W, long long
 
 int launch_linear_forward(const float* in, const float* W, const float* b, float* out, long long M, int K, int N,
                           int act, int apply_act, cudaStream_t st, float* pack = nullptr,
-                          const DeviceInfo* dev = nullptr) {
+                          const DeviceInfo* dev = nullptr, const float* prepacked = nullptr) {
   if (dev != nullptr && use_gemm_tc(M, K, N, pack))
     return launch_gemm_tc<GT_EPI_BIAS_ACT>(in, M, K, W, (long long)K, 1, N, out, b, nullptr, act, apply_act, pack, *dev,
-                                           st);
+                                           st, prepacked);
   if (N <= NARROW_MAX && env_int("MOLANN_B200_NARROW", 1) != 0) {
     long long blocks = (M + 7) / 8;
     const long long cap = (long long)(dev ? dev->sm_count : 148) * 8;
@@ -1104,11 +1132,11 @@ int launch_linear_forward(const float* in, const float* W, const float* b, float
 // gprev[M, K] = (gz[M, N] W[N, K]) * act'(hprev[M, K])
 int launch_linear_backward_input(const float* gz, const float* W, const float* hprev, float* gprev, long long M,
                                  int K, int N, int act, cudaStream_t st, float* pack = nullptr,
-                                 const DeviceInfo* dev = nullptr) {
+                                 const DeviceInfo* dev = nullptr, const float* prepacked = nullptr) {
   // gprev[M x K] = gz[M x N] * W[N x K]: as C = A B^T with B[j][c] = W[c * K + j] (rows = inputs, contraction = outputs)
   if (dev != nullptr && use_gemm_tc(M, N, K, pack))
     return launch_gemm_tc<GT_EPI_DACT>(gz, M, N, W, 1, (long long)K, K, gprev, nullptr, hprev, act, hprev != nullptr, pack,
-                                       *dev, st);
+                                       *dev, st, prepacked);
   if (N <= NARROW_MAX && env_int("MOLANN_B200_NARROW", 1) != 0) {
     long long blocks = (M * ((K + 3) / 4) + 255) / 256;
     const long long cap = (long long)(dev ? dev->sm_count : 148) * 16;
@@ -1155,7 +1183,7 @@ int launch_linear_backward_params(const float* gz, const float* hin, float* gW, 
 }
 
 int general_forward(const MolannPlan* p, const float* x, long long L, float* y, void* ws, size_t ws_bytes,
-                    const DeviceInfo& dev, cudaStream_t st) {
+                    const DeviceInfo& dev, cudaStream_t st, const MolannPrepared* prep = nullptr) {
   if (!ws || ws_bytes < general_ws_bytes(p, L, false)) return MOLANN_ERR_WORKSPACE;
   const DevPlan dp = to_dev(p);
   const long long ch = chunk_frames(p, L);
@@ -1178,7 +1206,7 @@ int general_forward(const MolannPlan* p, const float* x, long long L, float* y, 
       const bool last = (k == p->n_layers - 1);
       float* out = last ? (y + c0 * kout) : pp[k & 1];
       s = launch_linear_forward(in, p->W[k], p->b[k], out, Lc, p->dims[k], p->dims[k + 1], p->act_id, !last, st, pack,
-                                &dev);
+                                &dev, prep ? prep->gt_fwd[k] : nullptr);
       if (s) return s;
       in = out;
     }
@@ -1190,7 +1218,7 @@ int general_forward(const MolannPlan* p, const float* x, long long L, float* y, 
 // forward the caller wanted -- running molann_b200_forward first cost a second pass over x and both wide GEMMs).
 int general_backward(const MolannPlan* p, const float* x, const float* gy, long long L, float* gx, float* const* gW,
                      float* const* gb, void* ws, size_t ws_bytes, const DeviceInfo& dev, cudaStream_t st,
-                     float* y_out = nullptr) {
+                     float* y_out = nullptr, const MolannPrepared* prep = nullptr) {
   if (!ws || ws_bytes < general_ws_bytes(p, L, true)) return MOLANN_ERR_WORKSPACE;
   const DevPlan dp = to_dev(p);
   const long long ch = chunk_frames(p, L);
@@ -1217,12 +1245,12 @@ int general_backward(const MolannPlan* p, const float* x, const float* gy, long 
     if (s) return s;
     for (int k = 0; k < nl - 1; ++k) {
       s = launch_linear_forward(h[k], p->W[k], p->b[k], h[k + 1], Lc, p->dims[k], p->dims[k + 1], p->act_id, 1, st,
-                                pack, &dev);
+                                pack, &dev, prep ? prep->gt_fwd[k] : nullptr);
       if (s) return s;
     }
     if (y_out != nullptr) {
       s = launch_linear_forward(h[nl - 1], p->W[nl - 1], p->b[nl - 1], y_out + c0 * kout, Lc, p->dims[nl - 1], kout,
-                                p->act_id, 0, st, pack, &dev);
+                                p->act_id, 0, st, pack, &dev, prep ? prep->gt_fwd[nl - 1] : nullptr);
       if (s) return s;
     }
     const float* gz = gy + c0 * kout;
@@ -1235,7 +1263,7 @@ int general_backward(const MolannPlan* p, const float* x, const float* gy, long 
       if (k == 0 && gx == nullptr) break;       // training: nobody asked for the coordinate gradient
       float* gprev = pp[k & 1];
       s = launch_linear_backward_input(gz, p->W[k], k > 0 ? h[k] : nullptr, gprev, Lc, p->dims[k], p->dims[k + 1],
-                                       p->act_id, st, pack, &dev);
+                                       p->act_id, st, pack, &dev, prep ? prep->gt_bwd[k] : nullptr);
       if (s) return s;
       gz = gprev;
     }
@@ -1474,6 +1502,12 @@ int molann_b200_prepare(const MolannPlan* plan, void* device_buffer, size_t byte
   }
   h->w3 = reinterpret_cast<float*>(take((size_t)h->kout * h->nlastp * 4));
   h->b3 = reinterpret_cast<float*>(take((size_t)h->kout * 4));
+  for (int k = 0; k < plan->n_layers; ++k) {
+    if (plan->dims[k] >= 32 && plan->dims[k + 1] >= 32) {
+      h->gt_fwd[k] = reinterpret_cast<float*>(take((size_t)gt_pack_floats(plan->dims[k + 1], plan->dims[k]) * 4));
+      h->gt_bwd[k] = reinterpret_cast<float*>(take((size_t)gt_pack_floats(plan->dims[k], plan->dims[k + 1]) * 4));
+    }
+  }
   if ((size_t)(base - static_cast<char*>(device_buffer)) > bytes) { delete h; return MOLANN_ERR_WORKSPACE; }
   cudaError_t ce = cudaSuccess;
   if (h->n_pos) ce = cudaMemcpyAsync(h->pos_atom, pos_atom.data(), pos_atom.size() * 4, cudaMemcpyHostToDevice, st);
@@ -1504,7 +1538,15 @@ size_t molann_b200_prepared_workspace_bytes(const MolannPrepared* prepared, int6
   const long long ntiles = (L + FW_M - 1) / FW_M;
   const long long grid = dev.sm_count < ntiles ? dev.sm_count : ntiles;
   const long long slot_floats = (long long)FW_SUB * (FW_HDR_FLOATS + prepared->nkc1 * FW_KC);
-  return (size_t)grid * FW_MAX_SLOTS * slot_floats * 4;
+  const size_t wide = (size_t)grid * FW_MAX_SLOTS * slot_floats * 4;
+  // the layered kernels (value-and-gradient; forward when the wide kernel does not fit) share the same workspace
+  MolannPlan shape;
+  std::memset(&shape, 0, sizeof(shape));
+  shape.d_feat = prepared->d_feat;
+  shape.n_layers = prepared->n_layers;
+  for (int k = 0; k <= prepared->n_layers; ++k) shape.dims[k] = prepared->dims[k];
+  const size_t layered = general_ws_bytes(&shape, L, true);
+  return wide > layered ? wide : layered;
 }
 
 int molann_b200_forward_prepared(const MolannPrepared* prepared, const MolannPlan* plan, const float* x, int64_t L,
@@ -1519,7 +1561,8 @@ int molann_b200_forward_prepared(const MolannPrepared* prepared, const MolannPla
   const DeviceInfo dev = device_info();
   if (!dev.ok) return MOLANN_ERR_CUDA;
   WideChoice ch = choose_wide(prepared, plan, (long long)L, dev);
-  if (!ch.ok) return MOLANN_ERR_UNSUPPORTED;
+  if (!ch.ok || env_int("MOLANN_B200_WIDE", -1) == 0)      // e.g. 60 KB frames: layered kernels on the packed operands
+    return general_forward(plan, x, L, y, workspace, workspace_bytes, dev, static_cast<cudaStream_t>(stream), prepared);
   const size_t need = (size_t)ch.grid * (size_t)ch.P.cta_floats * 4;
   if (!workspace || workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 15u)) return MOLANN_ERR_WORKSPACE;
   ch.P.scratch = static_cast<float*>(workspace);
@@ -1530,6 +1573,23 @@ int molann_b200_forward_prepared(const MolannPrepared* prepared, const MolannPla
     case MOLANN_ACT_SIGMOID: return launch_wide_act<ACT_SIGMOID>(ch, x, y, (long long)L, st);
     default: return launch_wide_act<ACT_IDENTITY>(ch, x, y, (long long)L, st);
   }
+}
+
+int molann_b200_value_and_grad_prepared(const MolannPrepared* prepared, const MolannPlan* plan, const float* x,
+                                        const float* gy, int64_t L, float* y, float* gx, void* workspace,
+                                        size_t workspace_bytes, void* stream) {
+  int s = validate_full(plan);
+  if (s) return s;
+  if (!prepared_matches(prepared, plan)) return MOLANN_ERR_PLAN;
+  if (L < 0) return MOLANN_ERR_PLAN;
+  if (L == 0) return MOLANN_OK;
+  if (!x || !gy || !y || !gx) return MOLANN_ERR_NULL;
+  if (misaligned4(x) || misaligned4(gy) || misaligned4(y) || misaligned4(gx)) return MOLANN_ERR_ALIGNMENT;
+  const DeviceInfo dev = device_info();
+  if (!dev.ok) return MOLANN_ERR_CUDA;
+  // ONE pass of the layered kernels (the backward's forward recompute also writes y) on operands packed once
+  return general_backward(plan, x, gy, L, gx, nullptr, nullptr, workspace, workspace_bytes, dev,
+                          static_cast<cudaStream_t>(stream), y, prepared);
 }
 
 void molann_b200_prepared_destroy(MolannPrepared* prepared) {

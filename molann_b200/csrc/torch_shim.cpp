@@ -374,6 +374,16 @@ std::tuple<Tensor, Tensor> value_and_grad_impl(const Tensor& x, const Tensor& gy
   Tensor ws;
   void* wsp = nullptr;
   size_t ws_bytes = 0;
+  if (L > 0 && molann_b200_wide_eligible(&h.plan)) {           // big system: packed operands from the prepared plan
+    auto prep = prepared_for(h, x, entries, align_idx, ref_x, params, act, use_angle_value);
+    ws_bytes = molann_b200_prepared_workspace_bytes(prep->handle, L);
+    ws = at::empty({static_cast<int64_t>(ws_bytes)}, x.options().dtype(at::kByte));
+    check_status(molann_b200_value_and_grad_prepared(prep->handle, &h.plan, x.data_ptr<float>(), gy.data_ptr<float>(),
+                                                     L, y.data_ptr<float>(), gx.data_ptr<float>(), ws.data_ptr(),
+                                                     ws_bytes, cur_stream()),
+                 "value_and_grad_prepared");
+    return std::make_tuple(y, gx);
+  }
   if (molann_b200_kernel_family(&h.plan, 1) != 2) {
     ws_bytes = molann_b200_workspace_bytes(&h.plan, L, 1);
     ws = at::empty({static_cast<int64_t>(ws_bytes)}, x.options().dtype(at::kByte));

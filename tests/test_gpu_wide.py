@@ -168,8 +168,9 @@ def test_wide_weight_update_repacks(monkeypatch):
 @pytest.mark.parametrize("name,L", [("C3", 203), ("C5", 131)])
 def test_wide_full_width_default_path(name, L):
     """BASELINE configs[2] / [4] shapes.  C3: the fused wide kernel IS the default forward, one launch per call.  C5:
-    two 60 KB frames + the operand ring + the staging rows do not fit in 227 KB of shared memory yet, the torch shim
-    then falls back to the layered kernels (6 launches) -- either way the result must match the oracle."""
+    two 60 KB frames + the operand ring + the staging rows do not fit in 227 KB of shared memory yet,
+    `molann_b200_forward_prepared` then runs the layered kernels on the packed operands (4 launches) -- either way the
+    result must match the oracle."""
     from molann_b200 import _lib
     spec = S.get_spec(name)
     model, _ = S.build_model(spec)
@@ -182,11 +183,14 @@ def test_wide_full_width_default_path(name, L):
         before = _lib.launch_count()
         y2 = model(dev(x))
     n_launch = _lib.launch_count() - before
-    assert n_launch == 1 if name == "C3" else n_launch in (1, 6)
+    assert n_launch == 1 if name == "C3" else n_launch in (1, 4)        # layered on packed operands: no pack launches
     assert torch.equal(y, y2)
     assert_parity(y.cpu(), y64, y32, TOL, name + " y (fused wide kernel)")
-    # the layered path (kept for the backward) must agree to rounding
+    # the layered path (kept for the backward) must agree to rounding, and runs on the operands packed once:
+    # preprocess + 2 GEMMs + narrow (y) forward, narrow + 2 GEMMs + preprocess backward = 8 launches, no packing
+    before = _lib.launch_count()
     yl, _ = model.value_and_grad(dev(x), torch.ones(L, 2, device="cuda"))
+    assert _lib.launch_count() - before == 8
     assert float((yl - y).abs().max()) < 2e-5 * max(1.0, float(y.abs().max()))
 
 
