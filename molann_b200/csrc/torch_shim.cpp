@@ -515,19 +515,23 @@ Tensor molann_autograd(const Tensor& x, const Tensor& align_idx, const Tensor& r
 std::tuple<Tensor, Tensor> value_and_grad_autograd(const Tensor& x, const Tensor& gy, const Tensor& align_idx,
                                                    const Tensor& ref_x, const Tensor& entries, int64_t d_feat,
                                                    bool use_angle_value, at::TensorList params, int64_t act) {
-  at::AutoDispatchBelowADInplaceOrView g;
+  // (detach BEFORE the guard: below ADInplaceOrView a detach makes a fresh version counter, and the prepared-plan cache
+  // keys on the parameters' versions)
   std::vector<Tensor> plain;
   for (const Tensor& p : params) plain.push_back(p.detach());
-  return value_and_grad_impl(x.detach(), gy.detach(), align_idx, ref_x, entries, d_feat, use_angle_value, plain, act);
+  const Tensor xd = x.detach(), gyd = gy.detach();
+  at::AutoDispatchBelowADInplaceOrView g;
+  return value_and_grad_impl(xd, gyd, align_idx, ref_x, entries, d_feat, use_angle_value, plain, act);
 }
 
 std::tuple<Tensor, Tensor> value_and_jacobian_autograd(const Tensor& x, const Tensor& align_idx, const Tensor& ref_x,
                                                        const Tensor& entries, int64_t d_feat, bool use_angle_value,
                                                        at::TensorList params, int64_t act) {
-  at::AutoDispatchBelowADInplaceOrView g;
   std::vector<Tensor> plain;
   for (const Tensor& p : params) plain.push_back(p.detach());
-  return value_and_jacobian_impl(x.detach(), align_idx, ref_x, entries, d_feat, use_angle_value, plain, act);
+  const Tensor xd = x.detach();
+  at::AutoDispatchBelowADInplaceOrView g;
+  return value_and_jacobian_impl(xd, align_idx, ref_x, entries, d_feat, use_angle_value, plain, act);
 }
 
 // int16 wire frames -> fp32 coordinates (trajectory ingestion, include/molann_b200.h)
