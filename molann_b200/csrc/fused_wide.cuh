@@ -53,6 +53,17 @@
 #include "staged_block.cuh"
 #include "tc.cuh"
 
+// A/B switches of tests/cuda/fw_trace.cu (defaults = the shipped configuration)
+#ifndef FW_OPT_POLICY
+#define FW_OPT_POLICY 1      // evict-last scratch stores + discard of the rows the converter has read
+#endif
+#ifndef FW_OPT_XPROD2
+#define FW_OPT_XPROD2 1      // two X producer warps, four copies per loop trip (0: one warp, rolled loop)
+#endif
+#ifndef FW_OPT_LATE
+#define FW_OPT_LATE 1        // release the frame's ring slot before the dihedral arithmetic
+#endif
+
 namespace molann {
 
 constexpr int FW_M = 128;                 // frames per tile (tcgen05 M)
@@ -64,20 +75,26 @@ constexpr int FW_NMAX = 256;              // widest tensor-core layer
 constexpr int FW_CW = 64;                 // accumulator columns per epilogue thread
 constexpr int FW_WARPS = 32;
 constexpr int FW_THREADS = FW_WARPS * 32;
-constexpr int FW_W_EPI = 4, FW_W_WPROD = 20, FW_W_MMA = 21, FW_W_XPROD = 22, FW_W_GEO = 24;
-constexpr int FW_NGW = 4;                 // geometry warps per group (one group works on one frame)
-constexpr int FW_NGG = 2;                 // geometry groups (alternate frames)
+constexpr int FW_W_EPI = 4, FW_W_WPROD = 20, FW_W_MMA = 21, FW_W_XPROD = 22, FW_W_GEO = 24;   // X producer: warps 22, 23
+constexpr int FW_GEO_WARPS = 8;           // geometry warps: FW_NGG groups (alternate frames) of FW_NGW warps (one frame)
+constexpr int FW_NGG = 2, FW_NGW = FW_GEO_WARPS / FW_NGG;
+constexpr int FW_CONV_CHUNK = FW_M * FW_KC * 4;   // converter staging: one raw K-chunk of the tile, [unit][row][16 B]
+constexpr int FW_MAX_CDEPTH = 4;
 // setmaxnreg budgets; pool = 1024 threads x 64 registers = 65536 = 32 x (4 x 56 + 16 x 80 + 4 x 24 + 8 x 56).  The
 // geometry role bounds the kernel (tests/cuda/fw_trace.cu), so it gets two groups of spill-free warps; the MMA chain
 // has slack and pays for it with a few spill reloads per chunk.
 constexpr int FW_REGS_CONV = 56, FW_REGS_EPI = 80, FW_REGS_CTRL = 24, FW_REGS_GEO = 56;
-static_assert(4 * FW_REGS_CONV + 16 * FW_REGS_EPI + 4 * FW_REGS_CTRL + 4 * FW_REGS_GEO <= 28 * 72, "register pool");
+static_assert(4 * FW_REGS_CONV + 16 * FW_REGS_EPI + 4 * FW_REGS_CTRL + 8 * FW_REGS_GEO <= 32 * 64, "register pool");
 constexpr uint32_t FW_PIECE = 2048;      // bytes per bulk copy of the frame ring
-constexpr int FW_REGS_LAUNCH = 72;        // 65536 / 896 rounded down to a multiple of 8: what the CTA starts with
+constexpr int FW_REGS_LAUNCH = 64;        // 65536 / 1024 threads: what the CTA starts with
 constexpr int FW_A_HALF = FW_M * FW_KC * 4;                               // one of hi / lo: 8 KB
 constexpr int FW_STAGE_BYTES = 2 * FW_A_HALF + 2 * FW_NMAX * FW_KC * 4;   // 16 KB A + 32 KB W
 constexpr int FW_MAX_STAGES = 4, FW_MAX_RING = 8, FW_MAX_SLOTS = 8;
-constexpr int FW_HDR_FLOATS = 16;                                         // per scratch row: H[9], sum d[3], pad
+// per scratch row: one 12-float moment partial (H[9], sum d[3]) per geometry warp of the frame's group; the converter
+// adds them in a fixed order
+constexpr int FW_HDR_FLOATS = 12 * FW_NGW;
+// a row = header + nkc1 K-chunks, rounded up to whole 128-byte L2 lines (no line is shared by two rows)
+__host__ __device__ inline int fw_row_floats(int nkc1) { return (FW_HDR_FLOATS + nkc1 * FW_KC + 31) & ~31; }
 
 // Development aid (tests/cuda/fw_trace.cu): clock64() stamps of CTA 0, one lane per role.  Compiled out of the product.
 #ifdef MOLANN_WS_TRACE
@@ -86,10 +103,29 @@ __device__ long long g_fw_trace[4 * 256 * 8];       // [role][item][event]
   do {                                                                                           \
     if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (i) < 256) g_fw_trace[((role) * 256 + (i)) * 8 + (ev)] = clock64(); \
   } while (0)
+// per-tile steady-state record: [role][tile][0] = time stamp, [1..] = cumulative wait cycles of that role
+__device__ long long g_fw_tiles[4 * 32 * 8];
+#define FW_TILE(role, it, ev, val)                                                               \
+  do {                                                                                           \
+    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (it) < 32) g_fw_tiles[((role) * 32 + (it)) * 8 + (ev)] = (val); \
+  } while (0)
+#define FW_WAIT_BEGIN() const long long fw_t0_ = clock64()
+#define FW_WAIT_END(acc) (acc) += clock64() - fw_t0_
+#define FW_TRACE_ONLY(x) x
 #else
 #define FW_EVT(role, i, ev) \
   do {                      \
   } while (0)
+#define FW_TILE(role, it, ev, val) \
+  do {                             \
+  } while (0)
+#define FW_WAIT_BEGIN() \
+  do {                  \
+  } while (0)
+#define FW_WAIT_END(acc) \
+  do {                   \
+  } while (0)
+#define FW_TRACE_ONLY(x)
 #endif
 
 struct FwBars {
@@ -122,13 +158,15 @@ struct FwParams {
   const float* b2s;          // [n2p]
   const float* w3;           // [kout][nlastp]
   const float* b3;           // [kout]
+  const float* x_base;       // = x (the geometry role only needs its low address bits: where a frame sits in its ring slot)
   // transposition scratch (global memory, L2 resident): per CTA n_slots sub-tiles of slot_floats
   float* scratch;
   long long cta_floats;
   int slot_floats, n_slots, row_floats;
   // shared memory
   int n_stages, n_ring, ring_slot_bytes;
-  int off_stage, off_ring, off_b1, off_b2, off_w3, off_ypart, off_rowbuf;   // rowbuf: FW_NGW staging rows
+  int conv_depth;            // raw K-chunks the converter keeps in flight (cp.async staging ring)
+  int off_stage, off_ring, off_b1, off_b2, off_w3, off_ypart, off_cstage;
   int off_pos, off_aidx, off_ref, off_ent;      // plan tables staged in smem (-1: read from global memory)
   int total_smem;
 };
@@ -137,12 +175,30 @@ struct FwParams {
 template <int ACT>
 __device__ __forceinline__ float fw_act(float zs) { return ws_act<ACT>(zs); }
 
-// writer of an invariant feature column into this frame's scratch row
+// Scratch stores carry an evict-last L2 policy: a row must stay in L2 until the converter has read it (48 % of the
+// plain stores missed L2 and 88 % of the scratch was written back to DRAM while the evict-first frame stream passed
+// through: profiles/r3g).  The converter discards the lines when it is done with them.
+__device__ __forceinline__ void fw_st1(float* p, float v, unsigned long long pol) {
+#if FW_OPT_POLICY
+  asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
+#else
+  __stcg(p, v);
+#endif
+}
+__device__ __forceinline__ void fw_st2(float* p, float a, float b, unsigned long long pol) {
+#if FW_OPT_POLICY
+  asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(p), "f"(a), "f"(b), "l"(pol) : "memory");
+#else
+  __stcg(reinterpret_cast<float2*>(p), make_float2(a, b));
+#endif
+}
+// writer of an invariant feature column into this frame's scratch row (global memory, L2)
 struct FwInvOut {
-  float* units;              // unit area of the frame's staging row
+  float* units;              // unit area of the frame's scratch row
   int n_pos;
+  unsigned long long pol;
   __device__ __forceinline__ void operator()(int v, float val) {
-    units[v < n_pos ? 4 * v + 3 : 3 * n_pos + v] = val;             // unit * 4 + component
+    fw_st1(units + (v < n_pos ? 4 * v + 3 : 3 * n_pos + v), val, pol);   // unit * 4 + component
   }
 };
 
@@ -219,22 +275,203 @@ __device__ __forceinline__ float fw_rsqrt(float a) {
 }
 // dihedral as [cos, sin] (reference ann.py:338-351): C = n1.n2, S = (n1.r34) |r23|, out = (C, S) / sqrt(C^2 + S^2)
 template <class Out>
-__device__ __forceinline__ void fw_dihedral_cos_sin(const Entry& e, const float* __restrict__ xf, Out& out) {
-  const V3 x0 = ld3(xf, e.a0), x1 = ld3(xf, e.a1), x2 = ld3(xf, e.a2), x3 = ld3(xf, e.a3);
+__device__ __forceinline__ void fw_dihedral_cos_sin(V3 x0, V3 x1, V3 x2, V3 x3, int off, Out& out) {
   const V3 r12 = sub(x1, x0), r23 = sub(x2, x1), r34 = sub(x3, x2);
   const V3 n1 = cross(r12, r23), n2 = cross(r23, r34);
   const float d23 = dot(r23, r23);
   const float C = dot(n1, n2);
   const float S = dot(n1, r34) * (d23 * fw_rsqrt(d23));
   const float ir = fw_rsqrt(fmaf(C, C, S * S));
-  out(e.off, C * ir);
-  out(e.off + 1, S * ir);
+  out(off, C * ir);
+  out(off + 1, S * ir);
 }
 
 // A frame is copied from the 16-byte boundary below it, rounded up to 16 bytes: up to 15 bytes past its end.  That is
 // inside x for every frame but the last one of the batch, which is staged only if it ends on the grid.
 __device__ __forceinline__ bool fw_frame_is_staged(long long f, long long L, uint32_t off, uint32_t fbytes) {
   return f + 1 < L || ((off + fbytes) & 15u) == 0u;
+}
+
+// plan tables: shared memory when they fit (TS), else global memory
+template <bool TS>
+__device__ __forceinline__ int fw_tab_i(const unsigned char* smem, int off, const int* g, int i) {
+  return TS ? reinterpret_cast<const int*>(smem + off)[i] : __ldg(g + i);
+}
+template <bool TS>
+__device__ __forceinline__ float fw_tab_f(const unsigned char* smem, int off, const float* g, int i) {
+  return TS ? reinterpret_cast<const float*>(smem + off)[i] : __ldg(g + i);
+}
+
+// ================= geometry role: moments, raw position atoms, invariant features -> scratch =================
+// The FW_NGW warps of a group work on ONE frame at a time (thread = alignment atom / position atom / invariant entry),
+// so the frames behind it in the ring are pure prefetch and a frame's latency is that of one entry, not of
+// n_entries / 32 iterations of a single warp.  Alternate frames go to alternate groups.
+// The warps never meet: each writes its results STRAIGHT into the frame's scratch row (small L2 stores, no staging
+// row, no copy-out pass) and its own 12-float moment partial into the row header -- the converter adds the
+// partials.  The per-frame group barrier, the header pass and the staging copy were 40 % of a frame's latency
+// (tests/cuda/fw_trace.cu), and a frame's latency is what bounds this role.  Every frame is staged, so all
+// coordinate loads are shared-memory loads with 32-bit addresses (the role lives on 56 registers).
+template <bool TS>
+__device__ __forceinline__ void fw_geometry_role(const FwParams& P, FwBars* bars, unsigned char* smem, long long L,
+                                                 int ntile_cta, int gwarp, int lane) {
+  const int grp = gwarp / FW_NGW;
+  const int gw = gwarp % FW_NGW;
+  const int gt = gw * 32 + lane;                    // thread within the group
+  constexpr int gstride = FW_NGW * 32;
+  const bool aligned = P.n_align > 0;
+  const unsigned nfr = (unsigned)ntile_cta * FW_M;
+  float* const cta_scratch = P.scratch + (long long)blockIdx.x * P.cta_floats;
+  unsigned long long pol_keep;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+  int slot = 0, rs = grp % P.n_ring, prev_slot = -1;
+  uint32_t spar = 0, rpar = (uint32_t)(grp / P.n_ring) & 1u;
+  unsigned k2 = 0;                                   // this group's frame counter
+  FW_TRACE_ONLY(long long tw_slot = 0; long long tw_frame = 0; long long tw_bar = 0;)
+#pragma unroll 1
+  for (unsigned ic = (unsigned)grp; ic < nfr; ic += FW_NGG, ++k2) {
+    const unsigned it = ic / FW_M;
+    const int r = (int)(ic & (FW_M - 1));
+    if (gw == 0 && grp == 0 && r == 0) {
+      FW_TILE(0, it, 0, clock64());
+      FW_TILE(0, it, 1, tw_slot);
+      FW_TILE(0, it, 2, tw_frame);
+      FW_TILE(0, it, 3, tw_bar);
+    }
+    const long long f = ((long long)blockIdx.x + (long long)it * gridDim.x) * FW_M + r;
+    const int rr = r & (FW_SUB - 1);
+    if (gw == 0 && grp == 0) FW_EVT(0, k2, 0);
+    if (rr < FW_NGG) {                              // this group's first frame of a scratch sub-tile: slot must be free
+      if (ic >= FW_NGG && ++slot == P.n_slots) {
+        slot = 0;
+        spar ^= 1u;
+      }
+      {
+        // every lane waits (not lane 0 + __syncwarp): after a one-lane branch with a wait loop inside the warp stayed
+        // SPLIT (lane 0 | lanes 1-31) for the rest of the frame -- every instruction issued twice, every shuffle through
+        // the WARPSYNC.COLLECTIVE slow path (profiles/r3h: 13 collectives x 8 per frame)
+        FW_WAIT_BEGIN();
+        mbar_wait_hint(&bars->s_free[slot], spar ^ 1u);
+        FW_WAIT_END(tw_slot);
+      }
+    }
+    if (f < L) {
+      if (gw == 0 && grp == 0) FW_EVT(0, k2, 1);
+      {
+        FW_WAIT_BEGIN();
+        mbar_wait_hint(&bars->x_full[rs], rpar);
+        FW_WAIT_END(tw_frame);
+      }
+      // the frame sits `off` bytes into its ring slot (copies start on the 16-byte grid)
+      const uint32_t off = (uint32_t)((unsigned long long)f * (unsigned long long)(12 * P.n_inp) +
+                                      (unsigned long long)reinterpret_cast<uintptr_t>(P.x_base)) & 15u;
+      const float* xf = reinterpret_cast<const float*>(smem + P.off_ring + (size_t)rs * P.ring_slot_bytes + off);
+      if (gw == 0 && grp == 0) FW_EVT(0, k2, 2);
+      float* const row = cta_scratch + (long long)slot * P.slot_floats + (long long)rr * P.row_floats;
+      float* const units = row + FW_HDR_FLOATS;
+      // Order of a frame: every READ of the staged frame first (moment loop, position atoms, the entry's atoms into
+      // registers), then the ring slot goes back to the X producer, then the dihedral arithmetic and its stores, which
+      // need the frame no more.  A group gets a frame per max(T_frame, T_load), and the ring holds only four frames of
+      // a C3 system: the earlier a slot is released, the more of the reload overlaps the group's own work.
+      float pvx = 0.f, pvy = 0.f, pvz = 0.f;
+      if (aligned) {
+        // pivoted one-pass moments (reference ann.py:179-187): d_k = x_k - x_{A_0}, H = sum d_k^T y_k (the
+        // reference is centred); this warp's partial of H and of sum d_k goes to the row header
+        const float* p0 = xf + 3 * fw_tab_i<TS>(smem, P.off_aidx, P.align_idx, 0);
+        pvx = p0[0]; pvy = p0[1]; pvz = p0[2];
+        float m[12];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) m[i] = 0.f;
+#pragma unroll 1
+        for (int k = gt; k < P.n_align; k += gstride) {
+          const float* p = xf + 3 * fw_tab_i<TS>(smem, P.off_aidx, P.align_idx, k);
+          const float px = p[0] - pvx, py = p[1] - pvy, pz = p[2] - pvz;
+          const float y0 = fw_tab_f<TS>(smem, P.off_ref, P.ref_x, 3 * k), y1 = fw_tab_f<TS>(smem, P.off_ref, P.ref_x, 3 * k + 1),
+                      y2 = fw_tab_f<TS>(smem, P.off_ref, P.ref_x, 3 * k + 2);
+          m[0] = fmaf(px, y0, m[0]); m[1] = fmaf(px, y1, m[1]); m[2] = fmaf(px, y2, m[2]);
+          m[3] = fmaf(py, y0, m[3]); m[4] = fmaf(py, y1, m[4]); m[5] = fmaf(py, y2, m[5]);
+          m[6] = fmaf(pz, y0, m[6]); m[7] = fmaf(pz, y1, m[7]); m[8] = fmaf(pz, y2, m[8]);
+          m[9] += px; m[10] += py; m[11] += pz;
+          if (P.pos_is_align) {                     // the same atom is position unit k: its raw coordinates are here
+            float* dst = units + 4 * k;
+            fw_st2(dst, px, py, pol_keep);
+            fw_st1(dst + 2, pz, pol_keep);
+            if (k >= P.n_inv) fw_st1(dst + 3, 0.f, pol_keep);
+          }
+        }
+        // the loop's trip count differs between lanes: without this the two halves of the warp ran the rest of the frame
+        // one after the other (every instruction issued twice, each shuffle wrapped in a WARPSYNC.COLLECTIVE call)
+        __syncwarp();
+        sb_reduce12_store(m, row + gw * 12, lane);
+      }
+      if (gw == 0 && grp == 0) FW_EVT(0, k2, 3);
+      // raw (pivot-relative) coordinates of the position atoms; the w slot of a unit belongs to invariant
+      // column u when there is one, else it is zero
+      if (!(aligned && P.pos_is_align)) {
+        for (int u = gt; u < P.n_pos; u += gstride) {
+          const float* p = xf + 3 * fw_tab_i<TS>(smem, P.off_pos, P.pos_atom, u);
+          float* dst = units + 4 * u;
+          fw_st2(dst, p[0] - pvx, p[1] - pvy, pol_keep);
+          fw_st1(dst + 2, p[2] - pvz, pol_keep);
+          if (u >= P.n_inv) fw_st1(dst + 3, 0.f, pol_keep);
+        }
+        __syncwarp();
+      }
+      if (gw == 0 && grp == 0) FW_EVT(0, k2, 4);
+      // invariant features (bond / angle / dihedral, ann.py:323-351) from the raw coordinates.  With at most one
+      // entry per thread (C3: 100 dihedrals on 128 threads) a [cos, sin] dihedral only LOADS its four atoms here
+      FwInvOut out{units, P.n_pos, pol_keep};
+      bool late_dihedral = false;
+      V3 d0, d1, d2, d3;
+      int d_off = 0;
+      {
+        Rigid none;
+        const int* ient = TS ? reinterpret_cast<const int*>(smem + P.off_ent) : P.inv_ent;
+        if (P.n_inv_ent <= gstride) {
+          if (gt < P.n_inv_ent) {
+            const Entry en = load_entry(ient + ENTRY_INTS * gt);
+            if (FW_OPT_LATE && en.type == FEAT_DIHEDRAL && !P.use_angle) {
+              d0 = ld3(xf, en.a0); d1 = ld3(xf, en.a1); d2 = ld3(xf, en.a2); d3 = ld3(xf, en.a3);
+              d_off = en.off;
+              late_dihedral = true;
+            } else {
+              feature_forward(en, xf, false, none, P.use_angle, out);
+            }
+          }
+        } else {
+          for (int e = gt; e < P.n_inv_ent; e += gstride) {
+            const Entry en = load_entry(ient + ENTRY_INTS * e);
+            if (en.type == FEAT_DIHEDRAL && !P.use_angle)
+              fw_dihedral_cos_sin(ld3(xf, en.a0), ld3(xf, en.a1), ld3(xf, en.a2), ld3(xf, en.a3), en.off, out);
+            else feature_forward(en, xf, false, none, P.use_angle, out);
+          }
+        }
+      }
+      if (gw == 0 && grp == 0) FW_EVT(0, k2, 5);
+      __syncwarp();                                 // every lane has read what it needs of the frame
+      if (lane == 0) {
+        mbar_arrive(&bars->x_empty[rs]);
+        // publish this warp's part of the PREVIOUS frame's row: those stores were issued a whole frame ago, so
+        // the release does not stall
+        if (prev_slot >= 0) mbar_arrive(&bars->s_full[prev_slot]);
+      }
+      if (late_dihedral) fw_dihedral_cos_sin(d0, d1, d2, d3, d_off, out);
+      if (gt == 0 && P.n_inv > P.n_pos) {           // zero the unused tail of the last invariant unit
+        for (int v = P.n_inv; ((v - P.n_pos) & 3) != 0; ++v) out(v, 0.f);
+      }
+      prev_slot = slot;
+      if (gw == 0 && grp == 0) FW_EVT(0, k2, 6);
+      rs += FW_NGG;
+      while (rs >= P.n_ring) {
+        rs -= P.n_ring;
+        rpar ^= 1u;
+      }
+      if (gw == 0 && grp == 0) FW_EVT(0, k2, 7);
+    } else if (lane == 0) {
+      mbar_arrive(&bars->s_full[slot]);             // past the end of the batch: keep the sub-tile's count whole
+    }
+  }
+  __syncwarp();
+  if (lane == 0 && prev_slot >= 0) mbar_arrive(&bars->s_full[prev_slot]);
 }
 
 template <int ACT>
@@ -255,11 +492,11 @@ fused_wide_forward_kernel(const __grid_constant__ FwParams P, const float* __res
       mbar_init(&bars->d_free[s], 16 * 32);
     }
     for (int s = 0; s < FW_MAX_RING; ++s) {
-      mbar_init(&bars->x_full[s], 32);             // every lane of the X producer arrives (cp.async completion)
-      mbar_init(&bars->x_empty[s], 1);
+      mbar_init(&bars->x_full[s], FW_OPT_XPROD2 ? 64 : 32);   // every lane of the X producer warps arrives (cp.async completion)
+      mbar_init(&bars->x_empty[s], FW_NGW);   // every warp of the frame's group releases it
     }
     for (int s = 0; s < FW_MAX_SLOTS; ++s) {
-      mbar_init(&bars->s_full[s], FW_SUB * FW_NGW);  // the four warps of a frame's group each publish their part
+      mbar_init(&bars->s_full[s], FW_SUB * (FW_NGW));   // each warp publishes its part of a row
       mbar_init(&bars->s_free[s], 1);
     }
     for (int s = 0; s < 4; ++s) mbar_init(&bars->turn[s], 128);
@@ -310,15 +547,25 @@ fused_wide_forward_kernel(const __grid_constant__ FwParams P, const float* __res
 #define FW_RING (smem + P.off_ring)
 #define FW_CTA_SCRATCH (P.scratch + (long long)blockIdx.x * P.cta_floats)
 
-  if (warp >= FW_W_GEO) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(FW_REGS_GEO));
-  else if (warp >= FW_W_WPROD) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(FW_REGS_CTRL));
-
-  if (warp == FW_W_XPROD) {
-    // ================= X producer: whole frames into the shared-memory ring =================
+  // every role states its register budget at the TOP of its own branch: ptxas compiles a region under the smallest
+  // setmaxnreg that can reach it, and it does not correlate two tests of `warp` (a budget set in a separate if-chain
+  // ahead of the dispatch put the geometry role on the control warps' 24 registers: 57 spill stores per frame loop)
+  if (warp >= FW_W_WPROD && warp < FW_W_GEO) {
+  // ---- the control warpgroup (W producer, MMA issuer, two X producers): ONE setmaxnreg for its four warps (the
+  // instruction is .aligned per warpgroup: four copies in four branches are an illegal instruction)
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(FW_REGS_CTRL));
+  if (warp == FW_W_XPROD || (FW_OPT_XPROD2 && warp == FW_W_XPROD + 1)) {
+    // ================= X producers: whole frames into the shared-memory ring =================
     // 16-byte cp.async (LDGSTS) copies, NOT the bulk-copy engine: that engine is one in-order queue per SM, and with
     // 24 KB frame loads (HBM latency) always in flight every small bulk store and every fence.proxy.async of the
     // other roles waited 4.6 k cycles behind them (tests/cuda/fw_trace.cu).  A copy starts at the 16-byte boundary
-    // below the frame and may run up to 15 bytes past it -- never past the end of x (fw_plain_frame_copy).
+    // below the frame and may run up to 15 bytes past it -- never past the end of x (fw_frame_is_staged: the one
+    // frame of a batch that would is copied float by float).
+    // Two warps take alternate 2 KB pieces of every frame, four copies per loop trip: with one warp and a rolled loop
+    // the ISSUE of a frame's 47 copies took ~850 cycles, a quarter of the time from "slot free" to "frame landed",
+    // and that time, not the geometry, bounded a group's frame rate (ring of four frames, two groups).
+    const int half = warp - FW_W_XPROD;
+    constexpr uint32_t nprod = FW_OPT_XPROD2 ? 2 : 1;
     int rs = 0;
     uint32_t rpar = 0;
     const uint32_t fbytes = 12u * (uint32_t)P.n_inp;
@@ -337,16 +584,27 @@ fused_wide_forward_kernel(const __grid_constant__ FwParams P, const float* __res
         const uint32_t off = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15u);
         const uint32_t bytes = (fbytes + off + 15u) & ~15u;
         const uint32_t d0 = smem_u32(FW_RING) + (uint32_t)rs * (uint32_t)P.ring_slot_bytes;
-        // the batch's very last frame is not staged when its copy would run past the end of x: the geometry role
-        // reads that one frame straight from global memory (fw_frame_is_staged)
-        if (!fw_frame_is_staged(f0 + r, L, off, fbytes)) break;
-        if (lane == 0) mbar_wait_hint(&bars->x_empty[rs], rpar ^ 1u);
-        __syncwarp();
-        const unsigned char* s0 = src - off + lane * 16;
-        for (uint32_t o = (uint32_t)lane * 16u; o < bytes; o += 512u, s0 += 512)
-          asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(d0 + o), "l"(s0),
-                       "l"(pol_stream)
-                       : "memory");
+        mbar_wait_hint(&bars->x_empty[rs], rpar ^ 1u);
+        const unsigned char* s0 = src - off;
+        uint32_t o = (uint32_t)half * FW_PIECE + (uint32_t)lane * 16u;
+        // the batch's very last frame goes float by float when its 16-byte copies would run past the end of x
+        if (!fw_frame_is_staged(f0 + r, L, off, fbytes)) {
+          for (uint32_t b = (uint32_t)(half * 32 + lane) * 4u; b < fbytes; b += nprod * 32u * 4u)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d0 + off + b), "l"(src + b) : "memory");
+          o = bytes;
+        }
+        for (; o + 3u * 512u < bytes; o += nprod * FW_PIECE) {                                   // a whole 2 KB piece
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(d0 + o + q * 512u),
+                         "l"(s0 + o + q * 512u), "l"(pol_stream)
+                         : "memory");
+        }
+        for (int q = 0; q < 4; ++q)                                                               // the ragged last piece
+          if (o + q * 512u < bytes)
+            asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(d0 + o + q * 512u),
+                         "l"(s0 + o + q * 512u), "l"(pol_stream)
+                         : "memory");
         asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&bars->x_full[rs]))
                      : "memory");
         if (++rs == P.n_ring) {
@@ -354,220 +612,6 @@ fused_wide_forward_kernel(const __grid_constant__ FwParams P, const float* __res
           rpar ^= 1u;
         }
       }
-    }
-  } else if (warp >= FW_W_GEO) {
-    // ================= geometry: moments, raw position atoms, invariant features -> scratch =================
-    // The four warps work on ONE frame at a time (thread = alignment atom / position atom / invariant entry), so
-    // the frames behind it in the ring are pure prefetch and a frame's latency is that of one entry, not of
-    // n_entries / 32 iterations of a single warp (tests/cuda/fw_trace.cu: 18 k cycles per frame per warp before).
-    // Two such groups take alternate frames (frame ic goes to group ic mod 2), which doubles the chains in flight.
-    const int grp = (warp - FW_W_GEO) / FW_NGW;
-    const int gw = (warp - FW_W_GEO) % FW_NGW;
-    const int gt = gw * 32 + lane;                    // 0 .. 127 within the group
-    const bool aligned = P.n_align > 0;
-    const int n3 = 3 * P.n_inp;
-    // geo (per group): [2][row_floats] staging rows, then [2][4][12] per-warp moment partials (double-buffered)
-    float* const geo = reinterpret_cast<float*>(smem + P.off_rowbuf) + (size_t)grp * (2 * P.row_floats + 96);
-    float* const red_base = geo + 2 * (size_t)P.row_floats;
-    const unsigned nfr = (unsigned)((FW_NTILES - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * FW_M;
-    int slot = 0, rs = grp % P.n_ring, prev_slot = -1;
-    uint32_t spar = 0, rpar = (uint32_t)(grp / P.n_ring) & 1u;
-    unsigned k2 = 0;                                   // this group's frame counter (buffer parity)
-#pragma unroll 1
-    for (unsigned ic = (unsigned)grp; ic < nfr; ic += FW_NGG, ++k2) {
-      const unsigned it = ic / FW_M;
-      const int r = (int)(ic & (FW_M - 1));
-      const long long f = ((long long)blockIdx.x + (long long)it * gridDim.x) * FW_M + r;
-      const int rr = r & (FW_SUB - 1);
-      if (gw == 0 && grp == 0) FW_EVT(0, k2, 0);
-      if (rr < FW_NGG) {                              // this group's first frame of a scratch sub-tile: slot must be free
-        if (ic >= FW_NGG && ++slot == P.n_slots) {
-          slot = 0;
-          spar ^= 1u;
-        }
-        if (lane == 0) mbar_wait_hint(&bars->s_free[slot], spar ^ 1u);
-        __syncwarp();
-      }
-      if (f < L) {
-        if (gw == 0 && grp == 0) FW_EVT(0, k2, 1);
-        const uint32_t off = (uint32_t)(reinterpret_cast<uintptr_t>(x + f * n3) & 15u);
-        const bool staged = fw_frame_is_staged(f, L, off, 4u * (uint32_t)n3);
-        const float* xf = x + f * n3;                 // (the one unstaged frame of a batch is read in place)
-        if (staged) {
-          if (lane == 0) mbar_wait_hint(&bars->x_full[rs], rpar);
-          __syncwarp();
-          xf = reinterpret_cast<const float*>(FW_RING + (size_t)rs * P.ring_slot_bytes + off);
-        }
-        if (gw == 0 && grp == 0) FW_EVT(0, k2, 2);
-        float* const rowbuf = geo + (size_t)(k2 & 1u) * P.row_floats;
-        float* const red = red_base + (k2 & 1u) * 48;
-        float pvx = 0.f, pvy = 0.f, pvz = 0.f;
-        if (aligned) {
-          // pivoted one-pass moments (reference ann.py:179-187): d_k = x_k - x_{A_0}, H = sum d_k^T y_k (the
-          // reference is centred); the header carries H and sum d_k (c_rel = sum / n_a is formed by the converter)
-          const int* aidx = P.off_aidx >= 0 ? reinterpret_cast<const int*>(smem + P.off_aidx) : P.align_idx;
-          const float* refx = P.off_ref >= 0 ? reinterpret_cast<const float*>(smem + P.off_ref) : P.ref_x;
-          const float* p0 = xf + 3 * aidx[0];
-          pvx = p0[0]; pvy = p0[1]; pvz = p0[2];
-          float m[12];
-#pragma unroll
-          for (int i = 0; i < 12; ++i) m[i] = 0.f;
-#pragma unroll 1
-          for (int k = gt; k < P.n_align; k += 4 * 32) {
-            const float* p = xf + 3 * aidx[k];
-            const float px = p[0] - pvx, py = p[1] - pvy, pz = p[2] - pvz;
-            const float y0 = refx[3 * k], y1 = refx[3 * k + 1], y2 = refx[3 * k + 2];
-            m[0] = fmaf(px, y0, m[0]); m[1] = fmaf(px, y1, m[1]); m[2] = fmaf(px, y2, m[2]);
-            m[3] = fmaf(py, y0, m[3]); m[4] = fmaf(py, y1, m[4]); m[5] = fmaf(py, y2, m[5]);
-            m[6] = fmaf(pz, y0, m[6]); m[7] = fmaf(pz, y1, m[7]); m[8] = fmaf(pz, y2, m[8]);
-            m[9] += px; m[10] += py; m[11] += pz;
-            if (P.pos_is_align) {                     // the same atom is position unit k: its raw coordinates are here
-              float* dst = rowbuf + FW_HDR_FLOATS + 4 * k;
-              *reinterpret_cast<float2*>(dst) = make_float2(px, py);
-              dst[2] = pz;
-              if (k >= P.n_inv) dst[3] = 0.f;
-            }
-          }
-          sb_reduce12_store(m, red + gw * 12, lane);
-        }
-        if (gw == 0 && grp == 0) FW_EVT(0, k2, 3);
-        float* units = rowbuf + FW_HDR_FLOATS;
-        // raw (pivot-relative) coordinates of the position atoms; the w slot of a unit belongs to invariant
-        // column u when there is one, else it is zero
-        if (!(aligned && P.pos_is_align)) {
-          const int* pos_atom = P.off_pos >= 0 ? reinterpret_cast<const int*>(smem + P.off_pos) : P.pos_atom;
-          for (int u = gt; u < P.n_pos; u += 4 * 32) {
-            const float* p = xf + 3 * pos_atom[u];
-            float* dst = units + 4 * u;
-            *reinterpret_cast<float2*>(dst) = make_float2(p[0] - pvx, p[1] - pvy);
-            dst[2] = p[2] - pvz;
-            if (u >= P.n_inv) dst[3] = 0.f;
-          }
-        }
-        if (gw == 0 && grp == 0) FW_EVT(0, k2, 4);
-        // invariant features (bond / angle / dihedral, ann.py:323-351) from the raw coordinates
-        {
-          FwInvOut out{units, P.n_pos};
-          Rigid none;
-          const int* ient = P.off_ent >= 0 ? reinterpret_cast<const int*>(smem + P.off_ent) : P.inv_ent;
-          for (int e = gt; e < P.n_inv_ent; e += 4 * 32) {
-            const Entry en = load_entry(ient + ENTRY_INTS * e);
-            if (en.type == FEAT_DIHEDRAL && !P.use_angle) fw_dihedral_cos_sin(en, xf, out);
-            else feature_forward(en, xf, false, none, P.use_angle, out);
-          }
-          if (gt == 0 && P.n_inv > P.n_pos) {         // zero the unused tail of the last invariant unit
-            for (int v = P.n_inv; ((v - P.n_pos) & 3) != 0; ++v) out(v, 0.f);
-          }
-        }
-        if (gw == 0 && grp == 0) FW_EVT(0, k2, 5);
-        // the row, the partials; every read of the frame is done (named barrier of this group)
-        asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory");
-        if (gw == 0 && grp == 0) FW_EVT(0, k2, 6);
-        if (lane == 0) {
-          if (gw == 0 && staged) mbar_arrive(&bars->x_empty[rs]);
-          // publish this warp's part of the PREVIOUS frame's row: those stores were issued a whole frame ago, so
-          // the release does not stall
-          if (prev_slot >= 0) mbar_arrive(&bars->s_full[prev_slot]);
-        }
-        prev_slot = slot;
-        if (gw == 0) {                                // header: fixed-order sum of the four warps' partials
-          if (aligned && lane < 12) rowbuf[lane] = (red[lane] + red[12 + lane]) + (red[24 + lane] + red[36 + lane]);
-          __syncwarp();
-        }
-        {                                             // staging row -> scratch, coalesced 16-byte stores
-          float4* dst = reinterpret_cast<float4*>(FW_CTA_SCRATCH + (long long)slot * P.slot_floats +
-                                                  (long long)rr * P.row_floats);
-          const float4* srow = reinterpret_cast<const float4*>(rowbuf);
-          for (int i = gt; i < P.row_floats / 4; i += 4 * 32) dst[i] = srow[i];
-        }
-        if (gw == 0 && grp == 0) FW_EVT(0, k2, 7);
-        rs += FW_NGG;
-        while (rs >= P.n_ring) {
-          rs -= P.n_ring;
-          rpar ^= 1u;
-        }
-      } else if (lane == 0) {
-        mbar_arrive(&bars->s_full[slot]);             // past the end of the batch: keep the sub-tile's count whole
-      }
-    }
-    __syncwarp();
-    if (lane == 0 && prev_slot >= 0) mbar_arrive(&bars->s_full[prev_slot]);
-  } else if (warp < FW_W_EPI) {
-    // ================= converter: rotation per frame, then K-chunks scratch -> TF32 hi / lo operand tiles ==========
-    if (FW_REGS_CONV > FW_REGS_LAUNCH) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(FW_REGS_CONV));
-    if (FW_REGS_CONV < FW_REGS_LAUNCH) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(FW_REGS_CONV));
-    const int row = tid;                               // 0 .. 127
-    const bool aligned = P.n_align > 0;
-    unsigned it = 0;
-    int s = 0;
-    uint32_t par = 0;
-    const int ntiles = FW_NTILES;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-      // layer 2's operand chunks of the previous tile share the stage ring: they must all have been written before
-      // this role asks for a stage again (a waiter may be at most one phase ahead of an mbarrier)
-      if (warp == 0) FW_EVT(1, it, 0);
-      if (it > 0 && P.n_hidden == 2) mbar_wait_hint(&bars->turn[3], (it - 1u) & 1u);
-      if (warp == 0) FW_EVT(1, it, 1);
-      const unsigned j = it * (FW_M / FW_SUB) + (unsigned)warp;
-      const unsigned use = j / (unsigned)P.n_slots;
-      const int slot = (int)(j - use * (unsigned)P.n_slots);
-      mbar_wait_hint(&bars->s_full[slot], use & 1u);
-      if (warp == 0) FW_EVT(1, it, 2);
-      const float* myrow = FW_CTA_SCRATCH + (long long)slot * P.slot_floats + (long long)lane * P.row_floats;
-      const float4* units = reinterpret_cast<const float4*>(myrow + FW_HDR_FLOATS);
-      const bool valid = (long long)tile * FW_M + row < L;
-      Rigid rg;
-      float c0 = 0.f, c1 = 0.f, c2 = 0.f;
-      if (aligned) {
-        const float4* h = reinterpret_cast<const float4*>(myrow);
-        float4 h0 = make_float4(1.f, 0.f, 0.f, 0.f), h1 = make_float4(1.f, 0.f, 0.f, 0.f),
-               h2 = make_float4(1.f, 0.f, 0.f, 0.f);
-        if (valid) { h0 = __ldcg(h); h1 = __ldcg(h + 1); h2 = __ldcg(h + 2); }
-        rg.H[0] = h0.x; rg.H[1] = h0.y; rg.H[2] = h0.z; rg.H[3] = h0.w;
-        rg.H[4] = h1.x; rg.H[5] = h1.y; rg.H[6] = h1.z; rg.H[7] = h1.w; rg.H[8] = h2.x;
-        const float inv_n = 1.0f / (float)P.n_align;
-        c0 = h2.y * inv_n; c1 = h2.z * inv_n; c2 = h2.w * inv_n;
-        kabsch_rotation(rg);                          // reference ann.py:188-195 as a quaternion eigenproblem
-      }
-      if (warp == 0) FW_EVT(1, it, 3);
-      float4 nxt[FW_KU];
-#pragma unroll
-      for (int q = 0; q < FW_KU; ++q) nxt[q] = valid ? __ldcg(units + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int kc = 0; kc < P.nkc1; ++kc) {
-        float4 v[FW_KU];
-#pragma unroll
-        for (int q = 0; q < FW_KU; ++q) v[q] = nxt[q];
-        if (kc + 1 < P.nkc1 && valid) {
-          const float4* src = units + (size_t)(kc + 1) * FW_KU;
-#pragma unroll
-          for (int q = 0; q < FW_KU; ++q) nxt[q] = __ldcg(src + q);
-        }
-#pragma unroll
-        for (int q = 0; q < FW_KU; ++q) {
-          const int u = kc * FW_KU + q;
-          if (u >= P.n_units) {
-            v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-          } else if (aligned && u < P.n_pos) {        // z = (p - c) R  (ann.py:197), p and c relative to the pivot
-            const float dx = v[q].x - c0, dy = v[q].y - c1, dz = v[q].z - c2;
-            v[q].x = fmaf(dx, rg.R[0], fmaf(dy, rg.R[3], dz * rg.R[6]));
-            v[q].y = fmaf(dx, rg.R[1], fmaf(dy, rg.R[4], dz * rg.R[7]));
-            v[q].z = fmaf(dx, rg.R[2], fmaf(dy, rg.R[5], dz * rg.R[8]));
-          }
-        }
-        if (warp == 0 && it == 0) FW_EVT(1, 16 + kc, 0);
-        mbar_wait_hint(&bars->empty[s], par ^ 1u);
-        if (warp == 0 && it == 0) FW_EVT(1, 16 + kc, 1);
-        fw_store_units(FW_STAGES + (size_t)s * FW_STAGE_BYTES, row, v);
-        if (warp == 0 && it == 0) FW_EVT(1, 16 + kc, 2);
-        fence_proxy_async_smem();
-        mbar_arrive(&bars->a_full[s]);
-        if (warp == 0 && it == 0) FW_EVT(1, 16 + kc, 3);
-        fw_stage_step(s, par, P.n_stages);
-      }
-      __syncwarp();
-      if (warp == 0) FW_EVT(1, it, 4);
-      if (lane == 0) mbar_arrive(&bars->s_free[slot]);
-      if (P.n_hidden == 2) fw_stage_skip(s, par, P.nkc2, P.n_stages);
     }
   } else if (warp == FW_W_WPROD) {
     // ================= W producer: pre-packed weight blocks, layer 1 then layer 2 =================
@@ -601,7 +645,12 @@ fused_wide_forward_kernel(const __grid_constant__ FwParams P, const float* __res
     const int cpa2 = (P.nkc2 + (512 / stride2) - 1) / (512 / stride2);
     const int ntiles = FW_NTILES;
     unsigned char* const stages = FW_STAGES;
+    FW_TRACE_ONLY(long long tw_a = 0; long long tw_b = 0; long long tw_d = 0;)
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      FW_TILE(3, it, 0, clock64());
+      FW_TILE(3, it, 1, tw_a);
+      FW_TILE(3, it, 2, tw_b);
+      FW_TILE(3, it, 3, tw_d);
       if (it > 0 && P.n_hidden == 2) {                       // layer 2's accumulators of the previous tile are read
         mbar_wait_hint(&bars->l2_free, (it - 1u) & 1u);
         tc_fence_after_sync();
@@ -628,7 +677,9 @@ fused_wide_forward_kernel(const __grid_constant__ FwParams P, const float* __res
             first = (kc % FW_SEGC) == 0;
             seg_last = (kc % FW_SEGC) == FW_SEGC - 1 || kc == nkc - 1;
             if (first) {
+              FW_WAIT_BEGIN();
               mbar_wait_hint(&bars->d_free[db], ((sg >> 1) & 1u) ^ 1u);
+              FW_WAIT_END(tw_d);
               tc_fence_after_sync();
             }
           } else {
@@ -636,10 +687,19 @@ fused_wide_forward_kernel(const __grid_constant__ FwParams P, const float* __res
             first = (kc % cpa2) == 0;
           }
           FW_EVT(3, tci, 1);
-          mbar_wait_hint(&bars->a_full[s], par);
+          {
+            FW_WAIT_BEGIN();
+            mbar_wait_hint(&bars->a_full[s], par);
+            FW_WAIT_END(tw_a);
+          }
           FW_EVT(3, tci, 2);
-          mbar_wait_hint(&bars->b_full[s], par);
+          {
+            FW_WAIT_BEGIN();
+            mbar_wait_hint(&bars->b_full[s], par);
+            FW_WAIT_END(tw_b);
+          }
           FW_EVT(3, tci, 3);
+          if (layer == 1 && kc == 0) FW_TILE(3, it, 4, clock64());
           tc_fence_after_sync();
           const uint32_t a_hi = smem_u32(stages + (size_t)s * FW_STAGE_BYTES), a_lo = a_hi + FW_A_HALF;
           const uint32_t b_hi = a_hi + 2 * FW_A_HALF, b_lo = b_hi + (uint32_t)np * FW_KC * 4u;
@@ -673,6 +733,153 @@ fused_wide_forward_kernel(const __grid_constant__ FwParams P, const float* __res
         }
       }
     }
+  }
+  } else if (warp >= FW_W_GEO) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(FW_REGS_GEO));
+    const int ntile_cta = (FW_NTILES - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const bool tabs = P.off_ent >= 0 && (P.n_align == 0 || P.off_aidx >= 0) && (P.off_pos >= 0 || P.pos_is_align);
+    if (tabs) fw_geometry_role<true>(P, bars, smem, L, ntile_cta, warp - FW_W_GEO, lane);
+    else fw_geometry_role<false>(P, bars, smem, L, ntile_cta, warp - FW_W_GEO, lane);
+  } else if (warp < FW_W_EPI) {
+    // ================= converter: rotation per frame, then K-chunks scratch -> TF32 hi / lo operand tiles ==========
+    // The scratch is read with cp.async into a small staging ring, P.conv_depth chunks ahead: a read of the L2 scratch
+    // takes 3-4 k cycles while the frame stream keeps the memory pipe busy (tests/cuda/fw_trace.cu), and with one
+    // chunk of register prefetch that latency was the period of the whole MMA chain.
+    if (FW_REGS_CONV > FW_REGS_LAUNCH) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(FW_REGS_CONV));
+    if (FW_REGS_CONV < FW_REGS_LAUNCH) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(FW_REGS_CONV));
+    const int row = tid;                               // 0 .. 127
+    const bool aligned = P.n_align > 0;
+    constexpr int ngw = FW_NGW;
+    const int depth = P.conv_depth;
+    unsigned char* const cst = smem + P.off_cstage + row * 16;     // this thread's 16-byte column of the staging ring
+    unsigned it = 0;
+    int s = 0;
+    uint32_t par = 0;
+    const int ntiles = FW_NTILES;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      if (warp == 0) FW_EVT(1, it, 0);
+      if (warp == 0) FW_TILE(1, it, 0, clock64());
+      const unsigned j = it * (FW_M / FW_SUB) + (unsigned)warp;
+      const unsigned use = j / (unsigned)P.n_slots;
+      const int slot = (int)(j - use * (unsigned)P.n_slots);
+      mbar_wait_hint(&bars->s_full[slot], use & 1u);
+      if (warp == 0) FW_EVT(1, it, 1);
+      if (warp == 0) FW_TILE(1, it, 1, clock64());
+      const float* myrow = FW_CTA_SCRATCH + (long long)slot * P.slot_floats + (long long)lane * P.row_floats;
+      const float* units = myrow + FW_HDR_FLOATS;
+      const bool valid = (long long)tile * FW_M + row < L;
+      // raw chunk kc of this row -> staging slot kc mod depth (one commit group per chunk, empty ones included, so
+      // that "all but the newest depth - 1 groups" always means "chunk kc has landed")
+      auto fetch = [&](int kc) {
+        if (kc < P.nkc1 && valid) {
+          const uint32_t d0 = smem_u32(cst) + (uint32_t)(kc % depth) * FW_CONV_CHUNK;
+          const float* src = units + (size_t)kc * FW_KC;
+#pragma unroll
+          for (int q = 0; q < FW_KU; ++q)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + (uint32_t)q * (FW_M * 16)), "l"(src + 4 * q)
+                         : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      };
+      for (int kc = 0; kc < depth - 1; ++kc) fetch(kc);
+      Rigid rg;
+      float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+      if (aligned) {
+        // moment partials of the frame's geometry warps, added in a fixed order: ((p0 + p1) + (p2 + p3)) [+ ...]
+        float hs[12];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) hs[i] = 0.f;
+        if (valid) {
+          const float4* h = reinterpret_cast<const float4*>(myrow);
+          for (int q4 = 0; q4 < ngw; q4 += 4) {
+            float quad[12];
+#pragma unroll
+            for (int pr = 0; pr < 2; ++pr) {
+              float a[12];
+#pragma unroll
+              for (int v4 = 0; v4 < 6; ++v4) {           // two partials = 24 floats = 6 float4
+                const float4 t = __ldcg(h + (q4 + 2 * pr) * 3 + v4);
+                const float tv[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                  const int i = 4 * v4 + c;
+                  if (i < 12) a[i] = tv[c];
+                  else a[i - 12] += tv[c];
+                }
+              }
+#pragma unroll
+              for (int i = 0; i < 12; ++i) quad[i] = pr == 0 ? a[i] : quad[i] + a[i];
+            }
+#pragma unroll
+            for (int i = 0; i < 12; ++i) hs[i] = q4 == 0 ? quad[i] : hs[i] + quad[i];
+          }
+        } else {
+          hs[0] = hs[4] = hs[8] = 1.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 9; ++i) rg.H[i] = hs[i];
+        const float inv_n = 1.0f / (float)P.n_align;
+        c0 = hs[9] * inv_n; c1 = hs[10] * inv_n; c2 = hs[11] * inv_n;
+        kabsch_rotation(rg);                          // reference ann.py:188-195 as a quaternion eigenproblem
+      }
+      if (warp == 0) FW_EVT(1, it, 2);
+      if (warp == 0) FW_TILE(1, it, 2, clock64());
+      // layer 2's operand chunks of the previous tile share the stage ring: they must all have been written before
+      // this role asks for a stage again (a waiter may be at most one phase ahead of an mbarrier)
+      if (it > 0 && P.n_hidden == 2) mbar_wait_hint(&bars->turn[3], (it - 1u) & 1u);
+      if (warp == 0) FW_EVT(1, it, 3);
+      if (warp == 0) FW_TILE(1, it, 3, clock64());
+      FW_TRACE_ONLY(long long tw_empty = 0;)
+      for (int kc = 0; kc < P.nkc1; ++kc) {
+        fetch(kc + depth - 1);
+        if (depth == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else if (depth == 3) asm volatile("cp.async.wait_group 2;" ::: "memory");
+        else asm volatile("cp.async.wait_group 3;" ::: "memory");
+        float4 v[FW_KU];
+        {
+          const unsigned char* src = cst + (size_t)(kc % depth) * FW_CONV_CHUNK;
+#pragma unroll
+          for (int q = 0; q < FW_KU; ++q)
+            v[q] = valid ? *reinterpret_cast<const float4*>(src + q * (FW_M * 16)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int q = 0; q < FW_KU; ++q) {
+          const int u = kc * FW_KU + q;
+          if (u >= P.n_units) {
+            v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+          } else if (aligned && u < P.n_pos) {        // z = (p - c) R  (ann.py:197), p and c relative to the pivot
+            const float dx = v[q].x - c0, dy = v[q].y - c1, dz = v[q].z - c2;
+            v[q].x = fmaf(dx, rg.R[0], fmaf(dy, rg.R[3], dz * rg.R[6]));
+            v[q].y = fmaf(dx, rg.R[1], fmaf(dy, rg.R[4], dz * rg.R[7]));
+            v[q].z = fmaf(dx, rg.R[2], fmaf(dy, rg.R[5], dz * rg.R[8]));
+          }
+        }
+        if (warp == 0 && it == 0) FW_EVT(1, 16 + kc, 0);
+        {
+          FW_WAIT_BEGIN();
+          mbar_wait_hint(&bars->empty[s], par ^ 1u);
+          FW_WAIT_END(tw_empty);
+        }
+        if (warp == 0 && it == 0) FW_EVT(1, 16 + kc, 1);
+        fw_store_units(FW_STAGES + (size_t)s * FW_STAGE_BYTES, row, v);
+        if (warp == 0 && it == 0) FW_EVT(1, 16 + kc, 2);
+        fence_proxy_async_smem();
+        mbar_arrive(&bars->a_full[s]);
+        if (warp == 0 && it == 0) FW_EVT(1, 16 + kc, 3);
+        fw_stage_step(s, par, P.n_stages);
+      }
+      // the row is dead: drop its L2 lines instead of letting them be written back to DRAM
+#if FW_OPT_POLICY
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      for (int b = 0; b < P.row_floats; b += 32) asm volatile("discard.global.L2 [%0], 128;" ::"l"(myrow + b) : "memory");
+#endif
+      __syncwarp();
+      if (warp == 0) FW_EVT(1, it, 4);
+      if (warp == 0) FW_TILE(1, it, 4, clock64());
+      if (warp == 0) FW_TILE(1, it, 5, tw_empty);
+      if (lane == 0) mbar_arrive(&bars->s_free[slot]);
+      if (P.n_hidden == 2) fw_stage_skip(s, par, P.nkc2, P.n_stages);
+    }
   } else if (warp < FW_W_WPROD) {
     // ================= epilogue: segment sums, activations, layer 2 operand chunks, last layer, y =================
     if (FW_REGS_EPI > FW_REGS_LAUNCH) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(FW_REGS_EPI));
@@ -691,8 +898,10 @@ fused_wide_forward_kernel(const __grid_constant__ FwParams P, const float* __res
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       float acc[FW_CW];
       if (warp == FW_W_EPI) FW_EVT(2, it, 0);
+      if (warp == FW_W_EPI) FW_TILE(2, it, 0, clock64());
       fw_sum_segments(acc, nseg1, col0, P.n1p, lane_base, bars, sg, warp == FW_W_EPI && it == 0);
       if (warp == FW_W_EPI) FW_EVT(2, it, 1);
+      if (warp == FW_W_EPI) FW_TILE(2, it, 1, clock64());
 #pragma unroll
       for (int c = 0; c < FW_CW; ++c)
         if (col0 + c < P.n1p) acc[c] = fw_act<ACT>(acc[c] + b1[col0 + c]);
@@ -731,6 +940,7 @@ fused_wide_forward_kernel(const __grid_constant__ FwParams P, const float* __res
         mbar_wait_hint(&bars->l2_full, it & 1u);
         tc_fence_after_sync();
         if (warp == FW_W_EPI) FW_EVT(2, it, 3);
+        if (warp == FW_W_EPI) FW_TILE(2, it, 3, clock64());
         const int cpa2 = (P.nkc2 + (512 / stride2) - 1) / (512 / stride2);
         const int nacc2 = (P.nkc2 + cpa2 - 1) / cpa2;
         for (int a = 0; a < nacc2; ++a) {
@@ -777,6 +987,7 @@ fused_wide_forward_kernel(const __grid_constant__ FwParams P, const float* __res
       }
       asm volatile("bar.sync 1, %0;" ::"n"(16 * 32) : "memory");
       if (warp == FW_W_EPI) FW_EVT(2, it, 4);
+      if (warp == FW_W_EPI) FW_TILE(2, it, 4, clock64());
     }
   }
   tc_fence_before_sync();

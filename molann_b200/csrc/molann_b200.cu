@@ -701,7 +701,7 @@ WideChoice choose_wide(const MolannPrepared* h, const MolannPlan* p, long long L
   P.n_hidden = h->n_hidden; P.nkc1 = h->nkc1; P.n1p = h->n1p; P.nkc2 = h->nkc2; P.n2p = h->n2p;
   P.nlastp = h->nlastp; P.kout = h->kout;
   P.w1p = h->w1p; P.w2p = h->w2p; P.b1s = h->b1s; P.b2s = h->b2s; P.w3 = h->w3; P.b3 = h->b3;
-  P.row_floats = FW_HDR_FLOATS + h->nkc1 * FW_KC;
+  P.row_floats = fw_row_floats(h->nkc1);
   P.slot_floats = FW_SUB * P.row_floats;
   int slots = env_int("MOLANN_B200_WIDE_SLOTS", 6);
   if (slots < 5) slots = 5;                       // a tile (4 sub-tiles) + at least one the geometry can run ahead in
@@ -715,7 +715,12 @@ WideChoice choose_wide(const MolannPrepared* h, const MolannPlan* p, long long L
   P.off_b2 = c.take((h->n_hidden == 2 ? h->n2p : 1) * 4, 16);
   P.off_w3 = c.take(h->kout * h->nlastp * 4, 16);
   P.off_ypart = c.take(4 * FW_M * h->kout * 4, 16);
-  P.off_rowbuf = c.take(FW_NGG * (2 * P.row_floats + 2 * FW_NGW * 12) * 4, 128);   // staging rows + moment partials
+  // MOLANN_B200_WIDE_CDEPTH: raw K-chunks the converter keeps in flight
+  int depth = env_int("MOLANN_B200_WIDE_CDEPTH", 2);
+  if (depth < 2) depth = 2;
+  if (depth > FW_MAX_CDEPTH) depth = FW_MAX_CDEPTH;
+  P.conv_depth = depth;
+  P.off_cstage = c.take(depth * FW_CONV_CHUNK, 128);
   const int fixed = c.off;
   // operand stages and the frame ring share what is left; plan tables move in when there is room
   int stages = env_int("MOLANN_B200_WIDE_STAGES", 2);
@@ -755,7 +760,9 @@ int launch_wide_act(const WideChoice& ch, const float* x, float* y, long long L,
   auto kern = fused_wide_forward_kernel<ACT>;
   int s = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ch.P.total_smem));
   if (s) return s;
-  kern<<<(unsigned)ch.grid, FW_THREADS, ch.P.total_smem, st>>>(ch.P, x, y, L);
+  FwParams P = ch.P;
+  P.x_base = x;
+  kern<<<(unsigned)ch.grid, FW_THREADS, P.total_smem, st>>>(P, x, y, L);
   return post_launch();
 }
 
@@ -1537,8 +1544,8 @@ size_t molann_b200_prepared_workspace_bytes(const MolannPrepared* prepared, int6
   if (!dev.ok) dev.sm_count = 148;
   const long long ntiles = (L + FW_M - 1) / FW_M;
   const long long grid = dev.sm_count < ntiles ? dev.sm_count : ntiles;
-  const long long slot_floats = (long long)FW_SUB * (FW_HDR_FLOATS + prepared->nkc1 * FW_KC);
-  const size_t wide = (size_t)grid * FW_MAX_SLOTS * slot_floats * 4;
+  const long long slot_floats = (long long)FW_SUB * fw_row_floats(prepared->nkc1);
+  const size_t wide = (size_t)grid * FW_MAX_SLOTS * slot_floats * 4 + 128;    // + alignment of the rows to L2 lines
   // the layered kernels (value-and-gradient; forward when the wide kernel does not fit) share the same workspace
   MolannPlan shape;
   std::memset(&shape, 0, sizeof(shape));
@@ -1563,9 +1570,10 @@ int molann_b200_forward_prepared(const MolannPrepared* prepared, const MolannPla
   WideChoice ch = choose_wide(prepared, plan, (long long)L, dev);
   if (!ch.ok || env_int("MOLANN_B200_WIDE", -1) == 0)      // e.g. 60 KB frames: layered kernels on the packed operands
     return general_forward(plan, x, L, y, workspace, workspace_bytes, dev, static_cast<cudaStream_t>(stream), prepared);
-  const size_t need = (size_t)ch.grid * (size_t)ch.P.cta_floats * 4;
+  const size_t need = (size_t)ch.grid * (size_t)ch.P.cta_floats * 4 + 128;
   if (!workspace || workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 15u)) return MOLANN_ERR_WORKSPACE;
-  ch.P.scratch = static_cast<float*>(workspace);
+  // rows start on 128-byte L2 lines: a converter thread discards the lines of its row once it has read them
+  ch.P.scratch = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 127u) & ~(uintptr_t)127u);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (plan->act_id) {
     case MOLANN_ACT_TANH: return launch_wide_act<ACT_TANH>(ch, x, y, (long long)L, st);

@@ -9,12 +9,13 @@
 int main(int argc, char** argv) {
   const int n = argc > 1 ? atoi(argv[1]) : 2000;
   const int na = n / 10, nd = n / 20;
-  const int L = 148 * 128 * 2;
-  std::vector<float> x((size_t)L * n * 3), ref(na * 3), base(n * 3);
+  const int reps = argc > 2 ? atoi(argv[2]) : 2;        // tiles per CTA
+  const int L0 = 148 * 128, L = L0 * reps;             // host frames (one tile per CTA), replicated on the device
+  std::vector<float> x((size_t)L0 * n * 3), ref(na * 3), base(n * 3);
   unsigned s = 777u;
   auto rnd = [&]() { s = s * 1664525u + 1013904223u; return ((s >> 8) & 0xffff) / 65536.0f - 0.5f; };
   for (int j = 0; j < n; ++j) { base[3 * j] = 1.5f * j * 0.3f + rnd(); base[3 * j + 1] = 10.f * rnd(); base[3 * j + 2] = 10.f * rnd(); }
-  for (size_t f = 0; f < (size_t)L; ++f)
+  for (size_t f = 0; f < (size_t)L0; ++f)
     for (int j = 0; j < n * 3; ++j) x[f * n * 3 + j] = base[j] + 0.2f * rnd();
   std::vector<int> aidx(na), ent;
   float c[3] = {0, 0, 0};
@@ -25,7 +26,8 @@ int main(int argc, char** argv) {
   for (int k = 0; k < nd; ++k) { int e[6] = {2, 20 * k, 20 * k + 1, 20 * k + 2, 20 * k + 3, col}; ent.insert(ent.end(), e, e + 6); col += 2; }
   const int dims[4] = {col, 256, 128, 2};
   float *dx, *dy, *dref, *dW[3], *db[3]; int *daidx, *dent;
-  cudaMalloc(&dx, x.size() * 4); cudaMemcpy(dx, x.data(), x.size() * 4, cudaMemcpyHostToDevice);
+  cudaMalloc(&dx, x.size() * 4 * reps);
+  for (int r = 0; r < reps; ++r) cudaMemcpy(dx + (size_t)r * x.size(), x.data(), x.size() * 4, cudaMemcpyHostToDevice);
   cudaMalloc(&dy, (size_t)L * 2 * 4);
   cudaMalloc(&dref, ref.size() * 4); cudaMemcpy(dref, ref.data(), ref.size() * 4, cudaMemcpyHostToDevice);
   cudaMalloc(&daidx, na * 4); cudaMemcpy(daidx, aidx.data(), na * 4, cudaMemcpyHostToDevice);
@@ -62,13 +64,31 @@ int main(int argc, char** argv) {
 #ifndef MOLANN_WS_TRACE
   return 0;                                   // timing-only build (ncu target)
 #else
-  static long long tr[4 * 256 * 8];
+  static long long tr[4 * 256 * 8], tt[4 * 32 * 8];
   cudaMemcpyFromSymbol(tr, molann::g_fw_trace, sizeof(tr));
+  cudaMemcpyFromSymbol(tt, molann::g_fw_tiles, sizeof(tt));
+  {
+    auto Q = [&](int role, int i, int ev) { return tt[(role * 32 + i) * 8 + ev]; };
+    const long long q0 = Q(0, 0, 0);
+    printf("per tile (CTA 0), cycles; waits are per-tile deltas of cumulative counters\n");
+    for (int i = 0; i + 1 < reps && i < 31; ++i) {
+      printf("tile %2d geo   @%9lld period %7lld | wait slot %7lld frame %7lld group-barrier %7lld\n", i, Q(0, i, 0) - q0,
+             Q(0, i + 1, 0) - Q(0, i, 0), Q(0, i + 1, 1) - Q(0, i, 1), Q(0, i + 1, 2) - Q(0, i, 2), Q(0, i + 1, 3) - Q(0, i, 3));
+      printf("        conv  @%9lld period %7lld | s_full %7lld prefetch+rotation %7lld turn %7lld chunks %7lld (of which wait empty %7lld)\n",
+             Q(1, i, 0) - q0, Q(1, i + 1, 0) - Q(1, i, 0), Q(1, i, 1) - Q(1, i, 0), Q(1, i, 2) - Q(1, i, 1),
+             Q(1, i, 3) - Q(1, i, 2), Q(1, i, 4) - Q(1, i, 3), Q(1, i, 5));
+      printf("        mma   @%9lld period %7lld | layer-1 %7lld | wait a_full %7lld b_full %7lld d_free %7lld\n", Q(3, i, 0) - q0,
+             Q(3, i + 1, 0) - Q(3, i, 0), Q(3, i, 4) - Q(3, i, 0), Q(3, i + 1, 1) - Q(3, i, 1), Q(3, i + 1, 2) - Q(3, i, 2),
+             Q(3, i + 1, 3) - Q(3, i, 3));
+      printf("        epi   @%9lld period %7lld | layer-1 sums %7lld h1 chunks + wait l2_full %7lld rest %7lld\n", Q(2, i, 0) - q0,
+             Q(2, i + 1, 0) - Q(2, i, 0), Q(2, i, 1) - Q(2, i, 0), Q(2, i, 3) - Q(2, i, 1), Q(2, i, 4) - Q(2, i, 3));
+    }
+  }
   auto T = [&](int role, int i, int ev) { return tr[(role * 256 + i) * 8 + ev]; };
   const long long t00 = T(0, 0, 0);
   printf("geometry warp 0 (frames it owns; cycles): wait slot | wait frame | moment loop | staging free + reduce | positions | "
          "invariants | fence | store + arrive | total\n");
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < 232; i += (i == 23 ? 177 : 1))
     printf("g %3d @%8lld: slot+%lld frame+%lld mom+%lld red+%lld pos+%lld inv+%lld fence+%lld out+%lld | %lld\n", i,
            T(0, i, 0) - t00, T(0, i, 1) - T(0, i, 0), T(0, i, 2) - T(0, i, 1), T(0, i, 3) - T(0, i, 2),
            T(0, i, 4) - T(0, i, 3), T(0, i, 5) - T(0, i, 4), T(0, i, 6) - T(0, i, 5), T(0, i, 7) - T(0, i, 6),

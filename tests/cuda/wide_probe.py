@@ -38,12 +38,10 @@ def run(name, env):
 
 
 if __name__ == "__main__":
-    names = sys.argv[1:] or ["C3", "C5"]
+    names = [a for a in sys.argv[1:] if not a.startswith("-")] or ["C3", "C5"]
     for name in names:
         run(name, {"MOLANN_B200_WIDE": "0"})
         run(name, {})
-        for slots in ("5", "8"):
-            run(name, {"MOLANN_B200_WIDE_SLOTS": slots})
-        for ring in ("2", "3"):
-            run(name, {"MOLANN_B200_WIDE_RING": ring})
-        run(name, {"MOLANN_B200_WIDE_STAGES": "3", "MOLANN_B200_WIDE_RING": "2"})
+        for env in ({"MOLANN_B200_WIDE_CDEPTH": "3"}, {"MOLANN_B200_WIDE_SLOTS": "5"}, {"MOLANN_B200_WIDE_SLOTS": "8"},
+                    {"MOLANN_B200_WIDE_RING": "3"}):
+            run(name, env)
