@@ -68,9 +68,10 @@ namespace molann {
 
 constexpr int FW_M = 128;                 // frames per tile (tcgen05 M)
 constexpr int FW_SUB = 32;                // frames per scratch sub-tile = rows of one converter warp
-constexpr int FW_KU = 4;                  // 16-byte units per K-chunk
-constexpr int FW_KC = 4 * FW_KU;          // K per chunk
-constexpr int FW_SEGC = 2;                // chunks per accumulation segment (32 K = 12 MMA steps)
+// K-chunk size: template parameter KU of the kernel = 16-byte units per chunk (4: K = 16 per operand stage, the
+// default; 2: K = 8, half-size stages for frames so large -- C5: 60 KB -- that two of them and two full stages do not
+// fit in shared memory).  An accumulation segment is always 32 K = 12 MMA steps.
+__host__ __device__ constexpr int fw_kc(int ku) { return 4 * ku; }
 constexpr int FW_NMAX = 256;              // widest tensor-core layer
 constexpr int FW_CW = 64;                 // accumulator columns per epilogue thread
 constexpr int FW_WARPS = 32;
@@ -78,7 +79,7 @@ constexpr int FW_THREADS = FW_WARPS * 32;
 constexpr int FW_W_EPI = 4, FW_W_WPROD = 20, FW_W_MMA = 21, FW_W_XPROD = 22, FW_W_GEO = 24;   // X producer: warps 22, 23
 constexpr int FW_GEO_WARPS = 8;           // geometry warps: FW_NGG groups (alternate frames) of FW_NGW warps (one frame)
 constexpr int FW_NGG = 2, FW_NGW = FW_GEO_WARPS / FW_NGG;
-constexpr int FW_CONV_CHUNK = FW_M * FW_KC * 4;   // converter staging: one raw K-chunk of the tile, [unit][row][16 B]
+__host__ __device__ constexpr int fw_conv_chunk(int ku) { return FW_M * fw_kc(ku) * 4; }   // converter staging: one raw K-chunk, [unit][row][16 B]
 constexpr int FW_MAX_CDEPTH = 4;
 // setmaxnreg budgets; pool = 1024 threads x 64 registers = 65536 = 32 x (4 x 56 + 16 x 80 + 4 x 24 + 8 x 56).  The
 // geometry role bounds the kernel (tests/cuda/fw_trace.cu), so it gets two groups of spill-free warps; the MMA chain
@@ -87,14 +88,14 @@ constexpr int FW_REGS_CONV = 56, FW_REGS_EPI = 80, FW_REGS_CTRL = 24, FW_REGS_GE
 static_assert(4 * FW_REGS_CONV + 16 * FW_REGS_EPI + 4 * FW_REGS_CTRL + 8 * FW_REGS_GEO <= 32 * 64, "register pool");
 constexpr uint32_t FW_PIECE = 2048;      // bytes per bulk copy of the frame ring
 constexpr int FW_REGS_LAUNCH = 64;        // 65536 / 1024 threads: what the CTA starts with
-constexpr int FW_A_HALF = FW_M * FW_KC * 4;                               // one of hi / lo: 8 KB
-constexpr int FW_STAGE_BYTES = 2 * FW_A_HALF + 2 * FW_NMAX * FW_KC * 4;   // 16 KB A + 32 KB W
+__host__ __device__ constexpr int fw_a_half(int ku) { return FW_M * fw_kc(ku) * 4; }           // one of hi / lo: 8 KB (KU = 4)
+__host__ __device__ constexpr int fw_stage_bytes(int ku) { return 2 * fw_a_half(ku) + 2 * FW_NMAX * fw_kc(ku) * 4; }   // 16 KB A + 32 KB W
 constexpr int FW_MAX_STAGES = 4, FW_MAX_RING = 8, FW_MAX_SLOTS = 8;
 // per scratch row: one 12-float moment partial (H[9], sum d[3]) per geometry warp of the frame's group; the converter
 // adds them in a fixed order
 constexpr int FW_HDR_FLOATS = 12 * FW_NGW;
 // a row = header + nkc1 K-chunks, rounded up to whole 128-byte L2 lines (no line is shared by two rows)
-__host__ __device__ inline int fw_row_floats(int nkc1) { return (FW_HDR_FLOATS + nkc1 * FW_KC + 31) & ~31; }
+__host__ __device__ inline int fw_row_floats(int nkc1, int ku) { return (FW_HDR_FLOATS + nkc1 * fw_kc(ku) + 31) & ~31; }
 
 // Development aid (tests/cuda/fw_trace.cu): clock64() stamps of CTA 0, one lane per role.  Compiled out of the product.
 #ifdef MOLANN_WS_TRACE
@@ -223,10 +224,11 @@ __device__ __forceinline__ void fw_stage_skip(int& s, uint32_t& par, int by, int
 }
 
 // one row's 16 values of a K-chunk -> TF32 hi / lo -> canonical K-major operand tile (unit j at j * 2048 + row * 16)
-__device__ __forceinline__ void fw_store_units(unsigned char* a_hi, int row, const float4 (&v)[FW_KU]) {
-  unsigned char* a_lo = a_hi + FW_A_HALF;
+template <int KU>
+__device__ __forceinline__ void fw_store_units(unsigned char* a_hi, int row, const float4 (&v)[KU]) {
+  unsigned char* a_lo = a_hi + fw_a_half(KU);
 #pragma unroll
-  for (int j = 0; j < FW_KU; ++j) {
+  for (int j = 0; j < KU; ++j) {
     uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
     split_tf32_rn(v[j].x, h0, l0);
     split_tf32_rn(v[j].y, h1, l1);
@@ -474,10 +476,12 @@ __device__ __forceinline__ void fw_geometry_role(const FwParams& P, FwBars* bars
   if (lane == 0 && prev_slot >= 0) mbar_arrive(&bars->s_full[prev_slot]);
 }
 
-template <int ACT>
+template <int ACT, int KU>
 __global__ void __launch_bounds__(FW_THREADS, 1)
 fused_wide_forward_kernel(const __grid_constant__ FwParams P, const float* __restrict__ x, float* __restrict__ y,
                           long long L) {
+  constexpr int FW_KU = KU, FW_KC = fw_kc(KU), FW_SEGC = 32 / FW_KC;      // chunks per accumulation segment
+  constexpr int FW_A_HALF = fw_a_half(KU), FW_STAGE_BYTES = fw_stage_bytes(KU), FW_CONV_CHUNK = fw_conv_chunk(KU);
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   FwBars* bars = reinterpret_cast<FwBars*>(smem);
@@ -861,7 +865,7 @@ fused_wide_forward_kernel(const __grid_constant__ FwParams P, const float* __res
           FW_WAIT_END(tw_empty);
         }
         if (warp == 0 && it == 0) FW_EVT(1, 16 + kc, 1);
-        fw_store_units(FW_STAGES + (size_t)s * FW_STAGE_BYTES, row, v);
+        fw_store_units<KU>(FW_STAGES + (size_t)s * FW_STAGE_BYTES, row, v);
         if (warp == 0 && it == 0) FW_EVT(1, 16 + kc, 2);
         fence_proxy_async_smem();
         mbar_arrive(&bars->a_full[s]);
@@ -923,7 +927,7 @@ fused_wide_forward_kernel(const __grid_constant__ FwParams P, const float* __res
             for (int jx = 0; jx < FW_KU; ++jx)
               v[jx] = make_float4(acc[FW_KC * q + 4 * jx], acc[FW_KC * q + 4 * jx + 1], acc[FW_KC * q + 4 * jx + 2],
                                   acc[FW_KC * q + 4 * jx + 3]);
-            fw_store_units(stages + (size_t)s * FW_STAGE_BYTES, row, v);
+            fw_store_units<KU>(stages + (size_t)s * FW_STAGE_BYTES, row, v);
             fence_proxy_async_smem();
             mbar_arrive(&bars->a_full[s]);
           }
@@ -1004,7 +1008,7 @@ fused_wide_forward_kernel(const __grid_constant__ FwParams P, const float* __res
 // One-time packing (molann_b200_prepare): out[kc][hi | lo][(k / 4)][np][4] of  scale * W[n][colmap[k]]
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void fw_pack_kernel(const float* __restrict__ W, int ldw, int N, const int* __restrict__ colmap, int Kp,
-                               int np, float scale, float* __restrict__ out) {
+                               int np, float scale, float* __restrict__ out, int FW_KC) {
   const long long total = (long long)np * Kp;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {

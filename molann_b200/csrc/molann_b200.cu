@@ -565,6 +565,7 @@ struct MolannPrepared {
   // kernel-order program
   int n_pos, n_inv_ent, n_inv, n_units, n_hidden, pos_is_align;
   int nkc1, n1, n1p, nkc2, n2, n2p, nlast, nlastp, kout, kpad;
+  int ku;                    // K-chunk of the fused wide kernel in 16-byte units (fused_wide.cuh): 4, or 2 for very large frames
   // device pointers into the caller's buffer
   int* pos_atom;
   int* inv_ent;
@@ -599,6 +600,14 @@ bool wide_shape_ok(const MolannPlan* p) {
   return true;
 }
 
+// K-chunk of the fused wide kernel: 16 (KU = 4) unless three frames of the ring and two full operand stages do not fit
+// next to each other in shared memory (C5: 60 KB frames) -- then 8 (KU = 2), which halves the stages.
+int wide_ku_for(const MolannPlan* p) {
+  const int ring_slot = round_up(12 * p->n_inp + 32, 128);
+  const int budget = 227 * 1024;
+  return 2 * fw_stage_bytes(4) + 2 * fw_conv_chunk(4) + 8192 + 3 * ring_slot <= budget ? 4 : 2;
+}
+
 struct WideCounts {
   int n_pos = 0, n_inv_ent = 0, n_inv = 0, n_units = 0;
 };
@@ -607,6 +616,7 @@ int wide_units(int n_pos, int n_inv) { return n_pos + (n_inv > n_pos ? (n_inv - 
 size_t wide_prepared_bytes_for(const MolannPlan* p, int n_pos_max, int n_inv_ent_max, int n_units_max) {
   const int nl = p->n_layers;
   const int n1p = round_up(p->dims[1], 16);
+  const int FW_KU = wide_ku_for(p), FW_KC = fw_kc(FW_KU);
   const int nkc1 = (n_units_max + FW_KU - 1) / FW_KU;
   size_t b = 0;
   b += align256((size_t)n_pos_max * 4);
@@ -646,7 +656,8 @@ int wide_pack_weights(const MolannPrepared* h, const MolannPlan* p, cudaStream_t
     const long long total = (long long)h->n1p * h->kpad;
     unsigned blocks = (unsigned)((total + 255) / 256);
     if (blocks > 2048u) blocks = 2048u;
-    fw_pack_kernel<<<blocks, 256, 0, st>>>(p->W[0], p->d_feat, h->n1, h->colmap, h->kpad, h->n1p, scale, h->w1p);
+    fw_pack_kernel<<<blocks, 256, 0, st>>>(p->W[0], p->d_feat, h->n1, h->colmap, h->kpad, h->n1p, scale, h->w1p,
+                                           fw_kc(h->ku));
     int s = post_launch();
     if (s) return s;
   }
@@ -654,7 +665,7 @@ int wide_pack_weights(const MolannPrepared* h, const MolannPlan* p, cudaStream_t
     const long long total = (long long)h->n2p * h->n1p;
     unsigned blocks = (unsigned)((total + 255) / 256);
     if (blocks > 2048u) blocks = 2048u;
-    fw_pack_kernel<<<blocks, 256, 0, st>>>(p->W[1], h->n1, h->n2, nullptr, h->n1p, h->n2p, scale, h->w2p);
+    fw_pack_kernel<<<blocks, 256, 0, st>>>(p->W[1], h->n1, h->n2, nullptr, h->n1p, h->n2p, scale, h->w2p, fw_kc(h->ku));
     int s = post_launch();
     if (s) return s;
   }
@@ -701,9 +712,12 @@ WideChoice choose_wide(const MolannPrepared* h, const MolannPlan* p, long long L
   P.n_hidden = h->n_hidden; P.nkc1 = h->nkc1; P.n1p = h->n1p; P.nkc2 = h->nkc2; P.n2p = h->n2p;
   P.nlastp = h->nlastp; P.kout = h->kout;
   P.w1p = h->w1p; P.w2p = h->w2p; P.b1s = h->b1s; P.b2s = h->b2s; P.w3 = h->w3; P.b3 = h->b3;
-  P.row_floats = fw_row_floats(h->nkc1);
+  P.row_floats = fw_row_floats(h->nkc1, h->ku);
   P.slot_floats = FW_SUB * P.row_floats;
-  int slots = env_int("MOLANN_B200_WIDE_SLOTS", 6);
+  // six sub-tiles per CTA keep the scratch inside L2 for C3-class rows (3.4 KB: 96 MB for the chip); rows that cannot stay
+  // resident anyway (C5: 8.2 KB) take all eight so the geometry role runs further ahead of the converter (48 -> 51 M frames/s)
+  const long long six_slots_bytes = 6LL * P.slot_floats * 4 * dev.sm_count;
+  int slots = env_int("MOLANN_B200_WIDE_SLOTS", six_slots_bytes > (110LL << 20) ? 8 : 6);
   if (slots < 5) slots = 5;                       // a tile (4 sub-tiles) + at least one the geometry can run ahead in
   if (slots > FW_MAX_SLOTS) slots = FW_MAX_SLOTS;
   P.n_slots = slots;
@@ -720,7 +734,7 @@ WideChoice choose_wide(const MolannPrepared* h, const MolannPlan* p, long long L
   if (depth < 2) depth = 2;
   if (depth > FW_MAX_CDEPTH) depth = FW_MAX_CDEPTH;
   P.conv_depth = depth;
-  P.off_cstage = c.take(depth * FW_CONV_CHUNK, 128);
+  P.off_cstage = c.take(depth * fw_conv_chunk(h->ku), 128);
   const int fixed = c.off;
   // operand stages and the frame ring share what is left; plan tables move in when there is room
   int stages = env_int("MOLANN_B200_WIDE_STAGES", 2);
@@ -729,6 +743,7 @@ WideChoice choose_wide(const MolannPrepared* h, const MolannPlan* p, long long L
   int ring = env_int("MOLANN_B200_WIDE_RING", 4);
   if (ring > FW_MAX_RING) ring = FW_MAX_RING;
   const int budget = dev.max_smem_optin;
+  const int FW_STAGE_BYTES = fw_stage_bytes(h->ku);
   auto need = [&](int st, int rg) { return round_up(fixed, 1024) + st * FW_STAGE_BYTES + rg * P.ring_slot_bytes; };
   while (ring > 2 && need(stages, ring) > budget) --ring;
   while (stages > 2 && need(stages, ring) > budget) --stages;
@@ -755,9 +770,9 @@ WideChoice choose_wide(const MolannPrepared* h, const MolannPlan* p, long long L
   return ch;
 }
 
-template <int ACT>
+template <int ACT, int KU>
 int launch_wide_act(const WideChoice& ch, const float* x, float* y, long long L, cudaStream_t st) {
-  auto kern = fused_wide_forward_kernel<ACT>;
+  auto kern = fused_wide_forward_kernel<ACT, KU>;
   int s = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ch.P.total_smem));
   if (s) return s;
   FwParams P = ch.P;
@@ -1480,6 +1495,8 @@ int molann_b200_prepare(const MolannPlan* plan, void* device_buffer, size_t byte
     for (int u = 0; u < h->n_pos; ++u)
       if (al[u] != pos_atom[u]) { h->pos_is_align = 0; break; }
   }
+  h->ku = wide_ku_for(plan);
+  const int FW_KU = h->ku, FW_KC = fw_kc(h->ku);
   h->nkc1 = (h->n_units + FW_KU - 1) / FW_KU;
   if (h->nkc1 < 1) h->nkc1 = 1;
   h->kpad = h->nkc1 * FW_KC;
@@ -1544,7 +1561,7 @@ size_t molann_b200_prepared_workspace_bytes(const MolannPrepared* prepared, int6
   if (!dev.ok) dev.sm_count = 148;
   const long long ntiles = (L + FW_M - 1) / FW_M;
   const long long grid = dev.sm_count < ntiles ? dev.sm_count : ntiles;
-  const long long slot_floats = (long long)FW_SUB * fw_row_floats(prepared->nkc1);
+  const long long slot_floats = (long long)FW_SUB * fw_row_floats(prepared->nkc1, prepared->ku);
   const size_t wide = (size_t)grid * FW_MAX_SLOTS * slot_floats * 4 + 128;    // + alignment of the rows to L2 lines
   // the layered kernels (value-and-gradient; forward when the wide kernel does not fit) share the same workspace
   MolannPlan shape;
@@ -1576,10 +1593,13 @@ int molann_b200_forward_prepared(const MolannPrepared* prepared, const MolannPla
   ch.P.scratch = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 127u) & ~(uintptr_t)127u);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (plan->act_id) {
-    case MOLANN_ACT_TANH: return launch_wide_act<ACT_TANH>(ch, x, y, (long long)L, st);
-    case MOLANN_ACT_RELU: return launch_wide_act<ACT_RELU>(ch, x, y, (long long)L, st);
-    case MOLANN_ACT_SIGMOID: return launch_wide_act<ACT_SIGMOID>(ch, x, y, (long long)L, st);
-    default: return launch_wide_act<ACT_IDENTITY>(ch, x, y, (long long)L, st);
+#define WIDE_LAUNCH(A) \
+  (prepared->ku == 4 ? launch_wide_act<A, 4>(ch, x, y, (long long)L, st) : launch_wide_act<A, 2>(ch, x, y, (long long)L, st))
+    case MOLANN_ACT_TANH: return WIDE_LAUNCH(ACT_TANH);
+    case MOLANN_ACT_RELU: return WIDE_LAUNCH(ACT_RELU);
+    case MOLANN_ACT_SIGMOID: return WIDE_LAUNCH(ACT_SIGMOID);
+    default: return WIDE_LAUNCH(ACT_IDENTITY);
+#undef WIDE_LAUNCH
   }
 }
 
