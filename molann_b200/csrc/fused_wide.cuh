@@ -159,6 +159,9 @@ struct FwParams {
   const float* b2s;          // [n2p]
   const float* w3;           // [kout][nlastp]
   const float* b3;           // [kout]
+  float* h1_out;             // optional [L][n1] / [L][n2]: the hidden activations, for the value-and-gradient path
+  float* h2_out;
+  int n1, n2;                // true (unpadded) widths = row strides of h1_out / h2_out
   const float* x_base;       // = x (the geometry role only needs its low address bits: where a frame sits in its ring slot)
   // transposition scratch (global memory, L2 resident): per CTA n_slots sub-tiles of slot_floats
   float* scratch;
@@ -909,6 +912,18 @@ fused_wide_forward_kernel(const __grid_constant__ FwParams P, const float* __res
 #pragma unroll
       for (int c = 0; c < FW_CW; ++c)
         if (col0 + c < P.n1p) acc[c] = fw_act<ACT>(acc[c] + b1[col0 + c]);
+      if (P.h1_out != nullptr && (long long)tile * FW_M + row < L) {       // value-and-gradient: keep h1 for act'
+        float* dst = P.h1_out + ((long long)tile * FW_M + row) * P.n1 + col0;
+        if ((P.n1 & 3) == 0) {
+#pragma unroll
+          for (int c = 0; c < FW_CW; c += 4)
+            if (col0 + c < P.n1) __stcg(reinterpret_cast<float4*>(dst + c), make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]));
+        } else {
+#pragma unroll
+          for (int c = 0; c < FW_CW; ++c)
+            if (col0 + c < P.n1) __stcg(dst + c, acc[c]);
+        }
+      }
       int nlast = P.n1p, lcol0 = col0, lcw = FW_CW;      // columns of the last hidden layer this thread holds
       if (P.n_hidden == 2) {
         // h1 goes back into the operand ring as layer 2's A chunks, warpgroup after warpgroup (chunk order)
@@ -967,6 +982,19 @@ fused_wide_forward_kernel(const __grid_constant__ FwParams P, const float* __res
 #pragma unroll
         for (int c = 0; c < FW_CW; ++c)
           if (c < cw2 && lcol0 + c < P.n2p) acc[c] = fw_act<ACT>(acc[c] + b2[lcol0 + c]);
+        if (P.h2_out != nullptr && (long long)tile * FW_M + row < L) {
+          float* dst = P.h2_out + ((long long)tile * FW_M + row) * P.n2 + lcol0;
+          if ((P.n2 & 3) == 0) {
+#pragma unroll
+            for (int c = 0; c < FW_CW; c += 4)
+              if (c < cw2 && lcol0 + c < P.n2)
+                __stcg(reinterpret_cast<float4*>(dst + c), make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]));
+          } else {
+#pragma unroll
+            for (int c = 0; c < FW_CW; ++c)
+              if (c < cw2 && lcol0 + c < P.n2) __stcg(dst + c, acc[c]);
+          }
+        }
         nlast = P.n2p;
       }
       // last (narrow) layer: partial dot products over this thread's columns, summed in a fixed order

@@ -711,6 +711,7 @@ WideChoice choose_wide(const MolannPrepared* h, const MolannPlan* p, long long L
   P.n_units = h->n_units; P.use_angle = p->use_angle_value; P.pos_is_align = h->pos_is_align;
   P.n_hidden = h->n_hidden; P.nkc1 = h->nkc1; P.n1p = h->n1p; P.nkc2 = h->nkc2; P.n2p = h->n2p;
   P.nlastp = h->nlastp; P.kout = h->kout;
+  P.n1 = h->n1; P.n2 = h->n2;
   P.w1p = h->w1p; P.w2p = h->w2p; P.b1s = h->b1s; P.b2s = h->b2s; P.w3 = h->w3; P.b3 = h->b3;
   P.row_floats = fw_row_floats(h->nkc1, h->ku);
   P.slot_floats = FW_SUB * P.row_floats;
@@ -771,14 +772,30 @@ WideChoice choose_wide(const MolannPrepared* h, const MolannPlan* p, long long L
 }
 
 template <int ACT, int KU>
-int launch_wide_act(const WideChoice& ch, const float* x, float* y, long long L, cudaStream_t st) {
+int launch_wide_act(const WideChoice& ch, const float* x, float* y, long long L, cudaStream_t st, float* h1 = nullptr,
+                    float* h2 = nullptr) {
   auto kern = fused_wide_forward_kernel<ACT, KU>;
   int s = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ch.P.total_smem));
   if (s) return s;
   FwParams P = ch.P;
   P.x_base = x;
+  P.h1_out = h1;
+  P.h2_out = h2;
   kern<<<(unsigned)ch.grid, FW_THREADS, P.total_smem, st>>>(P, x, y, L);
   return post_launch();
+}
+
+int launch_wide(const WideChoice& ch, int ku, int act_id, const float* x, float* y, long long L, cudaStream_t st,
+                float* h1, float* h2) {
+#define WIDE_LAUNCH(A) \
+  (ku == 4 ? launch_wide_act<A, 4>(ch, x, y, L, st, h1, h2) : launch_wide_act<A, 2>(ch, x, y, L, st, h1, h2))
+  switch (act_id) {
+    case MOLANN_ACT_TANH: return WIDE_LAUNCH(ACT_TANH);
+    case MOLANN_ACT_RELU: return WIDE_LAUNCH(ACT_RELU);
+    case MOLANN_ACT_SIGMOID: return WIDE_LAUNCH(ACT_SIGMOID);
+    default: return WIDE_LAUNCH(ACT_IDENTITY);
+  }
+#undef WIDE_LAUNCH
 }
 
 // Jacobian mode of the same kernel (one tile per CTA: five 64-column TMEM blocks per tile)
@@ -1555,6 +1572,84 @@ int molann_b200_prepared_refresh(MolannPrepared* prepared, const MolannPlan* pla
   return wide_pack_weights(prepared, plan, static_cast<cudaStream_t>(stream));
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// value-and-gradient of a prepared wide plan: forward = the fused wide kernel, which also leaves the hidden
+// activations behind (1.5 KB per C3 frame); backward = the layered contractions on the packed operands + the block
+// preprocess backward.  The layered route (general_backward) recomputed the forward with four more launches per chunk
+// and wrote / re-read the [L, d] feature matrix.  Chunks are whole waves of 148 x 128 frames, as many as ~2 GB of
+// workspace hold: the fused kernel wants several tiles per CTA (pipeline fill = one tile).
+// ---------------------------------------------------------------------------------------------------------------
+long long wide_vg_chunk(const MolannPrepared* h, long long L, int sm_count) {
+  long long md = h->d_feat;
+  for (int k = 0; k <= h->n_layers; ++k) md = h->dims[k] > md ? h->dims[k] : md;
+  const long long per_frame = 4LL * (h->n1 + h->n2 + 2 * md);
+  const long long wave = (long long)sm_count * FW_M;
+  long long ch = (2LL << 30) / per_frame / wave * wave;
+  if (ch < wave) ch = wave;
+  ch = env_int("MOLANN_B200_WIDE_VG_CHUNK", (int)ch);
+  if (ch < FW_M) ch = FW_M;
+  return L < ch ? L : ch;
+}
+size_t wide_vg_ws_bytes(const MolannPrepared* h, long long L, int sm_count) {
+  const long long ch = wide_vg_chunk(h, L, sm_count);
+  long long md = h->d_feat;
+  for (int k = 0; k <= h->n_layers; ++k) md = h->dims[k] > md ? h->dims[k] : md;
+  const long long ntiles = (ch + FW_M - 1) / FW_M;
+  const long long grid = sm_count < ntiles ? sm_count : ntiles;
+  const long long slot_floats = (long long)FW_SUB * fw_row_floats(h->nkc1, h->ku);
+  size_t b = align256((size_t)grid * FW_MAX_SLOTS * slot_floats * 4 + 128);
+  b += align256((size_t)ch * h->n1 * 4) + align256((size_t)ch * (h->n2 > 0 ? h->n2 : 1) * 4);
+  b += 2 * align256((size_t)ch * md * 4);
+  return b;
+}
+int wide_value_and_grad(const MolannPrepared* h, const MolannPlan* p, const float* x, const float* gy, long long L,
+                        float* y, float* gx, void* ws, size_t ws_bytes, const DeviceInfo& dev, cudaStream_t st) {
+  if (!ws || ws_bytes < wide_vg_ws_bytes(h, L, dev.sm_count) || (reinterpret_cast<uintptr_t>(ws) & 15u))
+    return MOLANN_ERR_WORKSPACE;
+  const DevPlan dp = to_dev(p);
+  const long long ch = wide_vg_chunk(h, L, dev.sm_count);
+  const int nl = p->n_layers, kout = p->dims[nl];
+  long long md = p->d_feat;
+  for (int k = 0; k <= nl; ++k) md = p->dims[k] > md ? p->dims[k] : md;
+  char* base = static_cast<char*>(ws);
+  {
+    const long long ntiles = (ch + FW_M - 1) / FW_M;
+    const long long grid = dev.sm_count < ntiles ? dev.sm_count : ntiles;
+    const long long slot_floats = (long long)FW_SUB * fw_row_floats(h->nkc1, h->ku);
+    base += align256((size_t)grid * FW_MAX_SLOTS * slot_floats * 4 + 128);
+  }
+  float* hact[MOLANN_MAX_LAYERS] = {nullptr};          // hact[k] = activation after layer k (k = 1 .. nl - 1)
+  hact[1] = reinterpret_cast<float*>(base);
+  base += align256((size_t)ch * h->n1 * 4);
+  float* h2buf = reinterpret_cast<float*>(base);
+  base += align256((size_t)ch * (h->n2 > 0 ? h->n2 : 1) * 4);
+  if (nl == 3) hact[2] = h2buf;
+  float* pp[2];
+  pp[0] = reinterpret_cast<float*>(base);
+  base += align256((size_t)ch * md * 4);
+  pp[1] = reinterpret_cast<float*>(base);
+  for (long long c0 = 0; c0 < L; c0 += ch) {
+    const long long Lc = (L - c0 < ch) ? (L - c0) : ch;
+    const float* xc = x + c0 * 3 * p->n_inp;
+    WideChoice wc = choose_wide(h, p, Lc, dev);
+    if (!wc.ok) return MOLANN_ERR_PLAN;
+    wc.P.scratch = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 127u) & ~(uintptr_t)127u);
+    int s = launch_wide(wc, h->ku, p->act_id, xc, y + c0 * kout, Lc, st, hact[1], nl == 3 ? hact[2] : nullptr);
+    if (s) return s;
+    const float* gz = gy + c0 * kout;
+    for (int k = nl - 1; k >= 0; --k) {
+      float* gprev = pp[k & 1];
+      s = launch_linear_backward_input(gz, p->W[k], k > 0 ? hact[k] : nullptr, gprev, Lc, p->dims[k], p->dims[k + 1],
+                                       p->act_id, st, h->gt_bwd[k], &dev, h->gt_bwd[k]);   // (pack != NULL selects the tensor-core GEMM; nothing is packed here)
+      if (s) return s;
+      gz = gprev;
+    }
+    s = launch_preprocess_backward(p, dp, xc, gz, gx + c0 * 3 * p->n_inp, Lc, dev, st);
+    if (s) return s;
+  }
+  return MOLANN_OK;
+}
+
 size_t molann_b200_prepared_workspace_bytes(const MolannPrepared* prepared, int64_t L) {
   if (!prepared || prepared->magic != kPreparedMagic || L <= 0) return 0;
   DeviceInfo dev = device_info();
@@ -1570,7 +1665,9 @@ size_t molann_b200_prepared_workspace_bytes(const MolannPrepared* prepared, int6
   shape.n_layers = prepared->n_layers;
   for (int k = 0; k <= prepared->n_layers; ++k) shape.dims[k] = prepared->dims[k];
   const size_t layered = general_ws_bytes(&shape, L, true);
-  return wide > layered ? wide : layered;
+  const size_t vg = wide_vg_ws_bytes(prepared, L, dev.sm_count);
+  size_t m = wide > layered ? wide : layered;
+  return m > vg ? m : vg;
 }
 
 int molann_b200_forward_prepared(const MolannPrepared* prepared, const MolannPlan* plan, const float* x, int64_t L,
@@ -1592,15 +1689,7 @@ int molann_b200_forward_prepared(const MolannPrepared* prepared, const MolannPla
   // rows start on 128-byte L2 lines: a converter thread discards the lines of its row once it has read them
   ch.P.scratch = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 127u) & ~(uintptr_t)127u);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  switch (plan->act_id) {
-#define WIDE_LAUNCH(A) \
-  (prepared->ku == 4 ? launch_wide_act<A, 4>(ch, x, y, (long long)L, st) : launch_wide_act<A, 2>(ch, x, y, (long long)L, st))
-    case MOLANN_ACT_TANH: return WIDE_LAUNCH(ACT_TANH);
-    case MOLANN_ACT_RELU: return WIDE_LAUNCH(ACT_RELU);
-    case MOLANN_ACT_SIGMOID: return WIDE_LAUNCH(ACT_SIGMOID);
-    default: return WIDE_LAUNCH(ACT_IDENTITY);
-#undef WIDE_LAUNCH
-  }
+  return launch_wide(ch, prepared->ku, plan->act_id, x, y, (long long)L, st, nullptr, nullptr);
 }
 
 int molann_b200_value_and_grad_prepared(const MolannPrepared* prepared, const MolannPlan* plan, const float* x,
@@ -1615,7 +1704,12 @@ int molann_b200_value_and_grad_prepared(const MolannPrepared* prepared, const Mo
   if (misaligned4(x) || misaligned4(gy) || misaligned4(y) || misaligned4(gx)) return MOLANN_ERR_ALIGNMENT;
   const DeviceInfo dev = device_info();
   if (!dev.ok) return MOLANN_ERR_CUDA;
-  // ONE pass of the layered kernels (the backward's forward recompute also writes y) on operands packed once
+  // forward on the fused wide kernel (which keeps the hidden activations), backward on the layered kernels; without
+  // the wide kernel: ONE pass of the layered kernels (the backward's forward recompute also writes y)
+  if (env_int("MOLANN_B200_WIDE", -1) != 0 && env_int("MOLANN_B200_WIDE_VG", 1) != 0 &&
+      choose_wide(prepared, plan, (long long)L, dev).ok)
+    return wide_value_and_grad(prepared, plan, x, gy, (long long)L, y, gx, workspace, workspace_bytes, dev,
+                               static_cast<cudaStream_t>(stream));
   return general_backward(plan, x, gy, L, gx, nullptr, nullptr, workspace, workspace_bytes, dev,
                           static_cast<cudaStream_t>(stream), y, prepared);
 }

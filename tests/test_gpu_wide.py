@@ -167,10 +167,9 @@ def test_wide_weight_update_repacks(monkeypatch):
 
 @pytest.mark.parametrize("name,L", [("C3", 203), ("C5", 131)])
 def test_wide_full_width_default_path(name, L):
-    """BASELINE configs[2] / [4] shapes.  C3: the fused wide kernel IS the default forward, one launch per call.  C5:
-    two 60 KB frames + the operand ring + the staging rows do not fit in 227 KB of shared memory yet,
-    `molann_b200_forward_prepared` then runs the layered kernels on the packed operands (4 launches) -- either way the
-    result must match the oracle."""
+    """BASELINE configs[2] / [4] shapes: the fused wide kernel IS the default forward, one launch per call (C5's 60 KB
+    frames take the K = 8 operand stages so that two frames fit next to them in shared memory), and the result must
+    match the oracle."""
     from molann_b200 import _lib
     spec = S.get_spec(name)
     model, _ = S.build_model(spec)
@@ -183,15 +182,20 @@ def test_wide_full_width_default_path(name, L):
         before = _lib.launch_count()
         y2 = model(dev(x))
     n_launch = _lib.launch_count() - before
-    assert n_launch == 1 if name == "C3" else n_launch in (1, 4)        # layered on packed operands: no pack launches
+    assert n_launch == 1
     assert torch.equal(y, y2)
     assert_parity(y.cpu(), y64, y32, TOL, name + " y (fused wide kernel)")
-    # the layered path (kept for the backward) must agree to rounding, and runs on the operands packed once:
-    # preprocess + 2 GEMMs + narrow (y) forward, narrow + 2 GEMMs + preprocess backward = 8 launches, no packing
+    # value-and-gradient of a prepared wide plan: the SAME fused forward kernel (it also leaves the hidden activations
+    # behind), then narrow + 2 GEMMs backward-to-input on the operands packed once + the block preprocess backward
+    # = 5 launches, no forward recompute, no packing; y is bitwise the forward's, gx matches the fp64 oracle
+    cot = torch.randn(L, 2, generator=torch.Generator().manual_seed(5))
+    y64b, gx64 = oracle_value_and_grad(oracle_model(spec, ws, bs), x, cot)
+    _, gx32 = oracle_value_and_grad(oracle_model(spec, ws, bs, torch.float32), x, cot, torch.float32)
     before = _lib.launch_count()
-    yl, _ = model.value_and_grad(dev(x), torch.ones(L, 2, device="cuda"))
-    assert _lib.launch_count() - before == 8
-    assert float((yl - y).abs().max()) < 2e-5 * max(1.0, float(y.abs().max()))
+    yl, gx = model.value_and_grad(dev(x), cot.cuda())
+    assert _lib.launch_count() - before == 5
+    assert torch.equal(yl, y)
+    assert_parity(gx.cpu(), gx64, gx32, TOL, name + " gx (fused forward + layered backward)")
 
 
 @pytest.mark.parametrize("name", ["C3", "C5"])
