@@ -90,6 +90,9 @@ struct WsLayout {
   int total_bytes;
 };
 
+#ifndef MOLANN_WAIT_NS
+#define MOLANN_WAIT_NS 64     // back-off between two polls of an mbarrier (A/B switch of tests/cuda/ws_trace.cu)
+#endif
 __device__ __forceinline__ void mbar_arrive(void* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -102,12 +105,12 @@ __device__ __forceinline__ void mbar_wait_hint(void* bar, uint32_t parity) {
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
       "@p bra WS_DONE_%=;\n\t"
       "WS_WAIT_%=:\n\t"
-      "nanosleep.u32 64;\n\t"             // retries were a third of all issued instructions (profiles/r1_f)
+      "nanosleep.u32 %3;\n\t"             // retries were a third of all issued instructions (profiles/r1_f)
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
       "@!p bra WS_WAIT_%=;\n\t"
       "WS_DONE_%=:\n\t"
       "}" ::"r"(smem_u32(bar)),
-      "r"(parity), "r"(0x989680u)
+      "r"(parity), "r"(0x989680u), "n"(MOLANN_WAIT_NS)
       : "memory");
 }
 
