@@ -63,6 +63,16 @@
 #ifndef FW_OPT_LATE
 #define FW_OPT_LATE 1        // release the frame's ring slot before the dihedral arithmetic
 #endif
+#ifndef FW_SEG_K
+#define FW_SEG_K 64          // K per accumulation segment of layer 1 (64 K = 24 MMA steps into a fresh accumulator, the
+                             // same count as a layer-2 accumulator; 32 -> 64: +2 %, y error unchanged at 1e-6)
+#endif
+#ifndef FW_OPT_LD2
+#define FW_OPT_LD2 0         // segment drain: two TMEM loads per wait
+#endif
+#ifndef FW_OPT_ACC2
+#define FW_OPT_ACC2 0        // segment drain: packed f32x2 adds
+#endif
 
 namespace molann {
 
@@ -253,6 +263,27 @@ __device__ __forceinline__ void fw_sum_segments(float (&acc)[FW_CW], int nseg, i
     mbar_wait_hint(&bars->d_full[db], (sg >> 1) & 1u);
     tc_fence_after_sync();
     if (trace) FW_EVT(2, 16 + q, 1);
+#if FW_OPT_LD2
+#pragma unroll
+    for (int c = 0; c < FW_CW; c += 16) {
+      if (col0 + c < np) {
+        uint32_t u[8], v[8];
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
+                     : "r"(lane_base + (uint32_t)db * FW_NMAX + (uint32_t)(col0 + c))
+                     : "memory");
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                     : "r"(lane_base + (uint32_t)db * FW_NMAX + (uint32_t)(col0 + c + 8))
+                     : "memory");
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[c + i] += __uint_as_float(u[i]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[c + 8 + i] += __uint_as_float(v[i]);
+      }
+    }
+#else
 #pragma unroll
     for (int c = 0; c < FW_CW; c += 8) {
       if (col0 + c < np) {
@@ -262,10 +293,20 @@ __device__ __forceinline__ void fw_sum_segments(float (&acc)[FW_CW], int nseg, i
                      : "r"(lane_base + (uint32_t)db * FW_NMAX + (uint32_t)(col0 + c))
                      : "memory");
         tmem_wait_ld();
+#if FW_OPT_ACC2
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {
+          const unsigned long long r2 = f2_add(f2_pack(acc[c + i], acc[c + i + 1]),
+                                               f2_pack(__uint_as_float(u[i]), __uint_as_float(u[i + 1])));
+          f2_unpack(r2, acc[c + i], acc[c + i + 1]);
+        }
+#else
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[c + i] += __uint_as_float(u[i]);
+#endif
       }
     }
+#endif
     tc_fence_before_sync();
     mbar_arrive(&bars->d_free[db]);
     if (trace) FW_EVT(2, 16 + q, 2);
@@ -479,11 +520,13 @@ __device__ __forceinline__ void fw_geometry_role(const FwParams& P, FwBars* bars
   if (lane == 0 && prev_slot >= 0) mbar_arrive(&bars->s_full[prev_slot]);
 }
 
-template <int ACT, int KU>
+// STORE_H: also leave the hidden activations behind (value-and-gradient path).  A template parameter, not a run-time
+// test: the unused store code alone cost the plain forward 5 % (the kernel is sensitive to its instruction footprint).
+template <int ACT, int KU, bool STORE_H = false>
 __global__ void __launch_bounds__(FW_THREADS, 1)
 fused_wide_forward_kernel(const __grid_constant__ FwParams P, const float* __restrict__ x, float* __restrict__ y,
                           long long L) {
-  constexpr int FW_KU = KU, FW_KC = fw_kc(KU), FW_SEGC = 32 / FW_KC;      // chunks per accumulation segment
+  constexpr int FW_KU = KU, FW_KC = fw_kc(KU), FW_SEGC = FW_SEG_K / FW_KC;      // chunks per accumulation segment
   constexpr int FW_A_HALF = fw_a_half(KU), FW_STAGE_BYTES = fw_stage_bytes(KU), FW_CONV_CHUNK = fw_conv_chunk(KU);
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -912,7 +955,7 @@ fused_wide_forward_kernel(const __grid_constant__ FwParams P, const float* __res
 #pragma unroll
       for (int c = 0; c < FW_CW; ++c)
         if (col0 + c < P.n1p) acc[c] = fw_act<ACT>(acc[c] + b1[col0 + c]);
-      if (P.h1_out != nullptr && (long long)tile * FW_M + row < L) {       // value-and-gradient: keep h1 for act'
+      if (STORE_H && P.h1_out != nullptr && (long long)tile * FW_M + row < L) {       // value-and-gradient: keep h1 for act'
         float* dst = P.h1_out + ((long long)tile * FW_M + row) * P.n1 + col0;
         if ((P.n1 & 3) == 0) {
 #pragma unroll
@@ -982,7 +1025,7 @@ fused_wide_forward_kernel(const __grid_constant__ FwParams P, const float* __res
 #pragma unroll
         for (int c = 0; c < FW_CW; ++c)
           if (c < cw2 && lcol0 + c < P.n2p) acc[c] = fw_act<ACT>(acc[c] + b2[lcol0 + c]);
-        if (P.h2_out != nullptr && (long long)tile * FW_M + row < L) {
+        if (STORE_H && P.h2_out != nullptr && (long long)tile * FW_M + row < L) {
           float* dst = P.h2_out + ((long long)tile * FW_M + row) * P.n2 + lcol0;
           if ((P.n2 & 3) == 0) {
 #pragma unroll

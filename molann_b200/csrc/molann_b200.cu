@@ -771,10 +771,9 @@ WideChoice choose_wide(const MolannPrepared* h, const MolannPlan* p, long long L
   return ch;
 }
 
-template <int ACT, int KU>
-int launch_wide_act(const WideChoice& ch, const float* x, float* y, long long L, cudaStream_t st, float* h1 = nullptr,
-                    float* h2 = nullptr) {
-  auto kern = fused_wide_forward_kernel<ACT, KU>;
+template <int ACT, int KU, bool STORE_H>
+int launch_wide_act(const WideChoice& ch, const float* x, float* y, long long L, cudaStream_t st, float* h1, float* h2) {
+  auto kern = fused_wide_forward_kernel<ACT, KU, STORE_H>;
   int s = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ch.P.total_smem));
   if (s) return s;
   FwParams P = ch.P;
@@ -785,10 +784,20 @@ int launch_wide_act(const WideChoice& ch, const float* x, float* y, long long L,
   return post_launch();
 }
 
+// The activation-storing variant exists for tanh only (the reference's default and every BASELINE config); the
+// value-and-gradient of other activations takes the layered route.
+bool wide_can_store_h(int act_id) { return act_id == MOLANN_ACT_TANH; }
+
 int launch_wide(const WideChoice& ch, int ku, int act_id, const float* x, float* y, long long L, cudaStream_t st,
                 float* h1, float* h2) {
+  if (h1 != nullptr) {
+    if (!wide_can_store_h(act_id)) return MOLANN_ERR_PLAN;
+    return ku == 4 ? launch_wide_act<ACT_TANH, 4, true>(ch, x, y, L, st, h1, h2)
+                   : launch_wide_act<ACT_TANH, 2, true>(ch, x, y, L, st, h1, h2);
+  }
 #define WIDE_LAUNCH(A) \
-  (ku == 4 ? launch_wide_act<A, 4>(ch, x, y, L, st, h1, h2) : launch_wide_act<A, 2>(ch, x, y, L, st, h1, h2))
+  (ku == 4 ? launch_wide_act<A, 4, false>(ch, x, y, L, st, nullptr, nullptr) \
+           : launch_wide_act<A, 2, false>(ch, x, y, L, st, nullptr, nullptr))
   switch (act_id) {
     case MOLANN_ACT_TANH: return WIDE_LAUNCH(ACT_TANH);
     case MOLANN_ACT_RELU: return WIDE_LAUNCH(ACT_RELU);
@@ -1706,7 +1715,7 @@ int molann_b200_value_and_grad_prepared(const MolannPrepared* prepared, const Mo
   if (!dev.ok) return MOLANN_ERR_CUDA;
   // forward on the fused wide kernel (which keeps the hidden activations), backward on the layered kernels; without
   // the wide kernel: ONE pass of the layered kernels (the backward's forward recompute also writes y)
-  if (env_int("MOLANN_B200_WIDE", -1) != 0 && env_int("MOLANN_B200_WIDE_VG", 1) != 0 &&
+  if (env_int("MOLANN_B200_WIDE", -1) != 0 && env_int("MOLANN_B200_WIDE_VG", 1) != 0 && wide_can_store_h(plan->act_id) &&
       choose_wide(prepared, plan, (long long)L, dev).ok)
     return wide_value_and_grad(prepared, plan, x, gy, (long long)L, y, gx, workspace, workspace_bytes, dev,
                                static_cast<cudaStream_t>(stream));

