@@ -603,6 +603,8 @@ bool wide_shape_ok(const MolannPlan* p) {
 // K-chunk of the fused wide kernel: 16 (KU = 4) unless three frames of the ring and two full operand stages do not fit
 // next to each other in shared memory (C5: 60 KB frames) -- then 8 (KU = 2), which halves the stages.
 int wide_ku_for(const MolannPlan* p) {
+  const int forced = env_int("MOLANN_B200_WIDE_KU", 0);          // tests: both chunk sizes over the same goldens
+  if (forced == 2 || forced == 4) return forced;
   const int ring_slot = round_up(12 * p->n_inp + 32, 128);
   const int budget = 227 * 1024;
   return 2 * fw_stage_bytes(4) + 2 * fw_conv_chunk(4) + 8192 + 3 * ring_slot <= budget ? 4 : 2;
