@@ -428,7 +428,11 @@ __device__ __forceinline__ void fw_geometry_role(const FwParams& P, FwBars* bars
 #pragma unroll
         for (int i = 0; i < 12; ++i) m[i] = 0.f;
 #pragma unroll 1
+#ifdef FW_DBG_SKIP_MOM
+        for (int k = gt; k < 32; k += gstride) {
+#else
         for (int k = gt; k < P.n_align; k += gstride) {
+#endif
           const float* p = xf + 3 * fw_tab_i<TS>(smem, P.off_aidx, P.align_idx, k);
           const float px = p[0] - pvx, py = p[1] - pvy, pz = p[2] - pvz;
           const float y0 = fw_tab_f<TS>(smem, P.off_ref, P.ref_x, 3 * k), y1 = fw_tab_f<TS>(smem, P.off_ref, P.ref_x, 3 * k + 1),
@@ -500,7 +504,11 @@ __device__ __forceinline__ void fw_geometry_role(const FwParams& P, FwBars* bars
         // the release does not stall
         if (prev_slot >= 0) mbar_arrive(&bars->s_full[prev_slot]);
       }
+#ifdef FW_DBG_SKIP_DIH
+      if (late_dihedral) { out(d_off, d0.x); out(d_off + 1, d3.y); }
+#else
       if (late_dihedral) fw_dihedral_cos_sin(d0, d1, d2, d3, d_off, out);
+#endif
       if (gt == 0 && P.n_inv > P.n_pos) {           // zero the unused tail of the last invariant unit
         for (int v = P.n_inv; ((v - P.n_pos) & 3) != 0; ++v) out(v, 0.f);
       }
@@ -632,7 +640,11 @@ fused_wide_forward_kernel(const __grid_constant__ FwParams P, const float* __res
 #pragma unroll 1
       for (int r = 0; r < nf; ++r, src += fbytes) {
         const uint32_t off = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15u);
+#ifdef FW_DBG_HALF_X
+        const uint32_t bytes = ((fbytes / 2) + off + 15u) & ~15u;
+#else
         const uint32_t bytes = (fbytes + off + 15u) & ~15u;
+#endif
         const uint32_t d0 = smem_u32(FW_RING) + (uint32_t)rs * (uint32_t)P.ring_slot_bytes;
         mbar_wait_hint(&bars->x_empty[rs], rpar ^ 1u);
         const unsigned char* s0 = src - off;
@@ -761,8 +773,12 @@ fused_wide_forward_kernel(const __grid_constant__ FwParams P, const float* __res
             const uint64_t bh = smem_desc_kmajor(b_hi + jj * (2u * lbo_b), lbo_b, 128);
             const uint64_t bl = smem_desc_kmajor(b_lo + jj * (2u * lbo_b), lbo_b, 128);
             if (leader) {
+#ifdef FW_DBG_SKIP_CROSS      // timing probe only (wrong results): how much of the period is MMA count / operand fetch?
+              mma_tf32_ss(d, al, bh, idesc, (!first || jj > 0) ? 1u : 0u);
+#else
               mma_tf32_ss(d, al, bh, idesc, (!first || jj > 0) ? 1u : 0u);
               mma_tf32_ss(d, ah, bl, idesc, 1);
+#endif
             }
           }
 #pragma unroll 1
@@ -897,11 +913,13 @@ fused_wide_forward_kernel(const __grid_constant__ FwParams P, const float* __res
           const int u = kc * FW_KU + q;
           if (u >= P.n_units) {
             v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+#ifndef FW_DBG_SKIP_ROT
           } else if (aligned && u < P.n_pos) {        // z = (p - c) R  (ann.py:197), p and c relative to the pivot
             const float dx = v[q].x - c0, dy = v[q].y - c1, dz = v[q].z - c2;
             v[q].x = fmaf(dx, rg.R[0], fmaf(dy, rg.R[3], dz * rg.R[6]));
             v[q].y = fmaf(dx, rg.R[1], fmaf(dy, rg.R[4], dz * rg.R[7]));
             v[q].z = fmaf(dx, rg.R[2], fmaf(dy, rg.R[5], dz * rg.R[8]));
+#endif
           }
         }
         if (warp == 0 && it == 0) FW_EVT(1, 16 + kc, 0);

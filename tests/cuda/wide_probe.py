@@ -42,5 +42,11 @@ if __name__ == "__main__":
     for name in names:
         run(name, {"MOLANN_B200_WIDE": "0"})
         run(name, {})
-        for env in ({"MOLANN_B200_WIDE_SLOTS": "8"},):
-            run(name, env)
+        ku2 = {"MOLANN_B200_WIDE_KU": "2"}
+        for extra in ({}, {"MOLANN_B200_WIDE_STAGES": "4"}, {"MOLANN_B200_WIDE_STAGES": "3"},
+                      {"MOLANN_B200_WIDE_STAGES": "3", "MOLANN_B200_WIDE_RING": "5"},
+                      {"MOLANN_B200_WIDE_STAGES": "2", "MOLANN_B200_WIDE_RING": "6"},
+                      {"MOLANN_B200_WIDE_STAGES": "4", "MOLANN_B200_WIDE_CDEPTH": "4"}):
+            e = dict(ku2)
+            e.update(extra)
+            run(name, e)
