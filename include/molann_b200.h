@@ -161,7 +161,12 @@ int molann_b200_prepared_refresh(MolannPrepared* prepared, const MolannPlan* pla
 size_t molann_b200_prepared_workspace_bytes(const MolannPrepared* prepared, int64_t L);
 int molann_b200_forward_prepared(const MolannPrepared* prepared, const MolannPlan* plan, const float* x, int64_t L,
                                  float* y, void* workspace, size_t workspace_bytes, void* stream);
-/* y and gx = d<gy, y>/dx on a prepared plan: the layered tensor-core kernels on operands packed once (no pack launches) */
+/* y and gx = d<gy, y>/dx on a prepared plan (replaces `y = model(x); torch.autograd.grad(y, x, gy)` of
+ * molann/ann.py:553-565, 620-624): the forward is the fused wide kernel, which also leaves the hidden activations in the
+ * workspace (tanh plans; other activations recompute the forward with the layered kernels); the backward runs the
+ * layered tensor-core kernels on the operands packed once (no pack launches) and the block preprocess backward.  Frames
+ * are processed in chunks of whole 148 x 128-frame waves that fit ~2 GB of workspace
+ * (molann_b200_prepared_workspace_bytes covers it). */
 int molann_b200_value_and_grad_prepared(const MolannPrepared* prepared, const MolannPlan* plan, const float* x,
                                         const float* gy, int64_t L, float* y, float* gx, void* workspace,
                                         size_t workspace_bytes, void* stream);
