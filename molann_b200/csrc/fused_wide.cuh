@@ -17,34 +17,40 @@
 //      on the per-frame path) and applied when the operand chunk is built.  Bond / angle / dihedral features are
 //      rigid-motion invariant and final as soon as they are computed.
 //   2. A PER-CTA TRANSPOSITION SCRATCH IN L2.  Each CTA owns a small ring of 32-frame sub-tiles in global memory
-//      (C3: 5 x 104 KB per CTA, 77 MB for the chip -- it is overwritten every tile, so it lives in the 126 MB L2 and
-//      DRAM never sees it; x streams through with no reuse).  A geometry warp builds a frame's row in a shared-memory
-//      staging buffer and sends it out with ONE asynchronous bulk store (no release stall on scattered global stores);
-//      converter threads read 64 bytes of their row per K-chunk.  Row = [16 header floats][units].
+//      (C3: 6 x 108 KB per CTA, 96 MB for the chip -- it is overwritten every tile, so most of it lives in the 126 MB
+//      L2; x streams through with an evict-first hint, the scratch stores carry evict-last and the converter discards
+//      a row's lines once it has read them).  The geometry warps write their results STRAIGHT into the frame's row
+//      (small L2 stores); converter threads pull 64 bytes of their row per K-chunk through a cp.async staging ring.
+//      Row = [moment partials of the frame's geometry warps][units], padded to whole 128-byte lines.
 // Internal feature order ("units" of 4 floats = 16 bytes, the K-major granule of the tensor-core operand): unit u <
 // n_pos = (x, y, z of position atom u, invariant feature u); further invariant features follow four per unit.  With
 // as many invariant columns as position atoms (C3, C5) K stays exactly d.  The first layer's weights are permuted,
 // pre-scaled by the activation's exponent scale, split into TF32 hi / lo and laid out per K-chunk ONCE per plan
 // (molann_b200_prepare), so a weight block is one bulk copy and no pack kernel runs in the steady state.
 //
-// Roles (28 warps, persistent CTA per SM, everything hands over through mbarriers):
-//   X producer (1 warp)   cp.async.bulk of whole frames into a shared-memory ring
-//   geometry   (4 warps)  the four warps share ONE frame at a time (thread = alignment atom / position atom /
-//                         invariant entry): pivoted moments (shuffle + fixed-order sum), raw position atoms,
-//                         invariant features -> staging row -> scratch sub-tile;  no rotation here
-//   converter  (4 warps)  thread = frame: quaternion rotation from the moments (polynomial fast path / Jacobi
-//                         fallback, geometry.cuh) once per tile, then per K-chunk: 64 bytes from the scratch ->
+// Roles (32 warps, persistent CTA per SM, everything hands over through mbarriers; DESIGN.md 3.6 has the measurements
+// behind each choice):
+//   X producers (2 warps) cp.async (16 B, L2 evict-first) of whole frames into a shared-memory ring, alternate 2 KB pieces
+//   geometry   (8 warps)  two groups of four warps on alternate frames; the warps of a group share ONE frame (thread =
+//                         alignment atom / position atom / invariant entry) and never meet: pivoted moments -> the
+//                         warp's own 12-float partial in the row header, raw position atoms, invariant features ->
+//                         the row; the ring slot is released as soon as the frame has been read;  no rotation here
+//   converter  (4 warps)  thread = frame: sum of the moment partials, quaternion rotation (polynomial fast path /
+//                         Jacobi fallback, geometry.cuh) once per tile, then per K-chunk: 64 bytes of the row ->
 //                         (p - c) R -> TF32 hi / lo (round to nearest) -> canonical K-major operand tile in smem
 //   W producer (1 warp)   cp.async.bulk of the pre-packed weight block of each chunk (layer 1, then layer 2)
 //   MMA        (1 warp)   elected lane: tcgen05.mma 3xTF32, SS form, M = 128, N = N1 (layer 1) / N2 (layer 2), K = 8.
-//                         Layer 1: 32-wide K segments into two alternating 256-column TMEM accumulators (the tensor
+//                         Layer 1: 64-wide K segments into two alternating 256-column TMEM accumulators (the tensor
 //                         core truncates its fp32 accumulator at every step: long sums in one accumulator cost 1e-5,
-//                         gemm_tc.cuh).  Layer 2 (K <= 256): the four chunks of one epilogue warpgroup go into one of
+//                         gemm_tc.cuh).  Layer 2 (K <= 256): the chunks of one epilogue warpgroup go into one of
 //                         four 128-column accumulators (two of 256 when N2 > 128) -- 24 steps each and no drain
 //                         between its MMAs, so the epilogue can hand all of h1 over before it reads anything back
 //   epilogue   (16 warps) thread = row x 64 columns: fp32 sum of the segments in registers, bias + activation, the
 //                         activations go straight back into the operand ring as layer 2's A chunks (hi / lo), sum of
-//                         the layer-2 accumulators, activation, last (narrow) layer as register dot products, y.
+//                         the layer-2 accumulators, activation, last (narrow) layer as register dot products, y
+//                         (STORE_H instantiation: also h1 / h2 for the value-and-gradient path).
+// Template parameters: ACT, KU (16-byte units per K-chunk: 4, or 2 = half-size operand stages for 60 KB frames),
+// STORE_H.  FW_OPT_* / FW_DBG_* are the A/B and timing-ablation switches of tests/cuda/fw_trace.cu (profiles/r3i, r3u).
 #pragma once
 #include "common.cuh"
 #include "fused_tc.cuh"
