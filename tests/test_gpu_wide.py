@@ -231,3 +231,31 @@ def test_wide_bench_size(name):
     xs = x[idx.cuda()].cpu()
     y64, y32 = _oracle(spec, ws, bs, xs)
     assert_parity(y[idx.cuda()].cpu(), y64, y32, TOL, name + " bench-size y sample")
+
+
+@pytest.mark.parametrize("activation", ["tanh", "sigmoid"])
+def test_wide_value_and_grad_chunks_and_activations(activation, monkeypatch):
+    """value_and_grad of a prepared wide plan: (a) cut into several chunks (MOLANN_B200_WIDE_VG_CHUNK) it must agree with
+    the one-chunk result (frames are independent; the backward GEMM's summation order follows the tile's CTA, so to
+    rounding), (b) tanh takes the fused forward + stored activations, other activations the layered recompute -- both
+    must match the fp64 oracle."""
+    monkeypatch.setenv("MOLANN_B200_WIDE", "1")
+    spec = S.get_spec("C3s")
+    spec.activation = activation
+    model, _ = S.build_model(spec, init_seed=5)
+    nl = len(spec.layer_dims) - 1
+    ws, bs = _weights(model, nl)
+    L = 777
+    x = S.make_frames(spec, L, seed=21)
+    cot = torch.randn(L, spec.out_dim(), generator=torch.Generator().manual_seed(8))
+    y64, gx64 = oracle_value_and_grad(oracle_model(spec, ws, bs), x, cot)
+    y32, gx32 = oracle_value_and_grad(oracle_model(spec, ws, bs, torch.float32), x, cot, torch.float32)
+    model = model.cuda()
+    y, gx = model.value_and_grad(dev(x), cot.cuda())
+    assert_parity(y.cpu(), y64, y32, TOL, activation + " y")
+    assert_parity(gx.cpu(), gx64, gx32, TOL, activation + " gx")
+    monkeypatch.setenv("MOLANN_B200_WIDE_VG_CHUNK", "256")          # 777 frames = 3 chunks + a ragged one
+    yc, gxc = model.value_and_grad(dev(x), cot.cuda())
+    assert float((yc - y).abs().max()) <= 2e-6 * max(1.0, float(y.abs().max()))
+    assert float((gxc - gx).abs().max()) <= 2e-5 * max(1e-6, float(gx.abs().max()))
+    assert_parity(gxc.cpu(), gx64, gx32, TOL, activation + " gx (chunked)")
