@@ -90,6 +90,9 @@ struct WsLayout {
   int total_bytes;
 };
 
+#ifndef MOLANN_SHARED_RCP
+#define MOLANN_SHARED_RCP 0   // paired activation with one reciprocal (A/B switch)
+#endif
 #ifndef MOLANN_WAIT_NS
 #define MOLANN_WAIT_NS 64     // back-off between two polls of an mbarrier (A/B switch of tests/cuda/ws_trace.cu)
 #endif
@@ -142,12 +145,24 @@ template <int ACT>
 __device__ __forceinline__ void ws_act_x2(float z0, float z1, float& h0, float& h1) {
   if (ACT == ACT_TANH || ACT == ACT_SIGMOID) {
     float e0, e1, r0, r1;
+#if MOLANN_SHARED_RCP
+    // ONE reciprocal for the pair: 1 / s0 = s1 / (s0 s1) -- three MUFU operations per pair instead of four (the XU pipe
+    // is 58 % busy in the C2 forward and the geometry role's rsqrt / div queue behind the epilogues' on it).  The
+    // clamp keeps s0 s1 finite (2^124); tanh / sigmoid are saturated to fp32 rounding long before (|x| > 21).
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fminf(z0, 62.0f)));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fminf(z1, 62.0f)));
+    float s0, s1, rp;
+    f2_unpack(f2_add(f2_pack(e0, e1), f2_pack(1.0f, 1.0f)), s0, s1);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rp) : "f"(s0 * s1));
+    f2_unpack(f2_mul(f2_pack(rp, rp), f2_pack(s1, s0)), r0, r1);
+#else
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(z0));
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(z1));
     float s0, s1;
     f2_unpack(f2_add(f2_pack(e0, e1), f2_pack(1.0f, 1.0f)), s0, s1);
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(s0));
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(s1));
+#endif
     if (ACT == ACT_TANH) {
       f2_unpack(f2_fma(f2_pack(-2.0f, -2.0f), f2_pack(r0, r1), f2_pack(1.0f, 1.0f)), h0, h1);
     } else {
