@@ -757,13 +757,14 @@ WideChoice choose_wide(const MolannPrepared* h, const MolannPlan* p, long long L
   P.off_stage = c.take(stages * FW_STAGE_BYTES, 1024);
   P.off_ring = c.take(ring * P.ring_slot_bytes, 128);
   P.off_pos = P.off_aidx = P.off_ref = P.off_ent = -1;
-  if (c.off + h->n_inv_ent * ENTRY_INTS * 4 + 16 <= budget && h->n_inv_ent > 0)
+  const bool stage_tables = env_int("MOLANN_B200_WIDE_TABLES", 1) != 0;     // 0: tests force the global-memory tables
+  if (stage_tables && c.off + h->n_inv_ent * ENTRY_INTS * 4 + 16 <= budget && h->n_inv_ent > 0)
     P.off_ent = c.take(h->n_inv_ent * ENTRY_INTS * 4, 16);
-  if (c.off + p->n_align * 16 + 32 <= budget && p->n_align > 0) {
+  if (stage_tables && c.off + p->n_align * 16 + 32 <= budget && p->n_align > 0) {
     P.off_aidx = c.take(p->n_align * 4, 16);
     P.off_ref = c.take(p->n_align * 12, 16);
   }
-  if (c.off + h->n_pos * 4 + 16 <= budget && h->n_pos > 0) P.off_pos = c.take(h->n_pos * 4, 16);
+  if (stage_tables && c.off + h->n_pos * 4 + 16 <= budget && h->n_pos > 0) P.off_pos = c.take(h->n_pos * 4, 16);
   P.total_smem = round_up(c.off, 128);
   if (P.total_smem > budget) return ch;
   const long long ntiles = (L + FW_M - 1) / FW_M;

@@ -61,7 +61,7 @@ VARIANTS = ["one_hidden", "three_outputs", "narrow_wide", "mixed_program", "no_a
             "many_invariants", "angle_values"]
 
 
-@pytest.mark.parametrize("ku", ["4", "2"])
+@pytest.mark.parametrize("ku", ["4", "2", "4-global-tables"])
 @pytest.mark.parametrize("variant", VARIANTS)
 def test_wide_kernel_variants(variant, ku, monkeypatch):
     """Shapes and programs: one hidden layer, widths that are not multiples of 64, up to 8 outputs, programs mixing all
@@ -69,7 +69,9 @@ def test_wide_kernel_variants(variant, ku, monkeypatch):
     no alignment, the other activations, angle values -- on both K-chunk sizes of the kernel (KU = 4: K = 16 per operand
     stage, the default; KU = 2: the half-size stages that 60 KB frames need)."""
     monkeypatch.setenv("MOLANN_B200_WIDE", "1")
-    monkeypatch.setenv("MOLANN_B200_WIDE_KU", ku)
+    monkeypatch.setenv("MOLANN_B200_WIDE_KU", ku[0])
+    if ku.endswith("global-tables"):                               # plan tables read from global memory (the instantiation
+        monkeypatch.setenv("MOLANN_B200_WIDE_TABLES", "0")         # that plans too big for shared memory take)
     spec = S.get_spec("C2")
     if variant == "one_hidden":
         spec.layer_dims = [30, 48, 2]
