@@ -172,6 +172,41 @@ int molann_b200_value_and_grad_prepared(const MolannPrepared* prepared, const Mo
                                         size_t workspace_bytes, void* stream);
 void molann_b200_prepared_destroy(MolannPrepared* prepared);
 
+/* ---- autoencoder training step (BASELINE configs[3]) ------------------------------------------
+ * The reference has no training loop; what its modules allow is the composition
+ *   loss = mean((decoder(encoder(x)) - preprocessing(x))^2)
+ * with encoder = MolANN (molann/ann.py:567-624), decoder = create_sequential_nn (ann.py:37-67) and the encoder's own
+ * PreprocessingANN output (ann.py:553-565) as the target, differentiated by autograd w.r.t. every Linear parameter.
+ * molann_b200_train_loss_and_grads replaces that whole graph (forward, loss, backward) by ONE fused kernel per call
+ * plus a fixed-order reduction of the per-SM partial sums (csrc/fused_train.cuh):
+ *   flat[0 .. P)  = d loss / d parameters in torch parameter order: encoder W_1, b_1, W_2, b_2, ... then decoder
+ *                   W_1, b_1, ...  (each W row-major [out, in] like torch.nn.Linear.weight)
+ *   flat[P]       = loss_scale * sum over frames and feature columns of (reconstruction - target)^2
+ * `loss_scale` = 1 / (frames of the GLOBAL batch * d_feat) makes the sum over ranks of `flat` the gradient of the mean
+ * over the global batch: one sum-allreduce of P + 1 floats is the only collective of a data-parallel step.
+ * `dec->dims[0]` must equal the encoder's output width and the decoder's last width d_feat.  Deterministic: the same
+ * inputs give the same bits.  molann_b200_sgd_apply is the plain SGD update p -= lr * g over the same flat layout. */
+typedef struct MolannDecoder {
+  int32_t n_layers;
+  int32_t act_id;                          /* MOLANN_ACT_*, after every layer but the last */
+  int32_t dims[MOLANN_MAX_LAYERS + 1];
+  const float* W[MOLANN_MAX_LAYERS];
+  const float* b[MOLANN_MAX_LAYERS];
+} MolannDecoder;
+/* 1 if the fused training kernel serves this pair (every activation row of one 128-frame tile and all weights fit the
+ * SM's shared memory), else 0 */
+int molann_b200_train_eligible(const MolannPlan* encoder, const MolannDecoder* decoder);
+/* P: number of trainable floats (0 for an invalid pair) */
+size_t molann_b200_train_param_count(const MolannPlan* encoder, const MolannDecoder* decoder);
+size_t molann_b200_train_workspace_bytes(const MolannPlan* encoder, const MolannDecoder* decoder);
+int molann_b200_train_loss_and_grads(const MolannPlan* encoder, const MolannDecoder* decoder, const float* x, int64_t L,
+                                     float loss_scale, float* flat, void* workspace, size_t workspace_bytes,
+                                     void* stream);
+/* params[i][j] -= lr * flat[offset_i + j], offset_i = numel[0] + ... + numel[i-1]; n_params <= 4 * MOLANN_MAX_LAYERS.
+ * `params` and `numel` are HOST arrays of device pointers / element counts. */
+int molann_b200_sgd_apply(float* const* params, const int64_t* numel, int32_t n_params, const float* flat, float lr,
+                          void* stream);
+
 /* Tuning / introspection: which kernel family the dispatcher picks for this plan.
  * 0 = general (warp-per-frame geometry + layered GEMMs), 1 = fused small-system kernel. */
 int molann_b200_path_for(const MolannPlan* plan, int want_backward);

@@ -1,0 +1,409 @@
+// fused_train.cuh -- one fused kernel for the autoencoder training step (BASELINE configs[3]).
+//
+// The reference ships no training loop; C4 is the composition its modules allow:
+//   loss = mean((decoder(encoder(x)) - preprocessing(x))^2),  encoder = MolANN (molann/ann.py:567-624),
+//   decoder = create_sequential_nn (ann.py:37-67), target = PreprocessingANN(x) (ann.py:553-565).
+// Per tile of 128 frames a persistent CTA (one per SM) runs, without leaving the SM:
+//   TMA bulk stage-in of x -> Kabsch + feature program (two lanes per frame) -> every Linear layer of encoder and
+//   decoder forward (register-tiled FFMA, activations resident in shared memory as [width][frame] rows) -> residual,
+//   loss and its cotangent -> for each layer, last to first: the weight / bias gradient of the layer (frames are the
+//   contraction axis; each thread owns a 4 x 4 block of dW) and the backward to the layer input, in place.
+// Parameter gradients accumulate in a per-CTA plane of the workspace (thread-private read-modify-write, L2 resident,
+// no atomics: the result is deterministic); `train_reduce_kernel` sums the planes in a fixed order.  HBM traffic is the
+// algorithmic 12 n bytes per frame; the step is FFMA-bound (about 74 kFLOP per C4 frame).
+//
+// Shared-memory rows have a stride of 132 floats: the dW contraction reads four rows per thread at the same frame
+// quad, and with stride = 4 (mod 32) banks, rows r .. r+7 hit eight different bank quads.
+#pragma once
+#include "common.cuh"
+#include "geometry.cuh"
+#include "fused_small.cuh"
+
+namespace molann {
+
+constexpr int TR_MAXL = 2 * MOLANN_MAX_LAYERS;   // encoder + decoder Linear layers
+constexpr int TR_F = 128;                        // frames per tile
+constexpr int TR_FS = TR_F + 4;                  // row stride in floats
+constexpr int TR_NT = 256;                       // threads per CTA
+
+struct TrainNet {                  // the chain encoder ++ decoder
+  int nl, ne;                      // layers in total / in the encoder
+  int act_enc, act_dec;
+  int P;                           // trainable floats (flat gradient length; the loss sits at index P)
+  int c[TR_MAXL + 1];              // widths: c[0] = d_feat, c[ne] = bottleneck, c[nl] = d_feat
+  const float* W[TR_MAXL];
+  const float* b[TR_MAXL];
+  int gw[TR_MAXL], gb[TR_MAXL];    // offsets of dW_l / db_l in the flat gradient (torch parameter order)
+};
+
+struct TrainLayout {               // byte offsets into dynamic shared memory (host-computed)
+  int a_off[TR_MAXL + 1];          // a_l = input of layer l ([round4(c[l])][TR_FS]); a_off[nl] = loss cotangent
+  int w_off[TR_MAXL], b_off[TR_MAXL], ldk[TR_MAXL];
+  int act_lo, act_bytes;           // the activation region (zeroed once: padding rows must stay 0)
+  int xs_off;                      // coordinate tile, overlays the tail of the activation region
+  int aidx_off, ref_off, ent_off, mbar_off, red_off, total_bytes;
+};
+
+__device__ __forceinline__ int tr_layer_act(const TrainNet& n, int l) {   // activation applied to layer l's output
+  if (l == n.ne - 1 || l == n.nl - 1) return ACT_IDENTITY;              // create_sequential_nn: none after the last
+  return l < n.ne ? n.act_enc : n.act_dec;
+}
+
+__device__ __forceinline__ float tr_act(float v, int act) {
+  if (act == ACT_TANH) {                        // 1 - 2 / (1 + 2^(2 v log2 e)); saturates cleanly at +-1
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * 2.8853900817779268f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return fmaf(-2.0f, r, 1.0f);
+  }
+  if (act == ACT_SIGMOID) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * -1.4426950408889634f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return r;
+  }
+  if (act == ACT_RELU) return fmaxf(v, 0.f);
+  return v;
+}
+
+// acc[i][j] += sum_k A[k][f0 + i] * Wn[n0 + j][k]   (four frames x eight outputs, k in steps of four)
+__device__ __forceinline__ void tr_fwd_acc(const float* __restrict__ A, const float* __restrict__ Wn, int ldk, int K4,
+                                           int f0, int n0, float (&acc)[4][8]) {
+  const float* ap = A + f0;
+  const float* wp = Wn + n0 * ldk;
+#pragma unroll 2
+  for (int k = 0; k < K4; k += 4) {
+    const float4 a0 = *reinterpret_cast<const float4*>(ap);
+    const float4 a1 = *reinterpret_cast<const float4*>(ap + TR_FS);
+    const float4 a2 = *reinterpret_cast<const float4*>(ap + 2 * TR_FS);
+    const float4 a3 = *reinterpret_cast<const float4*>(ap + 3 * TR_FS);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 w = *reinterpret_cast<const float4*>(wp + j * ldk + k);
+      acc[0][j] = fmaf(a3.x, w.w, fmaf(a2.x, w.z, fmaf(a1.x, w.y, fmaf(a0.x, w.x, acc[0][j]))));
+      acc[1][j] = fmaf(a3.y, w.w, fmaf(a2.y, w.z, fmaf(a1.y, w.y, fmaf(a0.y, w.x, acc[1][j]))));
+      acc[2][j] = fmaf(a3.z, w.w, fmaf(a2.z, w.z, fmaf(a1.z, w.y, fmaf(a0.z, w.x, acc[2][j]))));
+      acc[3][j] = fmaf(a3.w, w.w, fmaf(a2.w, w.z, fmaf(a1.w, w.y, fmaf(a0.w, w.x, acc[3][j]))));
+    }
+    ap += 4 * TR_FS;
+  }
+}
+
+// O[n][f] = act(sum_k A[k][f] Wn[n][k] + b[n])
+__device__ __forceinline__ void tr_forward_layer(const float* __restrict__ A, float* __restrict__ O,
+                                                 const float* __restrict__ Wn, const float* __restrict__ bs, int ldk,
+                                                 int K4, int N, int act, int tid) {
+  const int nog = (N + 7) >> 3;
+  for (int item = tid; item < (TR_F / 4) * nog; item += TR_NT) {
+    const int f0 = (item & 31) * 4, n0 = (item >> 5) * 8;
+    float acc[4][8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float bj = bs[n0 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[i][j] = bj;
+    }
+    tr_fwd_acc(A, Wn, ldk, K4, f0, n0, acc);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (n0 + j < N)
+        *reinterpret_cast<float4*>(O + (n0 + j) * TR_FS + f0) =
+            make_float4(tr_act(acc[0][j], act), tr_act(acc[1][j], act), tr_act(acc[2][j], act), tr_act(acc[3][j], act));
+  }
+}
+
+// last layer: residual against the features, squared error (valid frames only) and the loss cotangent
+__device__ __forceinline__ float tr_last_layer(const float* __restrict__ A, const float* __restrict__ feat,
+                                               float* __restrict__ G, const float* __restrict__ Wn,
+                                               const float* __restrict__ bs, int ldk, int K4, int N, int nf,
+                                               float two_scale, int tid) {
+  const int nog = (N + 7) >> 3;
+  float sq = 0.f;
+  for (int item = tid; item < (TR_F / 4) * nog; item += TR_NT) {
+    const int f0 = (item & 31) * 4, n0 = (item >> 5) * 8;
+    float acc[4][8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float bj = bs[n0 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[i][j] = bj;
+    }
+    tr_fwd_acc(A, Wn, ldk, K4, f0, n0, acc);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (n0 + j < N) {
+        const float4 t = *reinterpret_cast<const float4*>(feat + (n0 + j) * TR_FS + f0);
+        float e[4] = {acc[0][j] - t.x, acc[1][j] - t.y, acc[2][j] - t.z, acc[3][j] - t.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (f0 + i >= nf) e[i] = 0.f;
+          sq = fmaf(e[i], e[i], sq);
+          e[i] *= two_scale;
+        }
+        *reinterpret_cast<float4*>(G + (n0 + j) * TR_FS + f0) = make_float4(e[0], e[1], e[2], e[3]);
+      }
+    }
+  }
+  return sq;
+}
+
+// IO[i][f] = (sum_o GZ[o][f] Wn[o][i]) * act'(IO[i][f])   -- in place on the layer input
+__device__ __forceinline__ void tr_backward_layer(const float* __restrict__ GZ, float* __restrict__ IO,
+                                                  const float* __restrict__ Wn, int ldk, int N, int K, int act_prev,
+                                                  int tid) {
+  const int nig = (K + 7) >> 3;
+  for (int item = tid; item < (TR_F / 4) * nig; item += TR_NT) {
+    const int f0 = (item & 31) * 4, i0 = (item >> 5) * 8;
+    float acc[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    const float* gp = GZ + f0;
+    const float* wp = Wn + i0;
+#pragma unroll 4
+    for (int o = 0; o < N; ++o) {
+      const float4 g = *reinterpret_cast<const float4*>(gp);
+      const float4 w0 = *reinterpret_cast<const float4*>(wp);
+      const float4 w1 = *reinterpret_cast<const float4*>(wp + 4);
+      const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc[0][j] = fmaf(g.x, w[j], acc[0][j]);
+        acc[1][j] = fmaf(g.y, w[j], acc[1][j]);
+        acc[2][j] = fmaf(g.z, w[j], acc[2][j]);
+        acc[3][j] = fmaf(g.w, w[j], acc[3][j]);
+      }
+      gp += TR_FS;
+      wp += ldk;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (i0 + j < K) {
+        float4* p = reinterpret_cast<float4*>(IO + (i0 + j) * TR_FS + f0);
+        const float4 h = *p;
+        *p = make_float4(acc[0][j] * act_grad_from_output(h.x, act_prev), acc[1][j] * act_grad_from_output(h.y, act_prev),
+                         acc[2][j] * act_grad_from_output(h.z, act_prev), acc[3][j] * act_grad_from_output(h.w, act_prev));
+      }
+    }
+  }
+}
+
+// dW[o][i] += sum_f GZ[o][f] A[i][f],  db[o] += sum_f GZ[o][f].  A thread owns rows o = to + TO r and i = ti + TI r
+// (r < 4, interleaved so that the eight `to` of a warp read eight different bank quads); a warp covers 8 x 4 threads.
+// The running sums live in this CTA's plane of the workspace; nobody else touches it.
+__device__ __forceinline__ void tr_dw_layer(const float* __restrict__ GZ, const float* __restrict__ A, int N, int K,
+                                            float* __restrict__ pw, float* __restrict__ pb, bool first, int tid) {
+  const int TO = (N + 3) >> 2, TI = (K + 3) >> 2;
+  const int nbo = (TO + 7) >> 3, nbi = (TI + 3) >> 2;
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int blk = warp; blk < nbo * nbi; blk += TR_NT / 32) {
+    const int to = (blk % nbo) * 8 + (lane & 7), ti = (blk / nbo) * 4 + (lane >> 3);
+    if (to >= TO || ti >= TI) continue;
+    const bool with_bias = (ti == 0);
+    float acc[4][4], sb[4];
+#pragma unroll
+    for (int ro = 0; ro < 4; ++ro) {
+      const int o = to + TO * ro;
+      sb[ro] = (with_bias && !first && o < N) ? __ldcg(pb + o) : 0.f;
+#pragma unroll
+      for (int ri = 0; ri < 4; ++ri) {
+        const int i = ti + TI * ri;
+        acc[ro][ri] = (!first && o < N && i < K) ? __ldcg(pw + o * K + i) : 0.f;
+      }
+    }
+    const float* gp = GZ + to * TR_FS;
+    const float* ap = A + ti * TR_FS;
+    const int gstep = TO * TR_FS, astep = TI * TR_FS;
+#pragma unroll 2
+    for (int fq = 0; fq < TR_F; fq += 4) {
+      float4 g[4], a[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        g[r] = *reinterpret_cast<const float4*>(gp + r * gstep + fq);
+        a[r] = *reinterpret_cast<const float4*>(ap + r * astep + fq);
+      }
+#pragma unroll
+      for (int ro = 0; ro < 4; ++ro)
+#pragma unroll
+        for (int ri = 0; ri < 4; ++ri)
+          acc[ro][ri] = fmaf(g[ro].w, a[ri].w, fmaf(g[ro].z, a[ri].z, fmaf(g[ro].y, a[ri].y, fmaf(g[ro].x, a[ri].x, acc[ro][ri]))));
+      if (with_bias) {
+#pragma unroll
+        for (int ro = 0; ro < 4; ++ro) sb[ro] += (g[ro].x + g[ro].y) + (g[ro].z + g[ro].w);
+      }
+    }
+#pragma unroll
+    for (int ro = 0; ro < 4; ++ro) {
+      const int o = to + TO * ro;
+      if (o < N) {
+        if (with_bias) __stcg(pb + o, sb[ro]);
+#pragma unroll
+        for (int ri = 0; ri < 4; ++ri) {
+          const int i = ti + TI * ri;
+          if (i < K) __stcg(pw + o * K + i, acc[ro][ri]);
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(TR_NT, 1)
+fused_train_kernel(const __grid_constant__ DevPlan p, const __grid_constant__ TrainNet net,
+                   const __grid_constant__ TrainLayout lay, const float* __restrict__ x, long long L, float loss_scale,
+                   float* __restrict__ planes, int use_tma) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int tid = threadIdx.x;
+  const int n3 = 3 * p.n_inp;
+  float* xs = reinterpret_cast<float*>(smem + lay.xs_off);
+  const int* aidx = reinterpret_cast<const int*>(smem + lay.aidx_off);
+  const float* ref = reinterpret_cast<const float*>(smem + lay.ref_off);
+  const int* ent = reinterpret_cast<const int*>(smem + lay.ent_off);
+  unsigned long long* mbar = reinterpret_cast<unsigned long long*>(smem + lay.mbar_off);
+  float* red = reinterpret_cast<float*>(smem + lay.red_off);
+  float* plane = planes + (size_t)blockIdx.x * (size_t)(net.P + 1);
+
+  // ---- once per CTA: constants, zero-padded natural weights Wn[round8(N)][ldk], zeroed activation rows ----
+  {
+    int* aidx_w = reinterpret_cast<int*>(smem + lay.aidx_off);
+    float* ref_w = reinterpret_cast<float*>(smem + lay.ref_off);
+    int* ent_w = reinterpret_cast<int*>(smem + lay.ent_off);
+    for (int i = tid; i < p.n_align; i += TR_NT) aidx_w[i] = p.align_idx[i];
+    for (int i = tid; i < 3 * p.n_align; i += TR_NT) ref_w[i] = p.ref_x[i];
+    for (int i = tid; i < ENTRY_INTS * p.n_entries; i += TR_NT) ent_w[i] = p.entries[i];
+  }
+  for (int l = 0; l < net.nl; ++l) {
+    const int K = net.c[l], N = net.c[l + 1], ld = lay.ldk[l], N8 = round_up(N, 8);
+    float* Wn = reinterpret_cast<float*>(smem + lay.w_off[l]);
+    float* bs = reinterpret_cast<float*>(smem + lay.b_off[l]);
+    const float* Wg = net.W[l];
+    const float* bg = net.b[l];
+    for (int idx = tid; idx < N8 * ld; idx += TR_NT) {
+      const int o = idx / ld, i = idx - o * ld;
+      Wn[idx] = (o < N && i < K) ? Wg[(long long)o * K + i] : 0.f;
+    }
+    for (int o = tid; o < N8; o += TR_NT) bs[o] = (o < N) ? bg[o] : 0.f;
+  }
+  {
+    float4* z = reinterpret_cast<float4*>(smem + lay.act_lo);
+    for (int i = tid; i < lay.act_bytes / 16; i += TR_NT) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (tid == 0) {
+    mbar_init(mbar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  const long long ntiles = (L + TR_F - 1) / TR_F;
+  const uint32_t tile_bytes = (uint32_t)TR_F * (uint32_t)n3 * 4u;
+  const float two_scale = 2.0f * loss_scale;
+  uint32_t phase = 0;
+  float sq = 0.f;
+  float* feat = reinterpret_cast<float*>(smem + lay.a_off[0]);
+  float* gout = reinterpret_cast<float*>(smem + lay.a_off[net.nl]);
+
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const bool first = (tile == (long long)blockIdx.x);
+    const long long f_base = tile * (long long)TR_F;
+    const int nf = (int)((L - f_base) < (long long)TR_F ? (L - f_base) : (long long)TR_F);
+    // ---- stage the coordinate tile (it overlays activation rows that are dead at this point) ----
+    if (use_tma && nf == TR_F) {
+      if (tid == 0) {
+        fence_proxy_async_smem();
+        mbar_expect_tx(mbar, tile_bytes);
+        bulk_g2s(xs, x + f_base * n3, tile_bytes, mbar);
+      }
+      mbar_wait(mbar, phase);
+      phase ^= 1u;
+    } else {
+      const float* src = x + f_base * n3;
+      for (int i = tid; i < nf * n3; i += TR_NT) xs[i] = src[i];
+      __syncthreads();
+    }
+    // ---- geometry: two lanes per frame ----
+    {
+      const int f = tid >> 1, sub = tid & 1;
+      const float* xf = xs + (f < nf ? f : nf - 1) * n3;     // idle frame slots recompute a valid frame (masked below)
+      Rigid rg;
+      const bool aligned = p.n_align > 0;
+      if (aligned) kabsch<2>(xf, aidx, ref, p.n_align, sub, rg);
+      TileOut out{feat, f, TR_FS};
+      for (int e = sub; e < p.n_entries; e += 2) {
+        const Entry en = load_entry(ent + ENTRY_INTS * e);
+        feature_forward(en, xf, aligned, rg, p.use_angle, out);
+      }
+    }
+    __syncthreads();
+    // the overlay is dead from here on; its rows must read as zero padding again where they are padding
+    if (lay.xs_off < lay.act_lo + lay.act_bytes) {
+      float4* z = reinterpret_cast<float4*>(xs);
+      for (int i = tid; i < (int)(tile_bytes / 16); i += TR_NT) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      __syncthreads();
+    }
+    // ---- forward through encoder and decoder ----
+    for (int l = 0; l < net.nl; ++l) {
+      const float* A = reinterpret_cast<const float*>(smem + lay.a_off[l]);
+      const float* Wn = reinterpret_cast<const float*>(smem + lay.w_off[l]);
+      const float* bs = reinterpret_cast<const float*>(smem + lay.b_off[l]);
+      const int K4 = round_up(net.c[l], 4), N = net.c[l + 1];
+      if (l < net.nl - 1) {
+        tr_forward_layer(A, reinterpret_cast<float*>(smem + lay.a_off[l + 1]), Wn, bs, lay.ldk[l], K4, N,
+                         tr_layer_act(net, l), tid);
+      } else {
+        sq += tr_last_layer(A, feat, gout, Wn, bs, lay.ldk[l], K4, N, nf, two_scale, tid);
+      }
+      __syncthreads();
+    }
+    // ---- backward: parameter gradients of layer l, then the cotangent of its input (in place) ----
+    for (int l = net.nl - 1; l >= 0; --l) {
+      const float* GZ = reinterpret_cast<const float*>(smem + lay.a_off[l + 1]);
+      float* A = reinterpret_cast<float*>(smem + lay.a_off[l]);
+      const int K = net.c[l], N = net.c[l + 1];
+      tr_dw_layer(GZ, A, N, K, plane + net.gw[l], plane + net.gb[l], first, tid);
+      if (l > 0) {
+        __syncthreads();
+        tr_backward_layer(GZ, A, reinterpret_cast<const float*>(smem + lay.w_off[l]), lay.ldk[l], N, K,
+                          tr_layer_act(net, l - 1), tid);
+      }
+      __syncthreads();
+    }
+  }
+  // ---- this CTA's share of the loss ----
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, s);
+  if ((tid & 31) == 0) red[tid >> 5] = sq;
+  __syncthreads();
+  if (tid == 0) {
+    float t = 0.f;
+    for (int w = 0; w < TR_NT / 32; ++w) t += red[w];
+    plane[net.P] = t * loss_scale;
+  }
+}
+
+// flat[p] = sum over the CTA planes, in plane order (deterministic)
+__global__ void train_reduce_kernel(const float* __restrict__ planes, int n_planes, int n, float* __restrict__ flat) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int c = 0; c < n_planes; ++c) s += __ldcg(planes + (size_t)c * n + i);
+  flat[i] = s;
+}
+
+// plain SGD over up to 2 TR_MAXL parameter tensors laid out like the flat gradient: p -= lr * g
+struct SgdTable {
+  float* ptr[2 * TR_MAXL];
+  int end[2 * TR_MAXL];            // exclusive prefix ends in the flat gradient
+  int n;
+};
+__global__ void train_sgd_kernel(const __grid_constant__ SgdTable tab, const float* __restrict__ flat, float lr,
+                                 int total) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int t = 0;
+  while (t < tab.n - 1 && i >= tab.end[t]) ++t;
+  const int start = t ? tab.end[t - 1] : 0;
+  float* q = tab.ptr[t] + (i - start);
+  *q = fmaf(-lr, flat[i], *q);
+}
+
+}  // namespace molann

@@ -21,6 +21,7 @@
 #include "staged_block.cuh"
 #include "small_tile.cuh"
 #include "general.cuh"
+#include "fused_train.cuh"
 
 using namespace molann;
 
@@ -1875,6 +1876,179 @@ int molann_b200_align_backward(const MolannPlan* plan, const float* x, const flo
   }
   align_backward_warp_kernel<<<warp_grid(L, dev), WARPS_PER_CTA * 32, 0, static_cast<cudaStream_t>(stream)>>>(
       dp, x, gout, gx, L);
+  return post_launch();
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// autoencoder training step (fused_train.cuh)
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct TrainChoice {
+  bool ok = false;
+  TrainNet net;
+  TrainLayout lay;
+};
+
+int validate_decoder(const MolannPlan* enc, const MolannDecoder* dec) {
+  int s = validate_full(enc);
+  if (s) return s;
+  if (!dec) return MOLANN_ERR_NULL;
+  if (enc->n_layers < 1 || dec->n_layers < 1 || dec->n_layers > MOLANN_MAX_LAYERS) return MOLANN_ERR_PLAN;
+  if (dec->act_id < 0 || dec->act_id > MOLANN_ACT_IDENTITY) return MOLANN_ERR_PLAN;
+  if (dec->dims[0] != enc->dims[enc->n_layers] || dec->dims[dec->n_layers] != enc->d_feat) return MOLANN_ERR_PLAN;
+  for (int k = 0; k <= dec->n_layers; ++k)
+    if (dec->dims[k] <= 0) return MOLANN_ERR_PLAN;
+  for (int k = 0; k < dec->n_layers; ++k)
+    if (!dec->W[k] || !dec->b[k]) return MOLANN_ERR_NULL;
+  return MOLANN_OK;
+}
+
+TrainChoice choose_train(const MolannPlan* enc, const MolannDecoder* dec, const DeviceInfo& dev) {
+  TrainChoice tc;
+  std::memset(&tc.net, 0, sizeof(tc.net));
+  std::memset(&tc.lay, 0, sizeof(tc.lay));
+  TrainNet& n = tc.net;
+  n.ne = enc->n_layers;
+  n.nl = enc->n_layers + dec->n_layers;
+  n.act_enc = enc->act_id;
+  n.act_dec = dec->act_id;
+  long long P = 0;
+  for (int l = 0; l < n.nl; ++l) {
+    const bool e = l < n.ne;
+    const int k = e ? l : l - n.ne;
+    n.c[l] = e ? enc->dims[k] : dec->dims[k];
+    n.c[l + 1] = e ? enc->dims[k + 1] : dec->dims[k + 1];
+    n.W[l] = e ? enc->W[k] : dec->W[k];
+    n.b[l] = e ? enc->b[k] : dec->b[k];
+    n.gw[l] = (int)P;
+    P += (long long)n.c[l] * n.c[l + 1];
+    n.gb[l] = (int)P;
+    P += n.c[l + 1];
+    if (P > (1ll << 28)) return tc;
+  }
+  n.P = (int)P;
+  TrainLayout& lay = tc.lay;
+  long long off = 0;
+  lay.act_lo = 0;
+  for (int l = 0; l <= n.nl; ++l) {
+    lay.a_off[l] = (int)off;
+    off += (long long)round_up(n.c[l], 4) * TR_FS * 4;
+  }
+  lay.act_bytes = (int)off;
+  const long long tile_bytes = (long long)TR_F * 3 * enc->n_inp * 4;
+  const long long over = (off - tile_bytes) / 128 * 128;       // overlay on the tail (dead rows during the geometry)
+  if (off - tile_bytes >= 0 && over >= lay.a_off[1]) {
+    lay.xs_off = (int)over;
+  } else {
+    off = (off + 127) / 128 * 128;
+    lay.xs_off = (int)off;
+    off += tile_bytes;
+  }
+  for (int l = 0; l < n.nl; ++l) {
+    lay.ldk[l] = round_up(n.c[l], 8);
+    off = (off + 15) / 16 * 16;
+    lay.w_off[l] = (int)off;
+    off += (long long)round_up(n.c[l + 1], 8) * lay.ldk[l] * 4;
+    lay.b_off[l] = (int)off;
+    off += (long long)round_up(n.c[l + 1], 8) * 4;
+    if (off > (1ll << 24)) return tc;
+  }
+  off = (off + 15) / 16 * 16;
+  lay.aidx_off = (int)off; off += (long long)round_up(enc->n_align > 0 ? enc->n_align : 1, 4) * 4;
+  lay.ref_off = (int)off; off += (long long)round_up(3 * (enc->n_align > 0 ? enc->n_align : 1), 4) * 4;
+  lay.ent_off = (int)off; off += (long long)round_up(ENTRY_INTS * enc->n_entries, 4) * 4;
+  lay.mbar_off = (int)off; off += 16;
+  lay.red_off = (int)off; off += (TR_NT / 32) * 4;
+  off = (off + 15) / 16 * 16;
+  lay.total_bytes = (int)off;
+  tc.ok = off <= dev.max_smem_optin;
+  return tc;
+}
+
+}  // namespace
+
+extern "C" {
+
+int molann_b200_train_eligible(const MolannPlan* encoder, const MolannDecoder* decoder) {
+  if (validate_decoder(encoder, decoder) != MOLANN_OK) return 0;
+  const DeviceInfo dev = device_info();
+  if (!dev.ok) return 0;
+  return choose_train(encoder, decoder, dev).ok ? 1 : 0;
+}
+
+size_t molann_b200_train_param_count(const MolannPlan* encoder, const MolannDecoder* decoder) {
+  if (validate_decoder(encoder, decoder) != MOLANN_OK) return 0;
+  size_t P = 0;
+  for (int k = 0; k < encoder->n_layers; ++k) P += (size_t)(encoder->dims[k] + 1) * encoder->dims[k + 1];
+  for (int k = 0; k < decoder->n_layers; ++k) P += (size_t)(decoder->dims[k] + 1) * decoder->dims[k + 1];
+  return P;
+}
+
+size_t molann_b200_train_workspace_bytes(const MolannPlan* encoder, const MolannDecoder* decoder) {
+  const size_t P = molann_b200_train_param_count(encoder, decoder);
+  const DeviceInfo dev = device_info();
+  if (!P || !dev.ok) return 0;
+  return align256((size_t)dev.sm_count * (P + 1) * 4);
+}
+
+int molann_b200_train_loss_and_grads(const MolannPlan* encoder, const MolannDecoder* decoder, const float* x, int64_t L,
+                                     float loss_scale, float* flat, void* workspace, size_t workspace_bytes,
+                                     void* stream) {
+  int s = validate_decoder(encoder, decoder);
+  if (s) return s;
+  if (L < 0) return MOLANN_ERR_PLAN;
+  if (!flat) return MOLANN_ERR_NULL;
+  if (misaligned4(flat)) return MOLANN_ERR_ALIGNMENT;
+  const DeviceInfo dev = device_info();
+  if (!dev.ok) return MOLANN_ERR_CUDA;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const TrainChoice tc = choose_train(encoder, decoder, dev);
+  if (!tc.ok) return MOLANN_ERR_UNSUPPORTED;
+  const size_t n_flat = (size_t)tc.net.P + 1;
+  if (L == 0) return check_cuda(cudaMemsetAsync(flat, 0, n_flat * 4, st));
+  if (!x) return MOLANN_ERR_NULL;
+  if (misaligned4(x)) return MOLANN_ERR_ALIGNMENT;
+  if (!workspace || workspace_bytes < molann_b200_train_workspace_bytes(encoder, decoder)) return MOLANN_ERR_WORKSPACE;
+  if (misaligned4(workspace)) return MOLANN_ERR_ALIGNMENT;
+  const long long ntiles = (L + TR_F - 1) / TR_F;
+  const int grid = (int)(ntiles < dev.sm_count ? ntiles : dev.sm_count);     // every CTA owns at least one tile
+  s = check_cuda(cudaFuncSetAttribute(fused_train_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      tc.lay.total_bytes));
+  if (s) return s;
+  const int use_tma = ((reinterpret_cast<uintptr_t>(x) & 15u) == 0 && env_int("MOLANN_B200_TMA", 1) != 0) ? 1 : 0;
+  float* planes = static_cast<float*>(workspace);
+  fused_train_kernel<<<grid, TR_NT, tc.lay.total_bytes, st>>>(to_dev(encoder), tc.net, tc.lay, x, (long long)L,
+                                                               loss_scale, planes, use_tma);
+  s = post_launch();
+  if (s) return s;
+  train_reduce_kernel<<<(unsigned)((n_flat + 255) / 256), 256, 0, st>>>(planes, grid, (int)n_flat, flat);
+  return post_launch();
+}
+
+int molann_b200_sgd_apply(float* const* params, const int64_t* numel, int32_t n_params, const float* flat, float lr,
+                          void* stream) {
+  if (!params || !numel || !flat) return MOLANN_ERR_NULL;
+  if (n_params < 0 || n_params > 2 * TR_MAXL) return MOLANN_ERR_PLAN;
+  if (n_params == 0) return MOLANN_OK;
+  SgdTable tab;
+  std::memset(&tab, 0, sizeof(tab));
+  long long total = 0;
+  for (int i = 0; i < n_params; ++i) {
+    if (!params[i]) return MOLANN_ERR_NULL;
+    if (numel[i] < 0 || misaligned4(params[i])) return numel[i] < 0 ? MOLANN_ERR_PLAN : MOLANN_ERR_ALIGNMENT;
+    total += numel[i];
+    if (total > (1ll << 30)) return MOLANN_ERR_PLAN;
+    tab.ptr[i] = params[i];
+    tab.end[i] = (int)total;
+  }
+  tab.n = n_params;
+  if (total == 0) return MOLANN_OK;
+  if (!device_info().ok) return MOLANN_ERR_CUDA;
+  train_sgd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(tab, flat, lr,
+                                                                                                   (int)total);
   return post_launch();
 }
 

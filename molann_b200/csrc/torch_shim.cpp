@@ -551,6 +551,103 @@ Tensor decode_frames_impl(const Tensor& q, double ox, double oy, double oz, doub
   return x;
 }
 
+// ---- autoencoder training step (include/molann_b200.h: molann_b200_train_*) ----
+struct DecoderHolder {
+  MolannDecoder dec;
+  std::vector<Tensor> keep;
+};
+
+void fill_decoder(DecoderHolder& d, const PlanHolder& h, const Tensor& x, at::TensorList params, int64_t act) {
+  std::memset(&d.dec, 0, sizeof(MolannDecoder));
+  TORCH_CHECK(params.size() >= 2 && params.size() % 2 == 0, "molann_b200: decoder params must be [W1, b1, W2, b2, ...]");
+  const int nl = static_cast<int>(params.size() / 2);
+  TORCH_CHECK(nl <= MOLANN_MAX_LAYERS, "molann_b200: at most ", MOLANN_MAX_LAYERS, " decoder layers are supported");
+  d.dec.n_layers = nl;
+  d.dec.act_id = static_cast<int32_t>(act);
+  d.dec.dims[0] = h.plan.dims[h.plan.n_layers];
+  for (int k = 0; k < nl; ++k) {
+    const Tensor& W = params[2 * k];
+    const Tensor& b = params[2 * k + 1];
+    TORCH_CHECK(W.dim() == 2 && b.dim() == 1 && W.size(0) == b.size(0), "molann_b200: bad decoder Linear shapes at layer ",
+                k + 1);
+    TORCH_CHECK(W.size(1) == d.dec.dims[k], "molann_b200: decoder layer ", k + 1, " expects ", W.size(1),
+                " inputs but receives ", d.dec.dims[k]);
+    TORCH_CHECK(W.device() == x.device() && b.device() == x.device(),
+                "molann_b200: decoder parameters must live on the input's device -- call module.to(device)");
+    TORCH_CHECK(W.scalar_type() == at::kFloat && b.scalar_type() == at::kFloat,
+                "molann_b200: decoder parameters must be float32");
+    d.keep.push_back(W.contiguous());
+    d.keep.push_back(b.contiguous());
+    d.dec.W[k] = d.keep[2 * k].data_ptr<float>();
+    d.dec.b[k] = d.keep[2 * k + 1].data_ptr<float>();
+    d.dec.dims[k + 1] = static_cast<int32_t>(W.size(0));
+  }
+  TORCH_CHECK(d.dec.dims[nl] == h.plan.d_feat, "molann_b200: the decoder must reconstruct the ", h.plan.d_feat,
+              " features, its last layer has ", d.dec.dims[nl], " outputs");
+}
+
+bool train_eligible_impl(const Tensor& x, const Tensor& align_idx, const Tensor& ref_x, const Tensor& entries,
+                         int64_t d_feat, bool use_angle_value, at::TensorList enc_params, int64_t enc_act,
+                         at::TensorList dec_params, int64_t dec_act) {
+  check_x(x, "train_eligible");
+  c10::cuda::CUDAGuard guard(x.device());
+  PlanHolder h;
+  fill_geometry(h, x, align_idx, ref_x);
+  fill_features(h, x, entries, d_feat, use_angle_value);
+  fill_mlp(h, x, enc_params, enc_act);
+  DecoderHolder d;
+  fill_decoder(d, h, x, dec_params, dec_act);
+  return molann_b200_train_eligible(&h.plan, &d.dec) != 0;
+}
+
+// flat[P + 1]: d loss / d (encoder, decoder parameters) in parameter order, then the loss (see the header)
+Tensor train_loss_and_grads_impl(const Tensor& x, const Tensor& align_idx, const Tensor& ref_x, const Tensor& entries,
+                                 int64_t d_feat, bool use_angle_value, at::TensorList enc_params, int64_t enc_act,
+                                 at::TensorList dec_params, int64_t dec_act, double loss_scale) {
+  check_x(x, "train_loss_and_grads");
+  NvtxRange nvtx("molann_b200::train_loss_and_grads");
+  c10::cuda::CUDAGuard guard(x.device());
+  PlanHolder h;
+  fill_geometry(h, x, align_idx, ref_x);
+  fill_features(h, x, entries, d_feat, use_angle_value);
+  fill_mlp(h, x, enc_params, enc_act);
+  DecoderHolder d;
+  fill_decoder(d, h, x, dec_params, dec_act);
+  const size_t P = molann_b200_train_param_count(&h.plan, &d.dec);
+  TORCH_CHECK(P > 0, "molann_b200::train_loss_and_grads: inconsistent encoder / decoder");
+  Tensor flat = at::empty({static_cast<int64_t>(P) + 1}, x.options());
+  const size_t ws_bytes = molann_b200_train_workspace_bytes(&h.plan, &d.dec);
+  Tensor ws = at::empty({static_cast<int64_t>(ws_bytes)}, x.options().dtype(at::kByte));
+  check_status(molann_b200_train_loss_and_grads(&h.plan, &d.dec, x.data_ptr<float>(), x.size(0),
+                                                static_cast<float>(loss_scale), flat.data_ptr<float>(), ws.data_ptr(),
+                                                ws_bytes, cur_stream()),
+               "train_loss_and_grads");
+  return flat;
+}
+
+// params[i] -= lr * flat[offset_i : offset_i + numel_i]   (in place, one launch)
+void sgd_apply_impl(at::TensorList params, const Tensor& flat, double lr) {
+  TORCH_CHECK(flat.is_cuda() && flat.scalar_type() == at::kFloat && flat.is_contiguous(),
+              "molann_b200::sgd_apply_: the flat gradient must be a contiguous float32 CUDA tensor");
+  TORCH_CHECK(params.size() <= 4 * MOLANN_MAX_LAYERS, "molann_b200::sgd_apply_: too many parameter tensors");
+  c10::cuda::CUDAGuard guard(flat.device());
+  std::vector<float*> ptrs;
+  std::vector<int64_t> numel;
+  int64_t total = 0;
+  for (const Tensor& p : params) {
+    TORCH_CHECK(p.device() == flat.device() && p.scalar_type() == at::kFloat && p.is_contiguous(),
+                "molann_b200::sgd_apply_: parameters must be contiguous float32 tensors on the gradient's device");
+    ptrs.push_back(p.data_ptr<float>());
+    numel.push_back(p.numel());
+    total += p.numel();
+  }
+  TORCH_CHECK(total <= flat.numel(), "molann_b200::sgd_apply_: the flat gradient holds ", flat.numel(),
+              " values, the parameters need ", total);
+  check_status(molann_b200_sgd_apply(ptrs.data(), numel.data(), static_cast<int32_t>(ptrs.size()),
+                                     flat.data_ptr<float>(), static_cast<float>(lr), cur_stream()),
+               "sgd_apply");
+}
+
 int64_t launch_count() { return molann_b200_launch_count(); }
 
 }  // namespace
@@ -565,6 +662,12 @@ TORCH_LIBRARY(molann_b200, m) {
   m.def("value_and_jacobian(Tensor x, Tensor align_idx, Tensor ref_x, Tensor entries, int d_feat, "
         "bool use_angle_value, Tensor[] params, int act) -> (Tensor, Tensor)");
   m.def("decode_frames(Tensor q, float ox, float oy, float oz, float resolution) -> Tensor");
+  m.def("train_eligible(Tensor x, Tensor align_idx, Tensor ref_x, Tensor entries, int d_feat, bool use_angle_value, "
+        "Tensor[] enc_params, int enc_act, Tensor[] dec_params, int dec_act) -> bool");
+  m.def("train_loss_and_grads(Tensor x, Tensor align_idx, Tensor ref_x, Tensor entries, int d_feat, "
+        "bool use_angle_value, Tensor[] enc_params, int enc_act, Tensor[] dec_params, int dec_act, float loss_scale) "
+        "-> Tensor");
+  m.def("sgd_apply_(Tensor(a!)[] params, Tensor flat, float lr) -> ()");
   m.def("launch_count() -> int", &launch_count);
 }
 
@@ -575,6 +678,9 @@ TORCH_LIBRARY_IMPL(molann_b200, CUDA, m) {
   m.impl("value_and_grad", &value_and_grad_impl);
   m.impl("value_and_jacobian", &value_and_jacobian_impl);
   m.impl("decode_frames", &decode_frames_impl);
+  m.impl("train_eligible", &train_eligible_impl);
+  m.impl("train_loss_and_grads", &train_loss_and_grads_impl);
+  m.impl("sgd_apply_", &sgd_apply_impl);
 }
 
 TORCH_LIBRARY_IMPL(molann_b200, Autograd, m) {

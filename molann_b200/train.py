@@ -8,10 +8,19 @@ sum-allreduce of all MLP parameter gradients (+ the loss scalar) per step (shard
 GPUs, gloo in the CPU tests).  The encoder forward/backward run through ``molann_b200::molann`` (fused align +
 features + MLP kernels, parameter gradients from the C ABI's ``molann_b200_backward``); the decoder is a plain
 ``torch.nn.Sequential`` (library GEMMs).
+
+When encoder and decoder are both ``create_sequential_nn``-style stacks small enough for the SM (C4 is), the whole
+step is the fused training kernel instead (``molann_b200::train_loss_and_grads``, csrc/fused_train.cuh): forward of
+encoder and decoder, loss, every parameter gradient and the loss in ONE kernel plus a fixed-order reduction, the flat
+result allreduced as it is, and the SGD update in one more launch (``molann_b200::sgd_apply_``) -- no library GEMM,
+no autograd graph.  ``MOLANN_B200_TRAIN_FUSED=0`` keeps the composed path.
 """
+import os
 from typing import Optional
 
 import torch
+
+import torch.distributed as dist
 
 from .shard import allreduce_flat_grads
 
@@ -33,10 +42,68 @@ class AutoencoderStep(object):
         self.lr = float(lr)
         self.global_frames = global_frames
         self.group = group
+        self._fused_args = None
+        self._fused_checked = False
+
+    # ---- the fused training kernel ---------------------------------------------------------------------------------
+    def _fused_call_args(self, x_local):
+        """Arguments of ``molann_b200::train_loss_and_grads`` when the fused kernel serves this pair, else None
+        (decided on the first CUDA batch: the modules must already live on the device)."""
+        if self._fused_checked:
+            return self._fused_args
+        self._fused_checked = True
+        if not x_local.is_cuda or os.environ.get("MOLANN_B200_TRAIN_FUSED", "1") == "0":
+            return None
+        from . import ann as _ann
+        enc, dec = self.encoder, self.decoder
+        if not isinstance(enc, _ann.MolANN) or not enc._fused or not enc._mlp_unchanged():
+            return None
+        dec_act = _ann._fusable_activation(dec)
+        if dec_act < 0:
+            return None
+        enc_params = [t for layer in enc.ann_layers if hasattr(layer, 'weight') for t in (layer.weight, layer.bias)]
+        dec_params = [t for layer in dec if hasattr(layer, 'weight') for t in (layer.weight, layer.bias)]
+        ordered = enc_params + dec_params
+        if len(ordered) != len(self.params) or any(a is not b for a, b in zip(ordered, self.params)):
+            return None                       # frozen or extra parameters: the flat layout would not match
+        if any(not q.is_contiguous() or q.dtype != torch.float32 or q.device != x_local.device for q in ordered):
+            return None
+        pp, flayer = enc.preprocessing_layer, enc.preprocessing_layer.feature_layer
+        if enc._fused_align:
+            geo = (pp.align_layer._align_idx, pp.align_layer.ref_x)
+        else:
+            geo = (flayer._no_idx, flayer._no_ref)
+        args = geo + (flayer._entries, flayer._dim, flayer.use_angle_value, enc_params, enc._act_id, dec_params, dec_act)
+        with torch.no_grad():
+            if not torch.ops.molann_b200.train_eligible(x_local, *[[q.detach() for q in a] if isinstance(a, list) else a
+                                                                   for a in args]):
+                return None
+        self._fused_args = args
+        return args
+
+    def _fused_loss_and_grads(self, x_local, args, n_global):
+        geo0, geo1, entries, d_feat, use_angle, enc_params, enc_act, dec_params, dec_act = args
+        with torch.no_grad():
+            flat = torch.ops.molann_b200.train_loss_and_grads(
+                x_local, geo0, geo1, entries, d_feat, use_angle, [q.detach() for q in enc_params], enc_act,
+                [q.detach() for q in dec_params], dec_act, 1.0 / (float(n_global) * float(d_feat)))
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+                dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+            off = 0
+            for q in self.params:               # gradients are views of the flat buffer: nothing is copied
+                n = q.numel()
+                q.grad = flat[off:off + n].view_as(q)
+                off += n
+        self._flat = flat
+        return flat[off:off + 1]
 
     def loss_and_grads(self, x_local: torch.Tensor) -> torch.Tensor:
         """Forward + backward on this rank's shard, then the single flat allreduce.  Returns the global loss."""
         n_global = self.global_frames if self.global_frames is not None else x_local.shape[0]
+        self._flat = None
+        fused = self._fused_call_args(x_local)
+        if fused is not None:
+            return self._fused_loss_and_grads(x_local, fused, n_global)
         for p in self.params:
             p.grad = None
         with torch.no_grad():
@@ -50,6 +117,9 @@ class AutoencoderStep(object):
     def step(self, x_local: torch.Tensor) -> torch.Tensor:
         loss = self.loss_and_grads(x_local)
         with torch.no_grad():
+            if self._flat is not None:          # fused path: one launch over the flat gradient
+                torch.ops.molann_b200.sgd_apply_([q.detach() for q in self.params], self._flat, self.lr)
+                return loss
             for p in self.params:
                 if p.grad is not None:
                     p.add_(p.grad, alpha=-self.lr)
