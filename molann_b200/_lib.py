@@ -31,6 +31,15 @@ class MolannPlan(ctypes.Structure):
     ]
 
 
+class MolannDecoder(ctypes.Structure):
+    """Mirror of ``struct MolannDecoder`` (include/molann_b200.h)."""
+    _fields_ = [
+        ("n_layers", ctypes.c_int32), ("act_id", ctypes.c_int32),
+        ("dims", ctypes.c_int32 * (MAX_LAYERS + 1)),
+        ("W", ctypes.c_void_p * MAX_LAYERS), ("b", ctypes.c_void_p * MAX_LAYERS),
+    ]
+
+
 _cabi = None
 _ops_loaded = False
 
@@ -81,6 +90,15 @@ def cabi():
     lib.molann_b200_value_and_grad_prepared.argtypes = [vp, P, vp, vp, i64, vp, vp, vp, sz, vp]
     lib.molann_b200_prepared_destroy.restype = None
     lib.molann_b200_prepared_destroy.argtypes = [vp]
+    D = ctypes.POINTER(MolannDecoder)
+    lib.molann_b200_train_eligible.argtypes = [P, D]
+    lib.molann_b200_train_param_count.restype = sz
+    lib.molann_b200_train_param_count.argtypes = [P, D]
+    lib.molann_b200_train_workspace_bytes.restype = sz
+    lib.molann_b200_train_workspace_bytes.argtypes = [P, D]
+    lib.molann_b200_train_loss_and_grads.argtypes = [P, D, vp, i64, ctypes.c_float, vp, vp, sz, vp]
+    lib.molann_b200_sgd_apply.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(i64), ctypes.c_int32, vp, ctypes.c_float,
+                                          vp]
     _cabi = lib
     return lib
 

@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include "geometry.cuh"
 #include "fused_small.cuh"
+#include "tc.cuh"
 
 namespace molann {
 
@@ -42,6 +43,7 @@ struct TrainLayout {               // byte offsets into dynamic shared memory (h
   int act_lo, act_bytes;           // the activation region (zeroed once: padding rows must stay 0)
   int xs_off;                      // coordinate tile, overlays the tail of the activation region
   int aidx_off, ref_off, ent_off, mbar_off, red_off, total_bytes;
+  int fw[TR_MAXL], bw[TR_MAXL], dw[TR_MAXL];   // work shape of each phase of layer l (TR_WIDE ..., TR_DW44 ...)
 };
 
 __device__ __forceinline__ int tr_layer_act(const TrainNet& n, int l) {   // activation applied to layer l's output
@@ -66,9 +68,18 @@ __device__ __forceinline__ float tr_act(float v, int act) {
   return v;
 }
 
-// acc[i][j] += sum_k A[k][f0 + i] * Wn[n0 + j][k]   (four frames x eight outputs, k in steps of four)
+// ---- work shapes -------------------------------------------------------------------------------------------------
+// Every phase between two CTA barriers should keep all eight warps busy, so the register tile of a work item shrinks
+// with the layer: 4 frames x 8 columns while that gives 256 items (width > 56), 4 x 4 below, and for widths <= 4 (the
+// bottleneck, a two-feature FeatureLayer) one thread pair per frame splitting the contraction instead of one warp
+// doing all of it.  The host picks the shape per layer (TrainLayout::fw / bw / dw).
+constexpr int TR_WIDE = 0, TR_HALF = 1, TR_NARROW = 2;              // fw / bw shapes
+constexpr int TR_DW44 = 0, TR_DW42 = 1, TR_DW24 = 2, TR_DW22 = 3, TR_DWTHIN = 4;
+
+// acc[i][j] += sum_k A[k][f0 + i] * Wn[n0 + j][k]   (four frames x NO outputs, k in steps of four)
+template <int NO>
 __device__ __forceinline__ void tr_fwd_acc(const float* __restrict__ A, const float* __restrict__ Wn, int ldk, int K4,
-                                           int f0, int n0, float (&acc)[4][8]) {
+                                           int f0, int n0, float (&acc)[4][NO]) {
   const float* ap = A + f0;
   const float* wp = Wn + n0 * ldk;
 #pragma unroll 2
@@ -78,7 +89,7 @@ __device__ __forceinline__ void tr_fwd_acc(const float* __restrict__ A, const fl
     const float4 a2 = *reinterpret_cast<const float4*>(ap + 2 * TR_FS);
     const float4 a3 = *reinterpret_cast<const float4*>(ap + 3 * TR_FS);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < NO; ++j) {
       const float4 w = *reinterpret_cast<const float4*>(wp + j * ldk + k);
       acc[0][j] = fmaf(a3.x, w.w, fmaf(a2.x, w.z, fmaf(a1.x, w.y, fmaf(a0.x, w.x, acc[0][j]))));
       acc[1][j] = fmaf(a3.y, w.w, fmaf(a2.y, w.z, fmaf(a1.y, w.y, fmaf(a0.y, w.x, acc[1][j]))));
@@ -89,58 +100,79 @@ __device__ __forceinline__ void tr_fwd_acc(const float* __restrict__ A, const fl
   }
 }
 
-// O[n][f] = act(sum_k A[k][f] Wn[n][k] + b[n])
-__device__ __forceinline__ void tr_forward_layer(const float* __restrict__ A, float* __restrict__ O,
-                                                 const float* __restrict__ Wn, const float* __restrict__ bs, int ldk,
-                                                 int K4, int N, int act, int tid) {
-  const int nog = (N + 7) >> 3;
-  for (int item = tid; item < (TR_F / 4) * nog; item += TR_NT) {
-    const int f0 = (item & 31) * 4, n0 = (item >> 5) * 8;
-    float acc[4][8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float bj = bs[n0 + j];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) acc[i][j] = bj;
-    }
-    tr_fwd_acc(A, Wn, ldk, K4, f0, n0, acc);
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (n0 + j < N)
-        *reinterpret_cast<float4*>(O + (n0 + j) * TR_FS + f0) =
-            make_float4(tr_act(acc[0][j], act), tr_act(acc[1][j], act), tr_act(acc[2][j], act), tr_act(acc[3][j], act));
-  }
-}
-
-// last layer: residual against the features, squared error (valid frames only) and the loss cotangent
-__device__ __forceinline__ float tr_last_layer(const float* __restrict__ A, const float* __restrict__ feat,
-                                               float* __restrict__ G, const float* __restrict__ Wn,
-                                               const float* __restrict__ bs, int ldk, int K4, int N, int nf,
-                                               float two_scale, int tid) {
-  const int nog = (N + 7) >> 3;
+// O[n][f] = act(sum_k A[k][f] Wn[n][k] + b[n]);  LAST: instead the residual against the features `feat`, the squared
+// error of the valid frames (returned) and the loss cotangent two_scale * residual written to O
+template <int NO, bool LAST>
+__device__ __forceinline__ float tr_forward_layer(const float* __restrict__ A, float* __restrict__ O,
+                                                  const float* __restrict__ Wn, const float* __restrict__ bs, int ldk,
+                                                  int K4, int N, int act, const float* __restrict__ feat, int nf,
+                                                  float two_scale, int tid) {
+  const int nog = (N + NO - 1) / NO;
   float sq = 0.f;
   for (int item = tid; item < (TR_F / 4) * nog; item += TR_NT) {
-    const int f0 = (item & 31) * 4, n0 = (item >> 5) * 8;
-    float acc[4][8];
+    const int f0 = (item & 31) * 4, n0 = (item >> 5) * NO;
+    float acc[4][NO];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < NO; ++j) {
       const float bj = bs[n0 + j];
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[i][j] = bj;
     }
-    tr_fwd_acc(A, Wn, ldk, K4, f0, n0, acc);
+    tr_fwd_acc<NO>(A, Wn, ldk, K4, f0, n0, acc);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < NO; ++j) {
       if (n0 + j < N) {
-        const float4 t = *reinterpret_cast<const float4*>(feat + (n0 + j) * TR_FS + f0);
-        float e[4] = {acc[0][j] - t.x, acc[1][j] - t.y, acc[2][j] - t.z, acc[3][j] - t.w};
+        float4* dst = reinterpret_cast<float4*>(O + (n0 + j) * TR_FS + f0);
+        if (LAST) {
+          const float4 t = *reinterpret_cast<const float4*>(feat + (n0 + j) * TR_FS + f0);
+          float e[4] = {acc[0][j] - t.x, acc[1][j] - t.y, acc[2][j] - t.z, acc[3][j] - t.w};
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          if (f0 + i >= nf) e[i] = 0.f;
-          sq = fmaf(e[i], e[i], sq);
-          e[i] *= two_scale;
+          for (int i = 0; i < 4; ++i) {
+            if (f0 + i >= nf) e[i] = 0.f;
+            sq = fmaf(e[i], e[i], sq);
+            e[i] *= two_scale;
+          }
+          *dst = make_float4(e[0], e[1], e[2], e[3]);
+        } else {
+          *dst = make_float4(tr_act(acc[0][j], act), tr_act(acc[1][j], act), tr_act(acc[2][j], act),
+                             tr_act(acc[3][j], act));
         }
-        *reinterpret_cast<float4*>(G + (n0 + j) * TR_FS + f0) = make_float4(e[0], e[1], e[2], e[3]);
+      }
+    }
+  }
+  return sq;
+}
+
+// the same layer for N <= 4: thread pair (f, kh) per frame, kh takes every other chunk of four k (rows 4 TR_FS apart
+// are 16 banks apart: the two halves of a warp never collide), the pair is summed by one shuffle
+template <bool LAST>
+__device__ __forceinline__ float tr_forward_narrow(const float* __restrict__ A, float* __restrict__ O,
+                                                   const float* __restrict__ Wn, const float* __restrict__ bs, int ldk,
+                                                   int K4, int N, int act, const float* __restrict__ feat, int nf,
+                                                   float two_scale, int tid) {
+  const int f = tid >> 1, kh = tid & 1;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int k = 4 * kh; k < K4; k += 8) {
+    const float a0 = A[k * TR_FS + f], a1 = A[(k + 1) * TR_FS + f], a2 = A[(k + 2) * TR_FS + f],
+                a3 = A[(k + 3) * TR_FS + f];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 w = *reinterpret_cast<const float4*>(Wn + j * ldk + k);     // rows up to round8(N) exist (zeros)
+      acc[j] = fmaf(a3, w.w, fmaf(a2, w.z, fmaf(a1, w.y, fmaf(a0, w.x, acc[j]))));
+    }
+  }
+  float sq = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float v = acc[j] + __shfl_xor_sync(0xffffffffu, acc[j], 1) + bs[j];
+    if (j < N && (j & 1) == kh) {
+      if (LAST) {
+        float e = v - feat[j * TR_FS + f];
+        if (f >= nf) e = 0.f;
+        sq = fmaf(e, e, sq);
+        O[j * TR_FS + f] = e * two_scale;
+      } else {
+        O[j * TR_FS + f] = tr_act(v, act);
       }
     }
   }
@@ -148,27 +180,31 @@ __device__ __forceinline__ float tr_last_layer(const float* __restrict__ A, cons
 }
 
 // IO[i][f] = (sum_o GZ[o][f] Wn[o][i]) * act'(IO[i][f])   -- in place on the layer input
+template <int NI>
 __device__ __forceinline__ void tr_backward_layer(const float* __restrict__ GZ, float* __restrict__ IO,
                                                   const float* __restrict__ Wn, int ldk, int N, int K, int act_prev,
                                                   int tid) {
-  const int nig = (K + 7) >> 3;
+  const int nig = (K + NI - 1) / NI;
   for (int item = tid; item < (TR_F / 4) * nig; item += TR_NT) {
-    const int f0 = (item & 31) * 4, i0 = (item >> 5) * 8;
-    float acc[4][8];
+    const int f0 = (item & 31) * 4, i0 = (item >> 5) * NI;
+    float acc[4][NI];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+      for (int j = 0; j < NI; ++j) acc[i][j] = 0.f;
     const float* gp = GZ + f0;
     const float* wp = Wn + i0;
 #pragma unroll 4
     for (int o = 0; o < N; ++o) {
       const float4 g = *reinterpret_cast<const float4*>(gp);
-      const float4 w0 = *reinterpret_cast<const float4*>(wp);
-      const float4 w1 = *reinterpret_cast<const float4*>(wp + 4);
-      const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+      float w[NI];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int q = 0; q < NI / 4; ++q) {
+        const float4 wq = *reinterpret_cast<const float4*>(wp + 4 * q);
+        w[4 * q] = wq.x; w[4 * q + 1] = wq.y; w[4 * q + 2] = wq.z; w[4 * q + 3] = wq.w;
+      }
+#pragma unroll
+      for (int j = 0; j < NI; ++j) {
         acc[0][j] = fmaf(g.x, w[j], acc[0][j]);
         acc[1][j] = fmaf(g.y, w[j], acc[1][j]);
         acc[2][j] = fmaf(g.z, w[j], acc[2][j]);
@@ -178,7 +214,7 @@ __device__ __forceinline__ void tr_backward_layer(const float* __restrict__ GZ, 
       wp += ldk;
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < NI; ++j) {
       if (i0 + j < K) {
         float4* p = reinterpret_cast<float4*>(IO + (i0 + j) * TR_FS + f0);
         const float4 h = *p;
@@ -189,61 +225,149 @@ __device__ __forceinline__ void tr_backward_layer(const float* __restrict__ GZ, 
   }
 }
 
-// dW[o][i] += sum_f GZ[o][f] A[i][f],  db[o] += sum_f GZ[o][f].  A thread owns rows o = to + TO r and i = ti + TI r
-// (r < 4, interleaved so that the eight `to` of a warp read eight different bank quads); a warp covers 8 x 4 threads.
+// the same for K <= 4 (the cotangent of the bottleneck): thread pair (f, oh), oh takes every other chunk of four o
+__device__ __forceinline__ void tr_backward_narrow(const float* __restrict__ GZ, float* __restrict__ IO,
+                                                   const float* __restrict__ Wn, int ldk, int N, int K, int act_prev,
+                                                   int tid) {
+  const int f = tid >> 1, oh = tid & 1;
+  const int N4 = round_up(N, 4);                      // GZ rows and W rows up to N4 exist and are zero
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int o = 4 * oh; o < N4; o += 8) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const float g = GZ[(o + r) * TR_FS + f];
+      const float4 w = *reinterpret_cast<const float4*>(Wn + (o + r) * ldk);
+      acc[0] = fmaf(g, w.x, acc[0]);
+      acc[1] = fmaf(g, w.y, acc[1]);
+      acc[2] = fmaf(g, w.z, acc[2]);
+      acc[3] = fmaf(g, w.w, acc[3]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float v = acc[j] + __shfl_xor_sync(0xffffffffu, acc[j], 1);
+    if (j < K && (j & 1) == oh) {
+      float* p = IO + j * TR_FS + f;
+      *p = v * act_grad_from_output(*p, act_prev);
+    }
+  }
+}
+
+// dW[o][i] += sum_f GZ[o][f] A[i][f],  db[o] += sum_f GZ[o][f].  A thread owns rows o = to + TO r (r < RO) and
+// i = ti + TI r (r < RI), interleaved so that the eight `to` of a warp read eight different bank quads; a warp covers
+// 8 x 4 threads.  The contraction runs on the packed fp32 pipe: the (even frame, odd frame) partial sums of one
+// dW[o][i] share a register pair, both operands of an FFMA2 are the natural pairs of the float4 rows.
 // The running sums live in this CTA's plane of the workspace; nobody else touches it.
+template <int RO, int RI>
 __device__ __forceinline__ void tr_dw_layer(const float* __restrict__ GZ, const float* __restrict__ A, int N, int K,
                                             float* __restrict__ pw, float* __restrict__ pb, bool first, int tid) {
-  const int TO = (N + 3) >> 2, TI = (K + 3) >> 2;
+  const int TO = (N + RO - 1) / RO, TI = (K + RI - 1) / RI;
   const int nbo = (TO + 7) >> 3, nbi = (TI + 3) >> 2;
   const int warp = tid >> 5, lane = tid & 31;
   for (int blk = warp; blk < nbo * nbi; blk += TR_NT / 32) {
     const int to = (blk % nbo) * 8 + (lane & 7), ti = (blk / nbo) * 4 + (lane >> 3);
     if (to >= TO || ti >= TI) continue;
     const bool with_bias = (ti == 0);
-    float acc[4][4], sb[4];
+    unsigned long long acc[RO][RI], sb[RO];
 #pragma unroll
-    for (int ro = 0; ro < 4; ++ro) {
+    for (int ro = 0; ro < RO; ++ro) {
       const int o = to + TO * ro;
-      sb[ro] = (with_bias && !first && o < N) ? __ldcg(pb + o) : 0.f;
+      sb[ro] = f2_pack((with_bias && !first && o < N) ? __ldcg(pb + o) : 0.f, 0.f);
 #pragma unroll
-      for (int ri = 0; ri < 4; ++ri) {
+      for (int ri = 0; ri < RI; ++ri) {
         const int i = ti + TI * ri;
-        acc[ro][ri] = (!first && o < N && i < K) ? __ldcg(pw + o * K + i) : 0.f;
+        acc[ro][ri] = f2_pack((!first && o < N && i < K) ? __ldcg(pw + o * K + i) : 0.f, 0.f);
       }
     }
-    const float* gp = GZ + to * TR_FS;
-    const float* ap = A + ti * TR_FS;
-    const int gstep = TO * TR_FS, astep = TI * TR_FS;
+    // rows past the layer's width are read as whatever follows them; clamp to a valid row (their sums are dropped)
+    const float* gp[RO];
+    const float* ap[RI];
+#pragma unroll
+    for (int r = 0; r < RO; ++r) gp[r] = GZ + (to + TO * r < N ? to + TO * r : to) * TR_FS;
+#pragma unroll
+    for (int r = 0; r < RI; ++r) ap[r] = A + (ti + TI * r < K ? ti + TI * r : ti) * TR_FS;
 #pragma unroll 2
     for (int fq = 0; fq < TR_F; fq += 4) {
-      float4 g[4], a[4];
+      ulonglong2 g[RO], a[RI];
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        g[r] = *reinterpret_cast<const float4*>(gp + r * gstep + fq);
-        a[r] = *reinterpret_cast<const float4*>(ap + r * astep + fq);
-      }
+      for (int r = 0; r < RO; ++r) g[r] = *reinterpret_cast<const ulonglong2*>(gp[r] + fq);
 #pragma unroll
-      for (int ro = 0; ro < 4; ++ro)
+      for (int r = 0; r < RI; ++r) a[r] = *reinterpret_cast<const ulonglong2*>(ap[r] + fq);
 #pragma unroll
-        for (int ri = 0; ri < 4; ++ri)
-          acc[ro][ri] = fmaf(g[ro].w, a[ri].w, fmaf(g[ro].z, a[ri].z, fmaf(g[ro].y, a[ri].y, fmaf(g[ro].x, a[ri].x, acc[ro][ri]))));
+      for (int ro = 0; ro < RO; ++ro)
+#pragma unroll
+        for (int ri = 0; ri < RI; ++ri)
+          acc[ro][ri] = f2_fma(g[ro].y, a[ri].y, f2_fma(g[ro].x, a[ri].x, acc[ro][ri]));
       if (with_bias) {
 #pragma unroll
-        for (int ro = 0; ro < 4; ++ro) sb[ro] += (g[ro].x + g[ro].y) + (g[ro].z + g[ro].w);
+        for (int ro = 0; ro < RO; ++ro) sb[ro] = f2_add(f2_add(sb[ro], g[ro].x), g[ro].y);
       }
     }
 #pragma unroll
-    for (int ro = 0; ro < 4; ++ro) {
+    for (int ro = 0; ro < RO; ++ro) {
       const int o = to + TO * ro;
       if (o < N) {
-        if (with_bias) __stcg(pb + o, sb[ro]);
+        float lo, hi;
+        if (with_bias) {
+          f2_unpack(sb[ro], lo, hi);
+          __stcg(pb + o, lo + hi);
+        }
 #pragma unroll
-        for (int ri = 0; ri < 4; ++ri) {
+        for (int ri = 0; ri < RI; ++ri) {
           const int i = ti + TI * ri;
-          if (i < K) __stcg(pw + o * K + i, acc[ro][ri]);
+          f2_unpack(acc[ro][ri], lo, hi);
+          if (i < K) __stcg(pw + o * K + i, lo + hi);
         }
       }
+    }
+  }
+}
+
+// the same for min(N, K) <= 4: one thread per row w of the wide side contracts it with the (at most four) rows of the
+// thin side over all frames; the thin rows are warp-wide broadcasts
+__device__ __forceinline__ void tr_dw_thin(const float* __restrict__ GZ, const float* __restrict__ A, int N, int K,
+                                           float* __restrict__ pw, float* __restrict__ pb, bool first, int tid) {
+  const bool n_thin = N <= K;                          // thin rows come from GZ (outputs), wide rows from A -- or not
+  const float* thin = n_thin ? GZ : A;
+  const float* wide = n_thin ? A : GZ;
+  const int T = n_thin ? N : K, Wd = n_thin ? K : N;
+  for (int w = tid; w < Wd; w += TR_NT) {
+    unsigned long long acc[4], sb = f2_pack(0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) acc[r] = f2_pack(0.f, 0.f);
+    const float* wp = wide + w * TR_FS;
+#pragma unroll 2
+    for (int fq = 0; fq < TR_F; fq += 4) {
+      const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(wp + fq);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {                    // rows up to round4(T) exist (zeros)
+        const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(thin + r * TR_FS + fq);
+        acc[r] = f2_fma(v.y, t.y, f2_fma(v.x, t.x, acc[r]));
+      }
+      sb = f2_add(f2_add(sb, v.x), v.y);
+    }
+    float lo, hi;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      if (r < T) {
+        float* q = n_thin ? pw + r * K + w : pw + w * K + r;
+        f2_unpack(acc[r], lo, hi);
+        __stcg(q, (first ? 0.f : __ldcg(q)) + (lo + hi));
+      }
+    }
+    if (!n_thin) {                                     // wide rows are the outputs: their frame sums are db
+      f2_unpack(sb, lo, hi);
+      __stcg(pb + w, (first ? 0.f : __ldcg(pb + w)) + (lo + hi));
+    }
+  }
+  if (n_thin && tid >= TR_NT - 32) {                   // db of the thin outputs: the last warp, one row at a time
+    const int lane = tid & 31;
+    for (int r = 0; r < T; ++r) {
+      const float4 v = *reinterpret_cast<const float4*>(thin + r * TR_FS + 4 * lane);
+      float s = (v.x + v.y) + (v.z + v.w);
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+      if (lane == 0) __stcg(pb + r, (first ? 0.f : __ldcg(pb + r)) + s);
     }
   }
 }
@@ -300,7 +424,6 @@ fused_train_kernel(const __grid_constant__ DevPlan p, const __grid_constant__ Tr
   uint32_t phase = 0;
   float sq = 0.f;
   float* feat = reinterpret_cast<float*>(smem + lay.a_off[0]);
-  float* gout = reinterpret_cast<float*>(smem + lay.a_off[net.nl]);
 
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const bool first = (tile == (long long)blockIdx.x);
@@ -343,14 +466,19 @@ fused_train_kernel(const __grid_constant__ DevPlan p, const __grid_constant__ Tr
     // ---- forward through encoder and decoder ----
     for (int l = 0; l < net.nl; ++l) {
       const float* A = reinterpret_cast<const float*>(smem + lay.a_off[l]);
+      float* O = reinterpret_cast<float*>(smem + lay.a_off[l + 1]);
       const float* Wn = reinterpret_cast<const float*>(smem + lay.w_off[l]);
       const float* bs = reinterpret_cast<const float*>(smem + lay.b_off[l]);
-      const int K4 = round_up(net.c[l], 4), N = net.c[l + 1];
+      const int K4 = round_up(net.c[l], 4), N = net.c[l + 1], ld = lay.ldk[l], act = tr_layer_act(net, l);
+      const int shape = lay.fw[l];
       if (l < net.nl - 1) {
-        tr_forward_layer(A, reinterpret_cast<float*>(smem + lay.a_off[l + 1]), Wn, bs, lay.ldk[l], K4, N,
-                         tr_layer_act(net, l), tid);
+        if (shape == TR_WIDE) tr_forward_layer<8, false>(A, O, Wn, bs, ld, K4, N, act, feat, nf, two_scale, tid);
+        else if (shape == TR_HALF) tr_forward_layer<4, false>(A, O, Wn, bs, ld, K4, N, act, feat, nf, two_scale, tid);
+        else tr_forward_narrow<false>(A, O, Wn, bs, ld, K4, N, act, feat, nf, two_scale, tid);
       } else {
-        sq += tr_last_layer(A, feat, gout, Wn, bs, lay.ldk[l], K4, N, nf, two_scale, tid);
+        if (shape == TR_WIDE) sq += tr_forward_layer<8, true>(A, O, Wn, bs, ld, K4, N, act, feat, nf, two_scale, tid);
+        else if (shape == TR_HALF) sq += tr_forward_layer<4, true>(A, O, Wn, bs, ld, K4, N, act, feat, nf, two_scale, tid);
+        else sq += tr_forward_narrow<true>(A, O, Wn, bs, ld, K4, N, act, feat, nf, two_scale, tid);
       }
       __syncthreads();
     }
@@ -359,11 +487,22 @@ fused_train_kernel(const __grid_constant__ DevPlan p, const __grid_constant__ Tr
       const float* GZ = reinterpret_cast<const float*>(smem + lay.a_off[l + 1]);
       float* A = reinterpret_cast<float*>(smem + lay.a_off[l]);
       const int K = net.c[l], N = net.c[l + 1];
-      tr_dw_layer(GZ, A, N, K, plane + net.gw[l], plane + net.gb[l], first, tid);
+      float* pw = plane + net.gw[l];
+      float* pb = plane + net.gb[l];
+      switch (lay.dw[l]) {
+        case TR_DW44: tr_dw_layer<4, 4>(GZ, A, N, K, pw, pb, first, tid); break;
+        case TR_DW42: tr_dw_layer<4, 2>(GZ, A, N, K, pw, pb, first, tid); break;
+        case TR_DW24: tr_dw_layer<2, 4>(GZ, A, N, K, pw, pb, first, tid); break;
+        case TR_DW22: tr_dw_layer<2, 2>(GZ, A, N, K, pw, pb, first, tid); break;
+        default: tr_dw_thin(GZ, A, N, K, pw, pb, first, tid); break;
+      }
       if (l > 0) {
         __syncthreads();
-        tr_backward_layer(GZ, A, reinterpret_cast<const float*>(smem + lay.w_off[l]), lay.ldk[l], N, K,
-                          tr_layer_act(net, l - 1), tid);
+        const float* Wn = reinterpret_cast<const float*>(smem + lay.w_off[l]);
+        const int act_prev = tr_layer_act(net, l - 1);
+        if (lay.bw[l] == TR_WIDE) tr_backward_layer<8>(GZ, A, Wn, lay.ldk[l], N, K, act_prev, tid);
+        else if (lay.bw[l] == TR_HALF) tr_backward_layer<4>(GZ, A, Wn, lay.ldk[l], N, K, act_prev, tid);
+        else tr_backward_narrow(GZ, A, Wn, lay.ldk[l], N, K, act_prev, tid);
       }
       __syncthreads();
     }

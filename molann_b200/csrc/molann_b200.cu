@@ -1956,6 +1956,25 @@ TrainChoice choose_train(const MolannPlan* enc, const MolannDecoder* dec, const 
     off += (long long)round_up(n.c[l + 1], 8) * 4;
     if (off > (1ll << 24)) return tc;
   }
+  // work shapes (fused_train.cuh): keep all eight warps busy in every phase
+  for (int l = 0; l < n.nl; ++l) {
+    const int K = n.c[l], N = n.c[l + 1];
+    lay.fw[l] = N <= 4 ? TR_NARROW : (N > 56 ? TR_WIDE : TR_HALF);
+    lay.bw[l] = K <= 4 ? TR_NARROW : (K > 56 ? TR_WIDE : TR_HALF);
+    lay.dw[l] = TR_DW22;
+    if (N <= 4 || K <= 4) {
+      lay.dw[l] = TR_DWTHIN;
+    } else {
+      const int ro[3] = {4, 4, 2}, ri[3] = {4, 2, 4}, mode[3] = {TR_DW44, TR_DW42, TR_DW24};
+      for (int c = 0; c < 3; ++c) {
+        const int TO = (N + ro[c] - 1) / ro[c], TI = (K + ri[c] - 1) / ri[c];
+        if (((TO + 7) / 8) * ((TI + 3) / 4) >= TR_NT / 32) {
+          lay.dw[l] = mode[c];
+          break;
+        }
+      }
+    }
+  }
   off = (off + 15) / 16 * 16;
   lay.aidx_off = (int)off; off += (long long)round_up(enc->n_align > 0 ? enc->n_align : 1, 4) * 4;
   lay.ref_off = (int)off; off += (long long)round_up(3 * (enc->n_align > 0 ? enc->n_align : 1), 4) * 4;

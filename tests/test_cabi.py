@@ -117,3 +117,42 @@ def test_compute_entry_points_fail_without_gpu():
     assert lib.molann_b200_forward(ctypes.byref(p), 0x10001, 8, 0x20000, None, 0, None) == 4
     q = host_plan(S.get_spec("C2"), n_layers=0)
     assert lib.molann_b200_forward(ctypes.byref(q), 0x10000, 8, 0x20000, None, 0, None) == 6
+
+
+def host_decoder(dims, act_id=0):
+    d = _lib.MolannDecoder()
+    d.n_layers, d.act_id = len(dims) - 1, act_id
+    for k, v in enumerate(dims):
+        d.dims[k] = v
+    for k in range(len(dims) - 1):
+        d.W[k], d.b[k] = 0xA000 + k * 0x100, 0xB000 + k * 0x100
+    return d
+
+
+def test_training_entry_points_validate_on_host():
+    """molann_b200_train_* (include/molann_b200.h): scalar validation and the flat layout need no GPU; compute fails
+    with MOLANN_ERR_CUDA here, never with a CPU result."""
+    lib = _lib.cabi()
+    assert ctypes.sizeof(_lib.MolannDecoder) == 8 + 36 + 4 + 64 + 64
+    enc = host_plan(S.get_spec("C2"))
+    dec = host_decoder([2, 64, 64, 30])
+    P = (30 + 1) * 64 + (64 + 1) * 64 + (64 + 1) * 2 + (2 + 1) * 64 + (64 + 1) * 64 + (64 + 1) * 30
+    assert lib.molann_b200_train_param_count(ctypes.byref(enc), ctypes.byref(dec)) == P == 12576
+    assert lib.molann_b200_train_param_count(ctypes.byref(enc), None) == 0
+    assert lib.molann_b200_train_param_count(ctypes.byref(enc), ctypes.byref(host_decoder([3, 64, 30]))) == 0
+    assert lib.molann_b200_train_param_count(ctypes.byref(enc), ctypes.byref(host_decoder([2, 64, 29]))) == 0
+    assert lib.molann_b200_train_eligible(ctypes.byref(enc), ctypes.byref(dec)) == 0        # no device here
+    a = (0x10000, 128, ctypes.c_float(1.0), 0x20000, 0x30000, 1 << 30, None)
+    assert lib.molann_b200_train_loss_and_grads(ctypes.byref(enc), ctypes.byref(dec), *a) == 5
+    assert lib.molann_b200_train_loss_and_grads(ctypes.byref(enc), None, *a) == 1
+    assert lib.molann_b200_train_loss_and_grads(ctypes.byref(enc), ctypes.byref(host_decoder([3, 64, 30])), *a) == 2
+    assert lib.molann_b200_train_loss_and_grads(ctypes.byref(enc), ctypes.byref(dec), 0x10000, 128,
+                                                ctypes.c_float(1.0), None, 0x30000, 1 << 30, None) == 1
+    assert lib.molann_b200_train_loss_and_grads(ctypes.byref(enc), ctypes.byref(dec), 0x10000, 128,
+                                                ctypes.c_float(1.0), 0x20002, 0x30000, 1 << 30, None) == 4
+    ptrs = (ctypes.c_void_p * 2)(0x1000, 0x2000)
+    numel = (ctypes.c_int64 * 2)(4, 4)
+    assert lib.molann_b200_sgd_apply(ptrs, numel, 0, 0x3000, ctypes.c_float(0.1), None) == 0     # nothing to do
+    assert lib.molann_b200_sgd_apply(None, numel, 2, 0x3000, ctypes.c_float(0.1), None) == 1
+    assert lib.molann_b200_sgd_apply(ptrs, numel, 99, 0x3000, ctypes.c_float(0.1), None) == 2
+    assert lib.molann_b200_sgd_apply(ptrs, numel, 2, 0x3000, ctypes.c_float(0.1), None) == 5
