@@ -411,9 +411,13 @@ def run_training(args, rank, local_rank, world):
                    "parallelism": "data-parallel x%d, one flat sum-allreduce of %d floats per step (NCCL)"
                                   % (world, nparam + 1)},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src,
-                     "note": "per GPU, algorithmic 12*n_inp bytes per frame; the step is compute/launch bound "
-                             "(74 kFLOP per frame incl. weight gradients), see DESIGN.md"},
+                     "traffic": (ncu_traffic("C4", "train") if (hi - lo) == C4_GLOBAL and trainer._fused_args else None),
+                     "peak_source": peak_src,
+                     "note": "per GPU, algorithmic 12*n_inp bytes per frame; the step is FMA / shared-memory bound "
+                             "(74 kFLOP per frame incl. weight gradients: %.1f TFLOP/s fp32 per GPU), see DESIGN.md 3.8"
+                             % (value * 74e3 / world / 1e12)},
+        "train_path": ("fused_train_kernel (one kernel per step + plane reduction + SGD launch)"
+                       if trainer._fused_args else "composed (fused encoder kernels + library decoder)"),
         "gpu_launches": int(launches), "allreduce_ms": ar_ms, "final_loss": float(loss), "clocks": clocks,
         "cuda_graph": {"used": graphed, "eager_ms_per_step": ms_eager / K,
                        "note": "value is the graph replay when used (one launch per step replays gpu_launches / steps "

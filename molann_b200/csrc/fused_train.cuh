@@ -268,15 +268,19 @@ __device__ __forceinline__ void tr_dw_layer(const float* __restrict__ GZ, const 
     const int to = (blk % nbo) * 8 + (lane & 7), ti = (blk / nbo) * 4 + (lane >> 3);
     if (to >= TO || ti >= TI) continue;
     const bool with_bias = (ti == 0);
+    // the running sums are fetched now and only needed after the frame loop: their L2 latency hides behind it
     unsigned long long acc[RO][RI], sb[RO];
+    float oldw[RO][RI], oldb[RO];
 #pragma unroll
     for (int ro = 0; ro < RO; ++ro) {
       const int o = to + TO * ro;
-      sb[ro] = f2_pack((with_bias && !first && o < N) ? __ldcg(pb + o) : 0.f, 0.f);
+      oldb[ro] = (with_bias && !first && o < N) ? __ldcg(pb + o) : 0.f;
+      sb[ro] = f2_pack(0.f, 0.f);
 #pragma unroll
       for (int ri = 0; ri < RI; ++ri) {
         const int i = ti + TI * ri;
-        acc[ro][ri] = f2_pack((!first && o < N && i < K) ? __ldcg(pw + o * K + i) : 0.f, 0.f);
+        oldw[ro][ri] = (!first && o < N && i < K) ? __ldcg(pw + o * K + i) : 0.f;
+        acc[ro][ri] = f2_pack(0.f, 0.f);
       }
     }
     // rows past the layer's width are read as whatever follows them; clamp to a valid row (their sums are dropped)
@@ -310,13 +314,13 @@ __device__ __forceinline__ void tr_dw_layer(const float* __restrict__ GZ, const 
         float lo, hi;
         if (with_bias) {
           f2_unpack(sb[ro], lo, hi);
-          __stcg(pb + o, lo + hi);
+          __stcg(pb + o, oldb[ro] + (lo + hi));
         }
 #pragma unroll
         for (int ri = 0; ri < RI; ++ri) {
           const int i = ti + TI * ri;
           f2_unpack(acc[ro][ri], lo, hi);
-          if (i < K) __stcg(pw + o * K + i, lo + hi);
+          if (i < K) __stcg(pw + o * K + i, oldw[ro][ri] + (lo + hi));
         }
       }
     }
