@@ -75,6 +75,7 @@ __device__ __forceinline__ float tr_act(float v, int act) {
 // doing all of it.  The host picks the shape per layer (TrainLayout::fw / bw / dw).
 constexpr int TR_WIDE = 0, TR_HALF = 1, TR_NARROW = 2;              // fw / bw shapes
 constexpr int TR_DW44 = 0, TR_DW42 = 1, TR_DW24 = 2, TR_DW22 = 3, TR_DWTHIN = 4;
+constexpr int TR_DWB88 = 5, TR_DWB84 = 6, TR_DWB48 = 7, TR_DWB44 = 8;   // large tiles over frame quarters (tr_dw_big)
 
 // acc[i][j] += sum_k A[k][f0 + i] * Wn[n0 + j][k]   (four frames x NO outputs, k in steps of four)
 template <int NO>
@@ -327,6 +328,91 @@ __device__ __forceinline__ void tr_dw_layer(const float* __restrict__ GZ, const 
   }
 }
 
+// The large-tile form of the same phase (layers at least ~ 28 wide on both sides, K <= 8 RI).  The contractions are
+// bound by the bytes shared memory returns to the register file (profiles/r5_train_ab.txt), i.e. by FMAs per loaded
+// float: an RO x RI = 8 x 8 tile needs half the loads of a 4 x 4 one.  To keep every lane busy with tiles that large the
+// four lane octets of a warp take the four frame quarters of the tile: lane = (t, q), columns i = t + TI r (r < RI)
+// over frames [32 q, 32 q + 32); warp w owns the row groups wo = w, w + 8, ... (o = wo + TO r, r < RO; its GZ rows
+// are warp-wide broadcasts).  The four partial sums of a dW entry meet by recursive halving over the two lane bits of q
+// (RO RI / 2 + RO RI / 4 shuffles instead of 2 RO RI), after which every lane holds RO RI / 4 finished entries; the
+// eight t-lanes of an octet hold eight consecutive columns of a dW row, one 32-byte sector of the plane.
+template <int RO, int RI>
+__device__ __forceinline__ void tr_dw_big(const float* __restrict__ GZ, const float* __restrict__ A, int N, int K,
+                                          float* __restrict__ pw, float* __restrict__ pb, bool first, int tid) {
+  constexpr int V = RO * RI;
+  const int TO = (N + RO - 1) / RO, TI = (K + RI - 1) / RI;      // TI <= 8 (host)
+  const int warp = tid >> 5, lane = tid & 31, t = lane & 7, q = lane >> 3;
+  const bool col_ok = t < TI;
+  const bool hi2 = (q & 2) != 0, hi1 = (q & 1) != 0;
+  const int base = (hi2 ? V / 2 : 0) + (hi1 ? V / 4 : 0);       // first of the V / 4 entries this lane finishes
+  const float* ap[RI];
+#pragma unroll
+  for (int r = 0; r < RI; ++r) ap[r] = A + ((col_ok && t + TI * r < K) ? t + TI * r : 0) * TR_FS + 32 * q;
+  for (int wo = warp; wo < TO; wo += TR_NT / 32) {
+    float acc[V], sb[RO];
+#pragma unroll
+    for (int v = 0; v < V; ++v) acc[v] = 0.f;
+#pragma unroll
+    for (int r = 0; r < RO; ++r) sb[r] = 0.f;
+    const float* gp[RO];
+#pragma unroll
+    for (int r = 0; r < RO; ++r) gp[r] = GZ + (wo + TO * r < N ? wo + TO * r : wo) * TR_FS + 32 * q;
+#pragma unroll 1
+    for (int fq = 0; fq < 32; fq += 4) {
+      float4 g[RO], a[RI];
+#pragma unroll
+      for (int r = 0; r < RO; ++r) g[r] = *reinterpret_cast<const float4*>(gp[r] + fq);
+#pragma unroll
+      for (int r = 0; r < RI; ++r) a[r] = *reinterpret_cast<const float4*>(ap[r] + fq);
+#pragma unroll
+      for (int ro = 0; ro < RO; ++ro) {
+#pragma unroll
+        for (int ri = 0; ri < RI; ++ri)
+          acc[ro * RI + ri] = fmaf(g[ro].w, a[ri].w, fmaf(g[ro].z, a[ri].z, fmaf(g[ro].y, a[ri].y,
+                                   fmaf(g[ro].x, a[ri].x, acc[ro * RI + ri]))));
+        sb[ro] += (g[ro].x + g[ro].y) + (g[ro].z + g[ro].w);
+      }
+    }
+    // the running sums of this lane's final entries: issued now, needed after the shuffles (the cache-hinted accesses
+    // are volatile asm -- interleaved with the stores each would wait a full L2 round trip)
+    float oldv[V / 4], oldb[RO];
+#pragma unroll
+    for (int v = 0; v < V / 4; ++v) {
+      const int idx = base + v, o = wo + TO * (idx / RI), i = t + TI * (idx % RI);
+      oldv[v] = (!first && col_ok && o < N && i < K) ? __ldcg(pw + o * K + i) : 0.f;
+    }
+#pragma unroll
+    for (int ro = 0; ro < RO; ++ro) {
+      const int o = wo + TO * ro;
+      oldb[ro] = (!first && lane == 0 && o < N) ? __ldcg(pb + o) : 0.f;
+    }
+    // frame quarters meet: xor 16 halves the entries a lane is responsible for, xor 8 halves them again
+    float h1[V / 2], h2[V / 4];
+#pragma unroll
+    for (int v = 0; v < V / 2; ++v) {
+      const float mine = hi2 ? acc[v + V / 2] : acc[v], other = hi2 ? acc[v] : acc[v + V / 2];
+      h1[v] = mine + __shfl_xor_sync(0xffffffffu, other, 16);
+    }
+#pragma unroll
+    for (int v = 0; v < V / 4; ++v) {
+      const float mine = hi1 ? h1[v + V / 4] : h1[v], other = hi1 ? h1[v] : h1[v + V / 4];
+      h2[v] = mine + __shfl_xor_sync(0xffffffffu, other, 8);
+    }
+#pragma unroll
+    for (int v = 0; v < V / 4; ++v) {
+      const int idx = base + v, o = wo + TO * (idx / RI), i = t + TI * (idx % RI);
+      if (col_ok && o < N && i < K) __stcg(pw + o * K + i, oldv[v] + h2[v]);
+    }
+#pragma unroll
+    for (int ro = 0; ro < RO; ++ro) {                  // every lane of the warp holds the same GZ rows: lane 0 writes db
+      float b = sb[ro] + __shfl_xor_sync(0xffffffffu, sb[ro], 16);
+      b += __shfl_xor_sync(0xffffffffu, b, 8);
+      const int o = wo + TO * ro;
+      if (lane == 0 && o < N) __stcg(pb + o, oldb[ro] + b);
+    }
+  }
+}
+
 // the same for min(N, K) <= 4: one thread per row w of the wide side contracts it with the (at most four) rows of the
 // thin side over all frames; the thin rows are warp-wide broadcasts
 __device__ __forceinline__ void tr_dw_thin(const float* __restrict__ GZ, const float* __restrict__ A, int N, int K,
@@ -498,6 +584,10 @@ fused_train_kernel(const __grid_constant__ DevPlan p, const __grid_constant__ Tr
         case TR_DW42: tr_dw_layer<4, 2>(GZ, A, N, K, pw, pb, first, tid); break;
         case TR_DW24: tr_dw_layer<2, 4>(GZ, A, N, K, pw, pb, first, tid); break;
         case TR_DW22: tr_dw_layer<2, 2>(GZ, A, N, K, pw, pb, first, tid); break;
+        case TR_DWB88: tr_dw_big<8, 8>(GZ, A, N, K, pw, pb, first, tid); break;
+        case TR_DWB84: tr_dw_big<8, 4>(GZ, A, N, K, pw, pb, first, tid); break;
+        case TR_DWB48: tr_dw_big<4, 8>(GZ, A, N, K, pw, pb, first, tid); break;
+        case TR_DWB44: tr_dw_big<4, 4>(GZ, A, N, K, pw, pb, first, tid); break;
         default: tr_dw_thin(GZ, A, N, K, pw, pb, first, tid); break;
       }
       if (l > 0) {

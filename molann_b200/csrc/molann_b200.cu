@@ -1973,6 +1973,17 @@ TrainChoice choose_train(const MolannPlan* enc, const MolannDecoder* dec, const 
           break;
         }
       }
+      // large tiles over frame quarters when they fill the lanes (6 .. 8 column groups) and all eight warps
+      if (env_int("MOLANN_B200_TRAIN_BIG", 1) != 0) {
+        const int bo[4] = {8, 8, 4, 4}, bi[4] = {8, 4, 8, 4}, bm[4] = {TR_DWB88, TR_DWB84, TR_DWB48, TR_DWB44};
+        for (int c = 0; c < 4; ++c) {
+          const int TO = (N + bo[c] - 1) / bo[c], TI = (K + bi[c] - 1) / bi[c];
+          if (TI >= 6 && TI <= 8 && TO >= 8 && TO % 8 == 0) {
+            lay.dw[l] = bm[c];
+            break;
+          }
+        }
+      }
     }
   }
   off = (off + 15) / 16 * 16;
