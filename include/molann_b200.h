@@ -207,6 +207,19 @@ int molann_b200_train_loss_and_grads(const MolannPlan* encoder, const MolannDeco
 int molann_b200_sgd_apply(float* const* params, const int64_t* numel, int32_t n_params, const float* flat, float lr,
                           void* stream);
 
+/* Data-parallel step without NCCL: one-shot sum-allreduce of `flat_local` (n floats: the result of
+ * molann_b200_train_loss_and_grads on this rank's shard) over NVLink peer memory, fused with the SGD update of this rank's
+ * parameters, in ONE kernel per rank.  `peer_buffers[r]` (r < world, HOST array) is the device address, valid on THIS
+ * device, of rank r's symmetric buffer (CUDA IPC / torch symmetric memory) of molann_b200_allreduce_buffer_bytes(n, world)
+ * bytes, zero-filled before the first step; `state` = 3 uint32 in this rank's device memory, initialised {1, 0, 0}.
+ * Every rank must call it once per step with the same n; the sums are formed in rank order, so all ranks get the same
+ * bits in `flat_global` and in their parameters.  lr == 0 leaves the parameters alone (allreduce only).
+ * Replayable in a CUDA graph (the step counter lives in `state`).  world <= 8. */
+size_t molann_b200_allreduce_buffer_bytes(int64_t n, int32_t world);
+int molann_b200_allreduce_sgd(const float* flat_local, float* flat_global, int64_t n, void* const* peer_buffers,
+                              int32_t rank, int32_t world, uint32_t* state, float* const* params,
+                              const int64_t* numel, int32_t n_params, float lr, void* stream);
+
 /* Tuning / introspection: which kernel family the dispatcher picks for this plan.
  * 0 = general (warp-per-frame geometry + layered GEMMs), 1 = fused small-system kernel. */
 int molann_b200_path_for(const MolannPlan* plan, int want_backward);

@@ -99,6 +99,10 @@ def cabi():
     lib.molann_b200_train_loss_and_grads.argtypes = [P, D, vp, i64, ctypes.c_float, vp, vp, sz, vp]
     lib.molann_b200_sgd_apply.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(i64), ctypes.c_int32, vp, ctypes.c_float,
                                           vp]
+    lib.molann_b200_allreduce_buffer_bytes.restype = sz
+    lib.molann_b200_allreduce_buffer_bytes.argtypes = [i64, ctypes.c_int32]
+    lib.molann_b200_allreduce_sgd.argtypes = [vp, vp, i64, ctypes.POINTER(vp), ctypes.c_int32, ctypes.c_int32, vp,
+                                              ctypes.POINTER(vp), ctypes.POINTER(i64), ctypes.c_int32, ctypes.c_float, vp]
     _cabi = lib
     return lib
 

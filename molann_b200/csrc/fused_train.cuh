@@ -639,4 +639,79 @@ __global__ void train_sgd_kernel(const __grid_constant__ SgdTable tab, const flo
   *q = fmaf(-lr, flat[i], *q);
 }
 
+// ---- data-parallel step: one-shot allreduce over NVLink peer memory fused with the SGD update -----------------------------
+// Every rank holds the flat vector of its shard (gradients + loss).  Instead of an NCCL allreduce followed by the SGD launch,
+// ONE kernel per rank: (1) publish the local vector in this rank's symmetric buffer (slot = step parity), (2) the last CTA to
+// finish signals every peer (release store of the step number into the peer's flag row, over NVLink), (3) every CTA waits
+// for all peers' flags, reads the W published vectors through peer pointers, sums them in RANK ORDER -- every rank computes
+// bit-identical sums, so the replicas never drift -- writes the global vector and applies p -= lr * g.
+// The step number lives in device memory and is advanced by the kernel itself, so a CUDA graph can replay the launch.
+// A rank cannot run two steps ahead of a peer (its step s + 1 needs the peer's step-s + 1 flag, which the peer raises after
+// it has finished reading step s), so two slots are enough.
+constexpr int TR_MAX_PEERS = 8;
+struct PeerTable {
+  float* buf[TR_MAX_PEERS];            // peer r's symmetric buffer: 2 slots of n floats, then the flag row
+  unsigned* flag[TR_MAX_PEERS];        // peer r's flag row: flag[r][q] = last step rank q has published
+  int rank, world;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float ld_peer(const float* p) {          // never from a stale cache line
+  float v;
+  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// state[0] = number of the step this launch performs (starts at 1), state[1] / state[2] = CTA arrival counters.
+// The grid must be co-resident (host: at most one CTA per SM).
+__global__ void __launch_bounds__(256)
+train_allreduce_sgd_kernel(const __grid_constant__ PeerTable peers, const __grid_constant__ SgdTable tab,
+                           const float* __restrict__ flat_local, float* __restrict__ flat_global, int n, int total,
+                           float lr, unsigned* __restrict__ state) {
+  const unsigned step = *reinterpret_cast<volatile unsigned*>(state);
+  const int slot = (int)(step & 1u) * n;
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gstride = gridDim.x * blockDim.x;
+  float* own = peers.buf[peers.rank] + slot;
+  for (int i = gtid; i < n; i += gstride) own[i] = flat_local[i];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (atomicAdd(state + 1, 1u) == gridDim.x - 1) {               // every CTA of this rank has published
+      __threadfence_system();
+      for (int r = 0; r < peers.world; ++r) st_release_sys(peers.flag[r] + peers.rank, step);
+    }
+    for (int r = 0; r < peers.world; ++r)
+      while (ld_acquire_sys(peers.flag[peers.rank] + r) < step) __nanosleep(64);
+  }
+  __syncthreads();
+  for (int i = gtid; i < n; i += gstride) {
+    float sum = 0.f;
+    for (int r = 0; r < peers.world; ++r) sum += ld_peer(peers.buf[r] + slot + i);
+    flat_global[i] = sum;
+    if (i < total && lr != 0.f) {
+      int t = 0;
+      while (t < tab.n - 1 && i >= tab.end[t]) ++t;
+      float* q = tab.ptr[t] + (i - (t ? tab.end[t - 1] : 0));
+      *q = fmaf(-lr, sum, *q);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(state + 2, 1u) == gridDim.x - 1) {               // last CTA out: re-arm for the next launch
+      state[1] = 0u;
+      state[2] = 0u;
+      __threadfence();
+      *reinterpret_cast<volatile unsigned*>(state) = step + 1u;
+    }
+  }
+}
+
 }  // namespace molann

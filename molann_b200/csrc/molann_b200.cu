@@ -2083,3 +2083,57 @@ int molann_b200_sgd_apply(float* const* params, const int64_t* numel, int32_t n_
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// one-shot allreduce over peer memory + SGD (fused_train.cuh)
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+size_t molann_b200_allreduce_buffer_bytes(int64_t n, int32_t world) {
+  if (n <= 0 || world < 1 || world > TR_MAX_PEERS) return 0;
+  return align256((size_t)2 * (size_t)n * 4) + 256;              // two slots, then the flag row (world uint32)
+}
+
+int molann_b200_allreduce_sgd(const float* flat_local, float* flat_global, int64_t n, void* const* peer_buffers,
+                              int32_t rank, int32_t world, uint32_t* state, float* const* params,
+                              const int64_t* numel, int32_t n_params, float lr, void* stream) {
+  if (!flat_local || !flat_global || !peer_buffers || !state) return MOLANN_ERR_NULL;
+  if (n <= 0 || n > (1ll << 28) || world < 1 || world > TR_MAX_PEERS || rank < 0 || rank >= world) return MOLANN_ERR_PLAN;
+  if (n_params < 0 || n_params > 2 * TR_MAXL || (n_params > 0 && (!params || !numel))) {
+    return n_params < 0 || n_params > 2 * TR_MAXL ? MOLANN_ERR_PLAN : MOLANN_ERR_NULL;
+  }
+  if (misaligned4(flat_local) || misaligned4(flat_global) || misaligned4(state)) return MOLANN_ERR_ALIGNMENT;
+  PeerTable pt;
+  std::memset(&pt, 0, sizeof(pt));
+  const size_t flag_off = align256((size_t)2 * (size_t)n * 4);
+  for (int r = 0; r < world; ++r) {
+    if (!peer_buffers[r]) return MOLANN_ERR_NULL;
+    if (reinterpret_cast<uintptr_t>(peer_buffers[r]) & 15u) return MOLANN_ERR_ALIGNMENT;
+    pt.buf[r] = static_cast<float*>(peer_buffers[r]);
+    pt.flag[r] = reinterpret_cast<unsigned*>(static_cast<char*>(peer_buffers[r]) + flag_off);
+  }
+  pt.rank = rank;
+  pt.world = world;
+  SgdTable tab;
+  std::memset(&tab, 0, sizeof(tab));
+  long long total = 0;
+  for (int i = 0; i < n_params; ++i) {
+    if (!params[i]) return MOLANN_ERR_NULL;
+    if (numel[i] < 0) return MOLANN_ERR_PLAN;
+    if (misaligned4(params[i])) return MOLANN_ERR_ALIGNMENT;
+    total += numel[i];
+    if (total > n) return MOLANN_ERR_PLAN;
+    tab.ptr[i] = params[i];
+    tab.end[i] = (int)total;
+  }
+  tab.n = n_params > 0 ? n_params : 1;
+  const DeviceInfo dev = device_info();
+  if (!dev.ok) return MOLANN_ERR_CUDA;
+  long long blocks = (n + 255) / 256;
+  if (blocks > dev.sm_count) blocks = dev.sm_count;              // co-resident: CTAs wait for each other
+  train_allreduce_sgd_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      pt, tab, flat_local, flat_global, (int)n, (int)total, n_params > 0 ? lr : 0.f, state);
+  return post_launch();
+}
+
+}  // extern "C"

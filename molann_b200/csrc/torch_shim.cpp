@@ -648,6 +648,42 @@ void sgd_apply_impl(at::TensorList params, const Tensor& flat, double lr) {
                "sgd_apply");
 }
 
+// one-shot allreduce of the flat vector over peer memory + SGD (include/molann_b200.h: molann_b200_allreduce_sgd).
+// `peer_ptrs[r]` = rank r's symmetric buffer as seen from this device (torch.distributed._symmetric_memory buffer_ptrs).
+Tensor allreduce_sgd_impl(at::TensorList params, const Tensor& flat_local, at::IntArrayRef peer_ptrs, int64_t rank,
+                          const Tensor& state, double lr) {
+  TORCH_CHECK(flat_local.is_cuda() && flat_local.scalar_type() == at::kFloat && flat_local.is_contiguous(),
+              "molann_b200::allreduce_sgd_: the flat vector must be a contiguous float32 CUDA tensor");
+  TORCH_CHECK(state.is_cuda() && state.device() == flat_local.device() && state.scalar_type() == at::kInt &&
+                  state.numel() >= 3 && state.is_contiguous(),
+              "molann_b200::allreduce_sgd_: state must be an int32[3] tensor on the vector's device");
+  TORCH_CHECK(!peer_ptrs.empty() && peer_ptrs.size() <= 8, "molann_b200::allreduce_sgd_: 1 .. 8 peers");
+  c10::cuda::CUDAGuard guard(flat_local.device());
+  NvtxRange nvtx("molann_b200::allreduce_sgd_");
+  std::vector<float*> ptrs;
+  std::vector<int64_t> numel;
+  for (const Tensor& p : params) {
+    TORCH_CHECK(p.device() == flat_local.device() && p.scalar_type() == at::kFloat && p.is_contiguous(),
+                "molann_b200::allreduce_sgd_: parameters must be contiguous float32 tensors on the vector's device");
+    ptrs.push_back(p.data_ptr<float>());
+    numel.push_back(p.numel());
+  }
+  std::vector<void*> bufs;
+  for (int64_t a : peer_ptrs) bufs.push_back(reinterpret_cast<void*>(static_cast<uintptr_t>(a)));
+  Tensor out = at::empty_like(flat_local);
+  check_status(molann_b200_allreduce_sgd(flat_local.data_ptr<float>(), out.data_ptr<float>(), flat_local.numel(),
+                                         bufs.data(), static_cast<int32_t>(rank), static_cast<int32_t>(bufs.size()),
+                                         reinterpret_cast<uint32_t*>(state.data_ptr<int32_t>()),
+                                         ptrs.empty() ? nullptr : ptrs.data(), numel.empty() ? nullptr : numel.data(),
+                                         static_cast<int32_t>(ptrs.size()), static_cast<float>(lr), cur_stream()),
+               "allreduce_sgd");
+  return out;
+}
+
+int64_t allreduce_buffer_bytes(int64_t n, int64_t world) {
+  return static_cast<int64_t>(molann_b200_allreduce_buffer_bytes(n, static_cast<int32_t>(world)));
+}
+
 int64_t launch_count() { return molann_b200_launch_count(); }
 
 }  // namespace
@@ -668,6 +704,9 @@ TORCH_LIBRARY(molann_b200, m) {
         "bool use_angle_value, Tensor[] enc_params, int enc_act, Tensor[] dec_params, int dec_act, float loss_scale) "
         "-> Tensor");
   m.def("sgd_apply_(Tensor(a!)[] params, Tensor flat, float lr) -> ()");
+  m.def("allreduce_sgd_(Tensor(a!)[] params, Tensor flat_local, int[] peer_ptrs, int rank, Tensor(b!) state, float lr) "
+        "-> Tensor");
+  m.def("allreduce_buffer_bytes(int n, int world) -> int", &allreduce_buffer_bytes);
   m.def("launch_count() -> int", &launch_count);
 }
 
@@ -681,6 +720,7 @@ TORCH_LIBRARY_IMPL(molann_b200, CUDA, m) {
   m.impl("train_eligible", &train_eligible_impl);
   m.impl("train_loss_and_grads", &train_loss_and_grads_impl);
   m.impl("sgd_apply_", &sgd_apply_impl);
+  m.impl("allreduce_sgd_", &allreduce_sgd_impl);
 }
 
 TORCH_LIBRARY_IMPL(molann_b200, Autograd, m) {

@@ -44,6 +44,10 @@ class AutoencoderStep(object):
         self.group = group
         self._fused_args = None
         self._fused_checked = False
+        self._peer = None
+        self._peer_checked = False
+        self._peer_error = None
+        self._updated = False
 
     # ---- the fused training kernel ---------------------------------------------------------------------------------
     def _fused_call_args(self, x_local):
@@ -81,14 +85,54 @@ class AutoencoderStep(object):
         self._fused_args = args
         return args
 
-    def _fused_loss_and_grads(self, x_local, args, n_global):
+    # ---- the collective of the fused path: one-shot allreduce over NVLink peer memory, fused with the SGD update ------
+    def _peer_setup(self, flat):
+        """Symmetric buffers of all ranks of the group (torch symmetric memory: CUDA IPC / fabric handles), or None --
+        then the flat vector goes through NCCL.  ``MOLANN_B200_TRAIN_P2P=0`` forces NCCL."""
+        if self._peer_checked:
+            return self._peer
+        self._peer_checked = True
+        self._peer = None
+        if os.environ.get("MOLANN_B200_TRAIN_P2P", "1") == "0":
+            return None
+        world = dist.get_world_size(self.group)
+        ok = torch.ones(1, device=flat.device)
+        try:
+            if world > 8 or dist.get_backend(self.group) != "nccl":
+                raise RuntimeError("one node, NCCL group, at most 8 ranks")
+            import torch.distributed._symmetric_memory as symm
+            nbytes = torch.ops.molann_b200.allreduce_buffer_bytes(flat.numel(), world)
+            buf = symm.empty(nbytes // 4, dtype=torch.float32, device=flat.device)
+            buf.zero_()
+            hdl = symm.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
+            ptrs = [int(a) for a in hdl.buffer_ptrs]
+            state = torch.tensor([1, 0, 0], dtype=torch.int32, device=flat.device)
+            peer = {"buf": buf, "hdl": hdl, "ptrs": ptrs, "rank": dist.get_rank(self.group), "state": state}
+        except Exception as exc:  # noqa: BLE001 -- no peer access on this stack: NCCL carries the vector
+            self._peer_error = repr(exc)
+            peer = None
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)      # all ranks take the same route
+        torch.cuda.synchronize()                                        # every buffer is zeroed before anyone signals
+        dist.barrier(group=self.group)
+        self._peer = peer if bool(ok.item() > 0.5) else None
+        return self._peer
+
+    def _fused_loss_and_grads(self, x_local, args, n_global, lr=0.0):
         geo0, geo1, entries, d_feat, use_angle, enc_params, enc_act, dec_params, dec_act = args
+        self._updated = False
         with torch.no_grad():
             flat = torch.ops.molann_b200.train_loss_and_grads(
                 x_local, geo0, geo1, entries, d_feat, use_angle, [q.detach() for q in enc_params], enc_act,
                 [q.detach() for q in dec_params], dec_act, 1.0 / (float(n_global) * float(d_feat)))
             if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
-                dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+                peer = self._peer_setup(flat)
+                if peer is not None:          # sum over ranks (in rank order) and, when lr != 0, p -= lr * g: one kernel
+                    flat = torch.ops.molann_b200.allreduce_sgd_([q.detach() for q in self.params], flat, peer["ptrs"],
+                                                                peer["rank"], peer["state"], lr)
+                    self._updated = lr != 0.0
+                else:
+                    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
             off = 0
             for q in self.params:               # gradients are views of the flat buffer: nothing is copied
                 n = q.numel()
@@ -97,13 +141,14 @@ class AutoencoderStep(object):
         self._flat = flat
         return flat[off:off + 1]
 
-    def loss_and_grads(self, x_local: torch.Tensor) -> torch.Tensor:
+    def loss_and_grads(self, x_local: torch.Tensor, _lr: float = 0.0) -> torch.Tensor:
         """Forward + backward on this rank's shard, then the single flat allreduce.  Returns the global loss."""
         n_global = self.global_frames if self.global_frames is not None else x_local.shape[0]
         self._flat = None
+        self._updated = False
         fused = self._fused_call_args(x_local)
         if fused is not None:
-            return self._fused_loss_and_grads(x_local, fused, n_global)
+            return self._fused_loss_and_grads(x_local, fused, n_global, _lr)
         for p in self.params:
             p.grad = None
         with torch.no_grad():
@@ -115,8 +160,10 @@ class AutoencoderStep(object):
         return total if total is not None else loss.detach().reshape(1)
 
     def step(self, x_local: torch.Tensor) -> torch.Tensor:
-        loss = self.loss_and_grads(x_local)
+        loss = self.loss_and_grads(x_local, self.lr)
         with torch.no_grad():
+            if self._updated:                   # the allreduce kernel already applied p -= lr * g
+                return loss
             if self._flat is not None:          # fused path: one launch over the flat gradient
                 torch.ops.molann_b200.sgd_apply_([q.detach() for q in self.params], self._flat, self.lr)
                 return loss

@@ -156,3 +156,19 @@ def test_autoencoder_step_fused_and_composed_agree(monkeypatch):
     tr = AutoencoderStep(enc.cuda(), dec.cuda(), lr=1e-3)
     l0 = float(tr.step(S.make_frames(small, 256, seed=4).cuda()))
     assert tr._fused_args is None and l0 > 0
+
+
+def test_two_gpu_peer_memory_allreduce_and_sgd():
+    """The collective of the fused step (one-shot allreduce over NVLink peer memory + SGD in one kernel,
+    molann_b200_allreduce_sgd) on two ranks: equals the full-batch gradient, trains like the NCCL route, keeps the
+    replicas bit-identical, replays as a CUDA graph (tests/cuda/train_p2p_check.py)."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    here = os.path.dirname(os.path.abspath(__file__))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29533", os.path.join(here, "cuda", "train_p2p_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0 and "P2P_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
