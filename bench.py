@@ -418,6 +418,9 @@ def run_training(args, rank, local_rank, world):
                              % (value * 74e3 / world / 1e12)},
         "train_path": ("fused_train_kernel (one kernel per step + plane reduction + SGD launch)"
                        if trainer._fused_args else "composed (fused encoder kernels + library decoder)"),
+        "collective": ("none (1 GPU)" if world == 1 else
+                       "one-shot allreduce over NVLink peer memory fused with SGD (train_allreduce_sgd_kernel)"
+                       if getattr(trainer, "_peer", None) is not None else "NCCL allreduce of the flat gradient"),
         "gpu_launches": int(launches), "allreduce_ms": ar_ms, "final_loss": float(loss), "clocks": clocks,
         "cuda_graph": {"used": graphed, "eager_ms_per_step": ms_eager / K,
                        "note": "value is the graph replay when used (one launch per step replays gpu_launches / steps "

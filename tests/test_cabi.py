@@ -156,3 +156,22 @@ def test_training_entry_points_validate_on_host():
     assert lib.molann_b200_sgd_apply(None, numel, 2, 0x3000, ctypes.c_float(0.1), None) == 1
     assert lib.molann_b200_sgd_apply(ptrs, numel, 99, 0x3000, ctypes.c_float(0.1), None) == 2
     assert lib.molann_b200_sgd_apply(ptrs, numel, 2, 0x3000, ctypes.c_float(0.1), None) == 5
+
+
+def test_allreduce_sgd_entry_point_validates_on_host():
+    """molann_b200_allreduce_sgd (include/molann_b200.h): buffer sizing and argument checks need no GPU."""
+    lib = _lib.cabi()
+    assert lib.molann_b200_allreduce_buffer_bytes(12577, 8) == (2 * 12577 * 4 + 255) // 256 * 256 + 256
+    assert lib.molann_b200_allreduce_buffer_bytes(12577, 9) == 0 and lib.molann_b200_allreduce_buffer_bytes(0, 2) == 0
+    bufs = (ctypes.c_void_p * 2)(0x100000, 0x200000)
+    ptrs = (ctypes.c_void_p * 1)(0x1000)
+    numel = (ctypes.c_int64 * 1)(16)
+    call = lib.molann_b200_allreduce_sgd
+    assert call(0x4000, 0x5000, 17, bufs, 0, 2, 0x6000, ptrs, numel, 1, ctypes.c_float(0.1), None) == 5    # no device
+    assert call(None, 0x5000, 17, bufs, 0, 2, 0x6000, ptrs, numel, 1, ctypes.c_float(0.1), None) == 1
+    assert call(0x4000, 0x5000, 17, bufs, 2, 2, 0x6000, ptrs, numel, 1, ctypes.c_float(0.1), None) == 2    # rank >= world
+    assert call(0x4000, 0x5000, 17, bufs, 0, 9, 0x6000, ptrs, numel, 1, ctypes.c_float(0.1), None) == 2
+    assert call(0x4000, 0x5000, 8, bufs, 0, 2, 0x6000, ptrs, numel, 1, ctypes.c_float(0.1), None) == 2     # params > vector
+    assert call(0x4002, 0x5000, 17, bufs, 0, 2, 0x6000, ptrs, numel, 1, ctypes.c_float(0.1), None) == 4
+    bad = (ctypes.c_void_p * 2)(0x100000, None)
+    assert call(0x4000, 0x5000, 17, bad, 0, 2, 0x6000, ptrs, numel, 1, ctypes.c_float(0.1), None) == 1
