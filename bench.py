@@ -893,7 +893,8 @@ def main():
                             "ms_per_step": c4["ms_per_step"], "allreduce_ms": c4["allreduce_ms"],
                             "gpu_launches": c4["gpu_launches"], "cuda_graph": c4["cuda_graph"]["used"],
                             "e2e": c4["e2e"], "final_loss": c4["final_loss"], "workload": c4["config"]["workload"],
-                            "cpu_baseline": c4.get("cpu_baseline")}
+                            "cpu_baseline": c4.get("cpu_baseline"), "train_path": c4.get("train_path"),
+                            "collective": c4.get("collective"), "roofline": c4.get("roofline")}
         if world == 1:
             others["latency_C2"] = latency_probe(dd)
     if rank == 0:
