@@ -416,6 +416,10 @@ def run_training(args, rank, local_rank, world):
                      "note": "per GPU, algorithmic 12*n_inp bytes per frame; the step is FMA / shared-memory bound "
                              "(74 kFLOP per frame incl. weight gradients: %.1f TFLOP/s fp32 per GPU), see DESIGN.md 3.8"
                              % (value * 74e3 / world / 1e12)},
+        "fp32": {"achieved_tflops": value * 74e3 / world / 1e12, "peak_tflops": 148 * 128 * 2 * 1.965e9 / 1e12,
+                 "frac": (value * 74e3 / world / 1e12) / (148 * 128 * 2 * 1.965e9 / 1e12),
+                 "note": "the step is bound by FP32 FMA work, not HBM: 74 kFLOP per frame against 148 SMs x 128 lanes x 2 "
+                         "x 1.965 GHz; profiles/r5_train_ab.txt, DESIGN.md 3.8"},
         "train_path": ("fused_train_kernel (one kernel per step + plane reduction + SGD launch)"
                        if trainer._fused_args else "composed (fused encoder kernels + library decoder)"),
         "collective": ("none (1 GPU)" if world == 1 else
