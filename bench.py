@@ -381,14 +381,22 @@ def run_training(args, rank, local_rank, world):
     xh = x.cpu().pin_memory()
     ke = max(3, min(K, 10))
     run = trainer.replay if graphed else (lambda: trainer.step(x))
+    if trainer._fused_args and int(os.environ.get("MOLANN_BENCH_TRAIN_PIPE", "1")):
+        # the shard streams in pieces while the fused kernel works on the previous piece (AutoencoderStep.step_from_host)
+        def e2e_step():
+            return float(trainer.step_from_host(xh, chunks=int(os.environ.get("MOLANN_BENCH_TRAIN_CHUNKS", "16"))))
+        e2e_api = "molann_b200.train.AutoencoderStep.step_from_host(pinned shard); float(loss)"
+    else:
+        def e2e_step():
+            x.copy_(xh, non_blocking=True)
+            return float(run())
+        e2e_api = "x.copy_(pinned shard); molann_b200.train.AutoencoderStep.step(x); float(loss)"
     for _ in range(2):
-        x.copy_(xh, non_blocking=True)
-        float(run())
+        e2e_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(ke):
-        x.copy_(xh, non_blocking=True)
-        last = float(run())
+        last = e2e_step()
     torch.cuda.synchronize()
     ms_e = max_over_ranks(1e3 * (time.perf_counter() - t0))
     clocks = sampler.summary()
@@ -432,7 +440,7 @@ def run_training(args, rank, local_rank, world):
                        "capture_error": getattr(trainer, "_capture_error", None)},
         "e2e": {"value": n_global * ke / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": 4, "steps": ke, "ms_per_step": ms_e / ke, "last_loss": last,
-                "api": "x.copy_(pinned shard); molann_b200.train.AutoencoderStep.step(x); float(loss)"},
+                "api": e2e_api},
     }
     if world == 1 and not args.no_cpu_baseline:
         rate, kind, where = c4_cpu_step_rate(1 << 16, 3)

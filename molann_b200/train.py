@@ -125,6 +125,12 @@ class AutoencoderStep(object):
             flat = torch.ops.molann_b200.train_loss_and_grads(
                 x_local, geo0, geo1, entries, d_feat, use_angle, [q.detach() for q in enc_params], enc_act,
                 [q.detach() for q in dec_params], dec_act, 1.0 / (float(n_global) * float(d_feat)))
+        return self._finish_flat(flat, lr)
+
+    def _finish_flat(self, flat, lr):
+        """The collective over the ranks' flat vectors (+ the SGD update when the peer-memory kernel runs and lr != 0);
+        every ``p.grad`` becomes a view of the global vector.  Returns the global loss."""
+        with torch.no_grad():
             if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
                 peer = self._peer_setup(flat)
                 if peer is not None:          # sum over ranks (in rank order) and, when lr != 0, p -= lr * g: one kernel
@@ -158,6 +164,55 @@ class AutoencoderStep(object):
         loss.backward()
         total = allreduce_flat_grads(self.params, group=self.group, extra=loss.detach().reshape(1))
         return total if total is not None else loss.detach().reshape(1)
+
+    def step_from_host(self, x_host: torch.Tensor, chunks: int = 8) -> torch.Tensor:
+        """One SGD step on a shard that lives in (pinned) HOST memory, fused path only: the shard streams to the device
+        in ``chunks`` pieces on a copy stream while the fused training kernel works on the previous piece -- the flat
+        vectors of the pieces simply add up, because ``loss_scale`` is that of the global batch -- then the collective
+        and the update as in :meth:`step`.  Returns the global loss (device tensor)."""
+        L = x_host.shape[0]
+        n_global = self.global_frames if self.global_frames is not None else L
+        dev = self.params[0].device
+        per = max(128, -(-L // max(1, chunks)))
+        per = -(-per // 128) * 128                              # whole 128-frame tiles per piece
+        if getattr(self, "_stage", None) is None or self._stage[0].shape[0] < per or self._stage[0].shape[1:] != x_host.shape[1:]:
+            self._stage = [torch.empty((per,) + tuple(x_host.shape[1:]), dtype=torch.float32, device=dev) for _ in range(2)]
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        main, copy = torch.cuda.current_stream(dev), self._copy_stream
+        fused = self._fused_call_args(self._stage[0])
+        if fused is None:
+            raise RuntimeError("molann_b200: step_from_host needs the fused training kernel (see train_eligible); "
+                               "copy the shard to the device and call step() instead")
+        geo0, geo1, entries, d_feat, use_angle, enc_params, enc_act, dec_params, dec_act = fused
+        scale = 1.0 / (float(n_global) * float(d_feat))
+        self._flat, self._updated = None, False
+        free = [None, None]
+        flat = None
+        copy.wait_stream(main)
+        with torch.no_grad():
+            for i, s in enumerate(range(0, L, per)):
+                e = min(L, s + per)
+                buf = self._stage[i % 2]
+                with torch.cuda.stream(copy):
+                    if free[i % 2] is not None:
+                        copy.wait_event(free[i % 2])            # the kernel that read this buffer two pieces ago is done
+                    buf[:e - s].copy_(x_host[s:e], non_blocking=True)
+                    ready = torch.cuda.Event()
+                    ready.record(copy)
+                main.wait_event(ready)
+                part = torch.ops.molann_b200.train_loss_and_grads(
+                    buf[:e - s], geo0, geo1, entries, d_feat, use_angle, [q.detach() for q in enc_params], enc_act,
+                    [q.detach() for q in dec_params], dec_act, scale)
+                free[i % 2] = torch.cuda.Event()
+                free[i % 2].record(main)
+                flat = part if flat is None else flat.add_(part)
+            if flat is None:
+                flat = torch.zeros(sum(q.numel() for q in self.params) + 1, device=dev)
+        loss = self._finish_flat(flat, self.lr)
+        with torch.no_grad():
+            if not self._updated:
+                torch.ops.molann_b200.sgd_apply_([q.detach() for q in self.params], self._flat, self.lr)
+        return loss
 
     def step(self, x_local: torch.Tensor) -> torch.Tensor:
         loss = self.loss_and_grads(x_local, self.lr)

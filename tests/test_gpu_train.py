@@ -172,3 +172,26 @@ def test_two_gpu_peer_memory_allreduce_and_sgd():
            "127.0.0.1", "--master-port", "29533", os.path.join(here, "cuda", "train_p2p_check.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
     assert out.returncode == 0 and "P2P_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+
+
+def test_step_from_host_equals_step_on_device():
+    """AutoencoderStep.step_from_host streams the pinned shard in pieces under the kernel; the pieces' flat vectors add
+    up to the one-launch result (to fp32 summation order), ragged last piece included."""
+    from molann_b200.train import AutoencoderStep
+    spec = S.get_spec("C2")
+    L = 5 * 1024 + 333
+    xh = S.make_frames(spec, L, seed=21).pin_memory()
+    out = {}
+    for mode in ("device", "host"):
+        enc, dec = make_pair(spec, [64, 64])
+        tr = AutoencoderStep(enc.cuda(), dec.cuda(), lr=0.05, global_frames=L)
+        losses = []
+        for _ in range(3):
+            losses.append(float(tr.step(xh.cuda()) if mode == "device" else tr.step_from_host(xh, chunks=3)))
+        torch.cuda.synchronize()
+        out[mode] = (losses, [p.detach().clone() for p in tr.params])
+    for a, b in zip(out["host"][0], out["device"][0]):
+        assert abs(a - b) < 1e-5 * abs(b), out
+    assert out["device"][0][-1] < out["device"][0][0]
+    for p, q in zip(out["host"][1], out["device"][1]):
+        assert float((p - q).abs().max()) < 1e-5 * float(q.abs().max())
