@@ -613,13 +613,24 @@ fused_train_kernel(const __grid_constant__ DevPlan p, const __grid_constant__ Tr
   }
 }
 
-// flat[p] = sum over the CTA planes, in plane order (deterministic)
-__global__ void train_reduce_kernel(const float* __restrict__ planes, int n_planes, int n, float* __restrict__ flat) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+// flat[p] = sum over the CTA planes in a fixed order (deterministic): block (64, 8), eight interleaved groups of planes per
+// entry, then the eight partial sums pairwise
+constexpr int TR_RED_X = 64, TR_RED_Y = 8;
+__global__ void __launch_bounds__(TR_RED_X * TR_RED_Y)
+train_reduce_kernel(const float* __restrict__ planes, int n_planes, int n, float* __restrict__ flat) {
+  __shared__ float part[TR_RED_Y][TR_RED_X];
+  const int i = blockIdx.x * TR_RED_X + threadIdx.x, g = threadIdx.y;
   float s = 0.f;
-  for (int c = 0; c < n_planes; ++c) s += __ldcg(planes + (size_t)c * n + i);
-  flat[i] = s;
+  if (i < n) {
+#pragma unroll 4
+    for (int c = g; c < n_planes; c += TR_RED_Y) s += __ldcg(planes + (size_t)c * n + i);
+  }
+  part[g][threadIdx.x] = s;
+  __syncthreads();
+  if (g == 0 && i < n) {
+    const int x = threadIdx.x;
+    flat[i] = ((part[0][x] + part[1][x]) + (part[2][x] + part[3][x])) + ((part[4][x] + part[5][x]) + (part[6][x] + part[7][x]));
+  }
 }
 
 // plain SGD over up to 2 TR_MAXL parameter tensors laid out like the flat gradient: p -= lr * g

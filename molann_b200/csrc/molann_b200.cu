@@ -2054,7 +2054,8 @@ int molann_b200_train_loss_and_grads(const MolannPlan* encoder, const MolannDeco
                                                                loss_scale, planes, use_tma);
   s = post_launch();
   if (s) return s;
-  train_reduce_kernel<<<(unsigned)((n_flat + 255) / 256), 256, 0, st>>>(planes, grid, (int)n_flat, flat);
+  train_reduce_kernel<<<(unsigned)((n_flat + TR_RED_X - 1) / TR_RED_X), dim3(TR_RED_X, TR_RED_Y), 0, st>>>(planes, grid, (int)n_flat,
+                                                                                                          flat);
   return post_launch();
 }
 
