@@ -98,7 +98,7 @@ class AutoencoderStep(object):
         world = dist.get_world_size(self.group)
         ok = torch.ones(1, device=flat.device)
         try:
-            if world > 8 or dist.get_backend(self.group) != "nccl":
+            if world > 8 or "nccl" not in str(dist.get_backend(self.group)):
                 raise RuntimeError("one node, NCCL group, at most 8 ranks")
             import torch.distributed._symmetric_memory as symm
             nbytes = torch.ops.molann_b200.allreduce_buffer_bytes(flat.numel(), world)
