@@ -7,10 +7,13 @@
 //   TMA bulk stage-in of x -> Kabsch + feature program (two lanes per frame) -> every Linear layer of encoder and
 //   decoder forward (register-tiled FFMA, activations resident in shared memory as [width][frame] rows) -> residual,
 //   loss and its cotangent -> for each layer, last to first: the weight / bias gradient of the layer (frames are the
-//   contraction axis; each thread owns a 4 x 4 block of dW) and the backward to the layer input, in place.
+//   contraction axis; a thread owns an 8 x 8 ... 4 x 4 block of dW, see the work shapes below) and the backward to the
+//   layer input, in place.
 // Parameter gradients accumulate in a per-CTA plane of the workspace (thread-private read-modify-write, L2 resident,
 // no atomics: the result is deterministic); `train_reduce_kernel` sums the planes in a fixed order.  HBM traffic is the
-// algorithmic 12 n bytes per frame; the step is FFMA-bound (about 74 kFLOP per C4 frame).
+// algorithmic 12 n bytes per frame; the step is bound by FP32 FMA work fed from shared memory (about 74 kFLOP per C4
+// frame; DESIGN.md 3.8, profiles/r5_train_ab.txt).  Across ranks `train_allreduce_sgd_kernel` (end of this file) sums the
+// flat vectors over NVLink peer memory and applies the SGD update in the same pass.
 //
 // Shared-memory rows have a stride of 132 floats: the dW contraction reads four rows per thread at the same frame
 // quad, and with stride = 4 (mod 32) banks, rows r .. r+7 hit eight different bank quads.

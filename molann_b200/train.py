@@ -11,9 +11,12 @@ features + MLP kernels, parameter gradients from the C ABI's ``molann_b200_backw
 
 When encoder and decoder are both ``create_sequential_nn``-style stacks small enough for the SM (C4 is), the whole
 step is the fused training kernel instead (``molann_b200::train_loss_and_grads``, csrc/fused_train.cuh): forward of
-encoder and decoder, loss, every parameter gradient and the loss in ONE kernel plus a fixed-order reduction, the flat
-result allreduced as it is, and the SGD update in one more launch (``molann_b200::sgd_apply_``) -- no library GEMM,
-no autograd graph.  ``MOLANN_B200_TRAIN_FUSED=0`` keeps the composed path.
+encoder and decoder, loss, every parameter gradient and the loss in ONE kernel plus a fixed-order reduction, and the
+SGD update in one more launch (``molann_b200::sgd_apply_``) -- no library GEMM, no autograd graph.  With several ranks
+the flat result is summed over NVLink peer memory and applied by ONE kernel per rank (``molann_b200::allreduce_sgd_``:
+one-shot allreduce in rank order, bit-identical replicas, no NCCL call; ``MOLANN_B200_TRAIN_P2P=0`` uses NCCL +
+``sgd_apply_``).  ``step_from_host`` streams a pinned host shard in pieces under the kernel.
+``MOLANN_B200_TRAIN_FUSED=0`` keeps the composed path.
 """
 import os
 from typing import Optional
