@@ -906,7 +906,7 @@ def main():
                             "gpu_launches": c4["gpu_launches"], "cuda_graph": c4["cuda_graph"]["used"],
                             "e2e": c4["e2e"], "final_loss": c4["final_loss"], "workload": c4["config"]["workload"],
                             "cpu_baseline": c4.get("cpu_baseline"), "train_path": c4.get("train_path"),
-                            "collective": c4.get("collective"), "roofline": c4.get("roofline")}
+                            "collective": c4.get("collective"), "roofline": c4.get("roofline"), "fp32": c4.get("fp32")}
         if world == 1:
             others["latency_C2"] = latency_probe(dd)
     if rank == 0:
